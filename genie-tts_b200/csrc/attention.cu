@@ -1,0 +1,242 @@
+// fp32 attention kernels.
+//  * attention_kernel: tiled online-softmax attention over ragged segments, with
+//    the T2S prefill mask (first_stage#[26-56]) or the VITS windowed
+//    relative-position terms (vits#[363-755], restated as a band |i-j|<=w).
+//  * decode_attention_kernel: one query per (utterance, head) streamed over the
+//    head-major fp32 KV cache (stage#[63-96] without the per-step Concat).
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace genie {
+namespace {
+
+constexpr int QT = 16;   // query rows per CTA (4 per warp)
+constexpr int KT = 32;   // keys per tile (one per lane)
+
+template <int D>
+__global__ void __launch_bounds__(128) attention_kernel(Attn p) {
+  constexpr int DC = D / 32;   // value columns per lane
+  __shared__ float Qs[QT][D];
+  __shared__ float Ks[KT][D + 1];
+  __shared__ float Vs[KT][D];
+  __shared__ float QRel[QT][16];
+  __shared__ float RelV[9][D];
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int qs = p.q_off ? p.q_off[b] : 0;
+  const int Tq = p.q_off ? p.q_off[b + 1] - qs : p.max_q;
+  const int ks = p.kv_off ? p.kv_off[b] : 0;
+  const int Tk = p.kv_off ? p.kv_off[b + 1] - ks : p.max_q;
+  const int q0 = blockIdx.x * QT;
+  if (q0 >= Tq) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = p.window;
+  const bool rel = p.rel_k != nullptr;
+  const int lx = (p.mask_mode == 1) ? p.lx[b] : 0;
+
+  for (int i = tid; i < QT * D; i += 128) {
+    int r = i / D, e = i % D;
+    float v = 0.f;
+    if (q0 + r < Tq) v = p.q[(long long)(qs + q0 + r) * p.ldq + h * D + e] * p.scale;
+    Qs[r][e] = v;
+  }
+  if (rel)
+    for (int i = tid; i < (2 * W + 1) * D; i += 128) RelV[i / D][i % D] = p.rel_v[i];
+  __syncthreads();
+  if (rel) {
+    // QRel[r][i] = (q_r * scale) . rel_k[i]
+    for (int i = tid; i < QT * (2 * W + 1); i += 128) {
+      int r = i / (2 * W + 1), c = i % (2 * W + 1);
+      float s = 0.f;
+      for (int e = 0; e < D; ++e) s = fmaf(Qs[r][e], p.rel_k[c * D + e], s);
+      QRel[r][c] = s;
+    }
+  }
+  __syncthreads();
+
+  float m_run[4], l_run[4], acc[4][DC];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    m_run[r] = -CUDART_INF_F; l_run[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < DC; ++c) acc[r][c] = 0.f;
+  }
+  const int qr0 = warp * 4;   // this warp's first row within the CTA tile
+
+  // keys beyond the last row this CTA can see are skipped for the causal mask
+  int k_end = Tk;
+  if (p.mask_mode == 1) {
+    int last_q = min(q0 + QT, Tq) - 1;
+    k_end = (last_q < lx) ? lx : last_q + 1;
+  }
+  for (int k0 = 0; k0 < k_end; k0 += KT) {
+    for (int i = tid; i < KT * D; i += 128) {
+      int j = i / D, e = i % D;
+      float kv = 0.f, vv = 0.f;
+      if (k0 + j < Tk) {
+        long long row = (long long)(ks + k0 + j);
+        kv = p.k[row * p.ldk + h * D + e];
+        vv = p.v[row * p.ldv + h * D + e];
+      }
+      Ks[j][e] = kv; Vs[j][e] = vv;
+    }
+    __syncthreads();
+    const int kj = k0 + lane;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int e = 0; e < D; ++e) {
+      float kv = Ks[lane][e];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] = fmaf(Qs[qr0 + r][e], kv, s[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int qi = q0 + qr0 + r;
+      bool ok = (kj < Tk) && (qi < Tq);
+      if (p.mask_mode == 1) ok = ok && ((qi < lx) ? (kj < lx) : (kj <= qi));
+      if (rel) {
+        int idx = kj - qi + W;
+        if (idx >= 0 && idx <= 2 * W) s[r] += QRel[qr0 + r][idx];
+      }
+      float sv = ok ? s[r] : -CUDART_INF_F;
+      float tmax = sv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      float m_new = fmaxf(m_run[r], tmax);
+      float pj = 0.f, corr = 1.f;
+      if (m_new != -CUDART_INF_F) {
+        pj = ok ? expf(sv - m_new) : 0.f;
+        corr = (m_run[r] == -CUDART_INF_F) ? 0.f : expf(m_run[r] - m_new);
+      }
+      float psum = pj;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      l_run[r] = l_run[r] * corr + psum;
+      m_run[r] = m_new;
+#pragma unroll
+      for (int c = 0; c < DC; ++c) acc[r][c] *= corr;
+      s[r] = pj;
+    }
+    // P.V (+ relative-position values inside the band)
+    for (int j = 0; j < KT; ++j) {
+      float vv[DC];
+#pragma unroll
+      for (int c = 0; c < DC; ++c) vv[c] = Vs[j][lane + 32 * c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float pj = __shfl_sync(0xffffffffu, s[r], j);
+#pragma unroll
+        for (int c = 0; c < DC; ++c) acc[r][c] = fmaf(pj, vv[c], acc[r][c]);
+        if (rel) {
+          int idx = (k0 + j) - (q0 + qr0 + r) + W;
+          if (idx >= 0 && idx <= 2 * W) {
+#pragma unroll
+            for (int c = 0; c < DC; ++c) acc[r][c] = fmaf(pj, RelV[idx][lane + 32 * c], acc[r][c]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int qi = q0 + qr0 + r;
+    if (qi >= Tq) continue;
+    float inv = 1.f / l_run[r];
+#pragma unroll
+    for (int c = 0; c < DC; ++c)
+      p.o[(long long)(qs + qi) * p.ldo + h * D + lane + 32 * c] = acc[r][c] * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Decode attention: grid (H=16, B); 128 threads.  8 lanes x float4 cover one
+// 32-float key row, so each warp-load touches 4 keys = 512 contiguous bytes.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) decode_attention_kernel(
+    const float* __restrict__ q, float* __restrict__ o, const float* __restrict__ kv_base,
+    long long utt_stride, long long layer_off, long long v_off, const int* __restrict__ kv_len,
+    const int* __restrict__ active, int cap, float scale, int t_add) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  if (active && !active[b]) return;
+  const int T = kv_len[b] + t_add;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  const float* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
+  const float* V = K + v_off;
+
+  float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * 512 + h * 32 + sub * 4);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+
+  float m = -CUDART_INF_F, l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int iters = (T + 15) / 16;
+  for (int it = 0; it < iters; ++it) {
+    const int j = it * 16 + warp * 4 + grp;
+    const bool ok = j < T;
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
+    if (ok) {
+      k4 = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
+      v4 = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+    }
+    float s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok) {
+      float m_new = fmaxf(m, s);
+      float c = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+      float pj = expf(s - m_new);
+      l = l * c + pj;
+      acc.x = acc.x * c + pj * v4.x; acc.y = acc.y * c + pj * v4.y;
+      acc.z = acc.z * c + pj * v4.z; acc.w = acc.w * c + pj * v4.w;
+      m = m_new;
+    }
+  }
+  __shared__ float sm_m[16], sm_l[16], sm_acc[16][32];
+  const int g = warp * 4 + grp;
+  if (sub == 0) { sm_m[g] = m; sm_l[g] = l; }
+  sm_acc[g][sub * 4 + 0] = acc.x; sm_acc[g][sub * 4 + 1] = acc.y;
+  sm_acc[g][sub * 4 + 2] = acc.z; sm_acc[g][sub * 4 + 3] = acc.w;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) M = fmaxf(M, sm_m[i]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float wgt = (sm_m[i] == -CUDART_INF_F) ? 0.f : expf(sm_m[i] - M);
+      num = fmaf(sm_acc[i][lane], wgt, num);
+      den = fmaf(sm_l[i], wgt, den);
+    }
+    o[(long long)b * 512 + h * 32 + lane] = num / den;
+  }
+}
+
+}  // namespace
+
+void launch_attention(const Attn& p, cudaStream_t s) {
+  if (p.B <= 0 || p.max_q <= 0) return;
+  GENIE_CHECK(p.window <= 4, "attention: window > 4 unsupported");
+  dim3 grid((p.max_q + QT - 1) / QT, p.H, p.B);
+  switch (p.d) {
+    case 32: attention_kernel<32><<<grid, 128, 0, s>>>(p); break;
+    case 64: attention_kernel<64><<<grid, 128, 0, s>>>(p); break;
+    case 96: attention_kernel<96><<<grid, 128, 0, s>>>(p); break;
+    case 128: attention_kernel<128><<<grid, 128, 0, s>>>(p); break;
+    default: GENIE_CHECK(false, "attention: unsupported head dim");
+  }
+  GENIE_LAUNCHED("attention");
+}
+
+void launch_decode_attention_raw(const float* q, float* o, const float* kv_base, long long utt_stride,
+                                 long long layer_off, long long v_off, const int* kv_len, const int* active,
+                                 int B, int cap, float scale, int t_add, cudaStream_t s) {
+  if (B <= 0) return;
+  decode_attention_kernel<<<dim3(16, B), 128, 0, s>>>(q, o, kv_base, utt_stride, layer_off, v_off, kv_len,
+                                                      active, cap, scale, t_add);
+  GENIE_LAUNCHED("decode_attention");
+}
+
+}  // namespace genie

@@ -1,0 +1,90 @@
+// Shared declarations for the genie_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+
+namespace genie {
+
+// ---- error plumbing: the C-ABI never aborts; it returns a status and keeps
+// the message for genie_last_error() (reference convention: everything inside
+// the worker is caught and logged, src/genie_tts/Core/TTSPlayer.py:109-114).
+void set_error(const std::string& msg);
+struct Error { std::string msg; };
+
+#define GENIE_CUDA(expr)                                                            \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      throw ::genie::Error{std::string(#expr) + " failed: " + cudaGetErrorString(_e) +  \
+                           " (" __FILE__ ":" + std::to_string(__LINE__) + ")"};     \
+  } while (0)
+
+#define GENIE_CHECK(cond, msg)                                                      \
+  do {                                                                              \
+    if (!(cond)) throw ::genie::Error{std::string(msg) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"}; \
+  } while (0)
+
+inline void check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw Error{std::string(what) + " launch failed: " + cudaGetErrorString(e)};
+}
+
+// global kernel-launch counter (bench.py reports it as gpu_launches)
+extern unsigned long long g_launches;
+#define GENIE_LAUNCHED(name) do { ++::genie::g_launches; ::genie::check_launch(name); } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_MISH = 3, ACT_TANH = 4 };
+
+// ---------------------------------------------------------------------------
+// Implicit-GEMM 1-D convolution / linear layer on channels-last activations.
+//   y[seg, out_mul*q + out_add, co] (op)= out_scale * act( sum_{m<ntaps} sum_{ci}
+//        pre(x[seg, q + in_shift0 + m*in_shift_step, ci]) * W[co, m, ci] + bias[co] + bias2[seg, co] ) + res[...]
+// Rows outside [0, T_seg) read as zero (conv zero padding at utterance edges).
+// A linear layer is ntaps=1, in_shift0=0 over one segment of M rows.
+// ---------------------------------------------------------------------------
+struct ConvGemm {
+  const float* x = nullptr;   int ldx = 0;     // input  rows x Cin   (fp32)
+  const void*  w = nullptr;   int w_f16 = 0;   // weights: element (co, m, ci) at co*w_co_stride + m*w_tap_stride + ci
+  long long w_co_stride = 0, w_tap_stride = 0;
+  const float* bias = nullptr;                 // [Cout]
+  const float* bias2 = nullptr; int ldb2 = 0;  // [B, ldb2] per-segment bias (conditioning)
+  const float* res = nullptr; int ldr = 0;     // residual rows x Cout (output row indexing)
+  float* y = nullptr;         int ldy = 0;
+  int Cin = 0, Cout = 0;
+  int ntaps = 1, in_shift0 = 0, in_shift_step = 1;
+  int out_mul = 1, out_add = 0;
+  float pre_slope = 1.f;                       // leaky-relu slope applied to x on load (1 = identity)
+  int act = ACT_NONE; float act_slope = 0.f;
+  float out_scale = 1.f;
+  int accumulate = 0;                          // y += result
+  // segments (utterances): rows of segment b are [in_off[b], in_off[b+1]) in x and
+  // [out_off[b], out_off[b+1]) in y/res.  Null => one segment [0, M) / [0, M_out).
+  const int* in_off = nullptr; const int* out_off = nullptr;
+  int B = 1; int M = 0; int M_out = 0;         // M: max #q per segment (grid sizing); single-segment row counts
+  int q_extra = 0;                             // q ranges over [0, T_in + q_extra)
+};
+void launch_conv_gemm(const ConvGemm& p, cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// attention
+// ---------------------------------------------------------------------------
+struct Attn {
+  const float* q = nullptr; int ldq = 0;       // [rows, H*d] (row-major, heads side by side)
+  const float* k = nullptr; int ldk = 0;
+  const float* v = nullptr; int ldv = 0;
+  float* o = nullptr;       int ldo = 0;
+  const int* q_off = nullptr;                  // [B+1] query segment offsets
+  const int* kv_off = nullptr;                 // [B+1] key segment offsets
+  int B = 1, H = 1, d = 32, max_q = 0;
+  float scale = 1.f;                           // applied to q before q.k (and q.rel_k)
+  int mask_mode = 0;                           // 0 none, 1 = T2S prefill (lx[b] text rows)
+  const int* lx = nullptr;
+  const float* rel_k = nullptr;                // [2*window+1, d] or null
+  const float* rel_v = nullptr;
+  int window = 0;
+};
+void launch_attention(const Attn& p, cudaStream_t s);
+
+}  // namespace genie

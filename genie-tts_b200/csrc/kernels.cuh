@@ -1,0 +1,78 @@
+// Launchers for the small fused / elementwise kernels (elementwise.cu, sampler.cu).
+#pragma once
+#include "common.cuh"
+
+namespace genie {
+
+void launch_decode_attention_raw(const float* q, float* o, const float* kv_base, long long utt_stride,
+                                 long long layer_off, long long v_off, const int* kv_len, const int* active,
+                                 int B, int cap, float scale, int t_add, cudaStream_t s);
+
+// y[r,:] = LN(x[r,:] (+ res[r,:])) * g + b   (eps 1e-5), C multiple of 32, C <= 1024
+void launch_layernorm(const float* x, const float* res, const float* g, const float* b, float* y,
+                      int rows, int C, cudaStream_t s);
+
+// x[r,:] += emb[seq[r],:] + alpha * PE(pos[r])     (text rows; pos is 1-based per utterance)
+void launch_text_embed_pe(float* x, const long long* seq, const int* pos, const float* emb, const float* alpha,
+                          const float* div_term, int rows, cudaStream_t s);
+// out[r,:] = emb[tok[r],:] + alpha * PE(pos[r]);  raw (no PE) copy optional
+void launch_audio_embed_pe(float* out, const int* tok, const int* pos, const float* emb, const float* alpha,
+                           const float* div_term, int rows, cudaStream_t s);
+// decode-step variant: token = hist[b, hist_len[b]-1], position = hist_len[b] - 0 (1-based audio position)
+void launch_decode_embed(float* out, const int* hist, int hist_ld, const int* hist_len, const int* active,
+                         const float* emb, const float* alpha, const float* div_term, int B, cudaStream_t s);
+
+// scatter K,V columns of qkv rows into the head-major cache:
+//   cache[b][layer][kv][h][pos][32], pos = dst_pos0[b] + (row - row_off[b])
+void launch_kv_scatter(const float* qkv, int ld, float* kv_base, long long utt_stride, long long layer_off,
+                       long long v_off, int cap, const int* row_off, const int* dst_pos0, const int* row2utt,
+                       int rows, const int* active, cudaStream_t s);
+
+struct SamplerArgs {
+  const float* logits;     // [B, ld]
+  int ld;
+  int* hist;               // [B, hist_ld] token history (prompt + generated)
+  int hist_ld;
+  int* hist_len;           // [B]
+  int* kv_len;             // [B] incremented when advance_kv
+  int* active;             // [B] cleared on stop (when honour_stop)
+  int* stop_step;          // [B] step index at which stop fired (or -1)
+  int B;
+  int top_k; float temperature; float penalty;
+  int greedy; unsigned long long seed; int step;
+  int honour_stop; int advance_kv; int check_stop;
+  float* dbg_noise;        // optional [B,1025] externally supplied noise (tests)
+};
+void launch_sampler(const SamplerArgs& a, cudaStream_t s);
+
+// ---- VITS helpers (channels-last fp32)
+void launch_gather_rows(float* out, int ldo, const float* table, int C, const long long* idx, int rows, int repeat,
+                        cudaStream_t s);   // out[r*repeat + j, :] = table[idx[r], :]
+void launch_gated_act(const float* x, int ldx, float* y, int ldy, int H, int rows, cudaStream_t s);  // tanh(a)*sigmoid(b)
+void launch_glu_residual(const float* y2, int ld2, float* x, int ldx, int H, int rows, cudaStream_t s); // x += a*sigmoid(b)
+void launch_flip_channels(const float* x, float* y, int C, int rows, cudaStream_t s);
+// z[:, 96:] -= mean  (flow coupling reverse, logs == 0)
+void launch_sub_cols(float* z, int ldz, int col0, const float* m, int ldm, int C, int rows, cudaStream_t s);
+// zp = m + noise * exp(logs) * scale ; stats [rows, 384] = (m | logs); noise may be null (zeros)
+void launch_zp(const float* stats, const float* noise, float* zp, float scale, int rows, cudaStream_t s);
+void launch_add_inplace(float* y, const float* x, long long n, cudaStream_t s);
+void launch_scale_inplace(float* y, float a, long long n, cudaStream_t s);
+void launch_fill(float* y, float a, long long n, cudaStream_t s);
+// audio[t] = tanh( sum_{j<7,c<C} lrelu(x[t+j-3, c], 0.01) * w[j*C+c] )   per segment
+void launch_conv_post_tanh(const float* x, int C, const float* w, float* audio, const int* off, int B, int maxT,
+                           cudaStream_t s);
+// spectrogram frames: reflect-pad 704, frame 2048, hop 640, periodic Hann -> frames [F, 2048]
+void launch_stft_frames(const float* audio, int n, float* frames, int F, cudaStream_t s);
+void launch_dft_matrix(float* w, cudaStream_t s);   // [1408, 2048]: rows 2b = cos, 2b+1 = -sin for bin b < 704
+void launch_magnitude(const float* reim, float* mag, int F, cudaStream_t s);   // [F,1408] -> [F,704]
+void launch_mean_rows(const float* x, int ld, int C, int rows, float* out, cudaStream_t s);
+void launch_prelu_add(float* ge, const float* add, const float* slope, int C, cudaStream_t s);
+// VQ: codes[r] = argmax_c -(|x_r|^2 - 2 x_r.e_c + |e_c|^2) given dots [rows, 1024] = (2*x).e
+void launch_vq_argmax(const float* x, int ldx, const float* xe2, const float* e2, int rows, long long* codes,
+                      cudaStream_t s);
+void launch_row_sqnorm(const float* x, int ld, int C, int rows, float* out, cudaStream_t s);
+// copy strided columns:  dst[r, :C] = src[r, c0:c0+C]
+void launch_copy_cols(const float* src, int lds, int c0, float* dst, int ldd, int d0, int C, int rows, cudaStream_t s);
+void launch_transpose(const float* src, int rows, int cols, float* dst, cudaStream_t s);   // dst[c, r] = src[r, c]
+
+}  // namespace genie

@@ -1,0 +1,165 @@
+// Internal model / prompt / workspace structures.
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+#include "../../include/genie_b200.h"
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace genie {
+
+struct DevBuf {
+  void* p = nullptr; size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  // grow-only; contents are NOT preserved
+  bool reserve(size_t n) {
+    if (n <= bytes) return false;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    size_t want = n + n / 8 + 256;
+    GENIE_CUDA(cudaMalloc(&p, want));
+    bytes = want;
+    return true;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct RawTensor {
+  void* d = nullptr; int f16 = 0; std::vector<int64_t> dims; long long numel = 0;
+};
+
+struct Linear {            // y = x W^T + b ; W [N,K] row-major
+  const void* w = nullptr; int w_f16 = 0; const float* b = nullptr; int N = 0, K = 0;
+};
+struct Conv {              // repacked [Cout][k][Cin] fp32 (weight-norm folded)
+  const float* w = nullptr; const float* b = nullptr; int Cout = 0, Cin = 0, k = 1;
+};
+struct ConvT {             // repacked [k][Cout][Cin] fp32
+  const float* w = nullptr; const float* b = nullptr; int Cout = 0, Cin = 0, k = 0, stride = 0, pad = 0;
+};
+
+struct T2SLayer {
+  Linear qkv, out, ff1, ff2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct VitsEncLayer {
+  Conv q, k, v, o, ff1, ff2;
+  const float *rel_k, *rel_v, *g1, *b1, *g2, *b2;
+};
+struct WNLayer { Conv in, rs; };
+struct FlowStep { Conv pre, post, cond; WNLayer wn[4]; };
+struct ResBlock { Conv c1[3], c2[3]; int k = 3; };
+struct MelStyle { Linear fc1, fc2, wq, wk, wv, fo, fc; Conv t0, t1; int out_dim = 512; };
+
+struct Workspace {
+  // named grow-only device buffers
+  std::map<std::string, std::unique_ptr<DevBuf>> bufs;
+  template <typename T> T* get(const std::string& name, size_t count) {
+    auto& b = bufs[name];
+    if (!b) b.reset(new DevBuf());
+    if (b->reserve(count * sizeof(T))) ++generation;
+    return b->as<T>();
+  }
+  size_t total() const { size_t t = 0; for (auto& kv : bufs) t += kv.second->bytes; return t; }
+  unsigned long long generation = 0;   // bumped whenever any buffer moves (invalidates captured graphs)
+};
+
+struct Model {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool finalized = false, v2pp = false;
+  std::unordered_map<std::string, RawTensor> raw[4];
+  std::vector<void*> owned;           // device allocations owned by the model
+  size_t weight_bytes = 0;
+
+  // constants
+  float* div_term = nullptr;          // [256]
+  int top_k = 15; float penalty = 1.35f, temperature = 1.0f, noise_scale = 0.5f;
+
+  // T2S
+  const float *text_emb = nullptr, *text_alpha = nullptr, *audio_emb = nullptr, *audio_alpha = nullptr;
+  Linear bert_proj, predict;
+  T2SLayer layers[24];
+  // prompt-time VQ
+  Conv ssl_vq;                        // k=2 stride-2 conv as a linear over row pairs
+  const float *codebook_enc = nullptr, *codebook_enc_sq = nullptr;
+
+  // VITS
+  int gin = 512;                      // global-embedding width of flow/dec conditioning (512 V2, 1024 V2ProPlus)
+  const float *codebook = nullptr, *vits_text_emb = nullptr;
+  Conv ssl_proj, enc_proj;
+  VitsEncLayer enc_ssl[3], enc_text[6], enc2[3];
+  Conv mrte_c_pre, mrte_text_pre, mrte_q, mrte_k, mrte_v, mrte_o, mrte_c_post;
+  FlowStep flow[4];                   // in execution order (flows.6, .4, .2, .0)
+  Conv dec_pre, dec_cond;
+  int n_up = 5;
+  ConvT ups[5];
+  ResBlock res[15];
+  const float* conv_post = nullptr;   // [7][C_last]
+  int c_last = 16;
+  MelStyle ref_enc;                   // V2: vits ref_enc.*; V2ProPlus: prompt_encoder ref_enc.*
+  Linear sv_emb, ge_to512; const float* prelu = nullptr;
+  float* dft = nullptr;               // [1408, 2048]
+
+  Workspace ws;
+  // decode-step CUDA graph cache
+  cudaGraphExec_t step_graph = nullptr; int step_graph_B = 0; unsigned long long step_graph_gen = 0;
+  int step_graph_cap = 0; int step_graph_flags = 0;
+  unsigned long long step_graph_seed = 0; float step_graph_temp = 0.f, step_graph_pen = 0.f;
+  int use_graph = 1;
+  // debug
+  bool record_logits = false, keep = false;
+  std::vector<float> logits_host;
+  std::map<std::string, std::vector<float>> kept;
+  float timing[8] = {0};
+
+  ~Model();
+};
+
+struct Prompt {
+  Model* model = nullptr;
+  int Lr = 0, Ly = 0, ge_dim = 0;
+  bool has_bert = false;
+  long long* ref_seq = nullptr;       // device int64 [Lr]
+  float* ref_bert = nullptr;          // device [Lr,1024] or null
+  int* prompts = nullptr;             // device int32 [Ly]
+  std::vector<int64_t> prompts_host;
+  float* ge = nullptr;                // device [ge_dim]
+  float* ge_mrte = nullptr;           // device [512] (V2: == ge; V2ProPlus: ge_advanced)
+  float* flow_cond = nullptr;         // device [4][1536]
+  float* dec_cond = nullptr;          // device [C0]
+  std::vector<void*> owned;
+  ~Prompt() { for (void* p : owned) cudaFree(p); }
+};
+
+// weights.cu
+void model_finalize(Model& m);
+// stages
+void prompt_build(Model& m, Prompt& p, const int64_t* ref_seq, int Lr, const float* ref_bert, const float* ssl, int Ts,
+                  const float* ref_audio, int n_audio, const float* sv_emb, const float* ge_in, int ge_dim,
+                  const float* ge_adv_in);
+struct SamplingCfg { int top_k; float temperature, penalty; int greedy; unsigned long long seed; int max_steps, fixed_steps; };
+int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
+                 const float* text_bert, const SamplingCfg& cfg, const volatile int* cancel, int io_dev,
+                 int64_t* y, int y_ld, int* y_len, int* idx);
+void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
+                 const int64_t* sem, const int* sem_len, const float* zp_noise, unsigned long long seed,
+                 float noise_scale, int io_dev, float* audio, int* audio_len);
+
+// helpers shared by the stage files
+void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, int ldy, int M, int act = ACT_NONE,
+                const float* res = nullptr, int ldr = 0);
+void keep_tensor(Model& m, const char* name, const float* dev, long long n);
+template <typename T> T* dev_alloc(std::vector<void*>& owned, size_t count) {
+  void* p = nullptr;
+  GENIE_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+  owned.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+}  // namespace genie

@@ -1,0 +1,345 @@
+// T2S GPT stage: text encode (t2s_encoder#[49-83]) -> prefill
+// (t2s_first_stage_decoder) -> decode loop (t2s_stage_decoder x <=500,
+// reference src/genie_tts/Core/Inference.py:76-106) for a ragged batch of
+// independent utterances.  KV cache: fp32, head-major, appended in place.
+#include "model.h"
+#include <algorithm>
+#include <cmath>
+
+namespace genie {
+namespace {
+
+constexpr int D = 512, NL = 24, H = 16, V = 1025;
+
+struct Batch {
+  int B = 0;
+  std::vector<int> Lr, Lt, Ly, Lx, S, row_off, txt_off;
+  int rows = 0, txt_rows = 0, maxS = 0, cap = 0, hist_ld = 0;
+};
+
+__global__ void fill_rows_kernel(float* x, const float* bias, int rows) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * 512) return;
+  x[i] = bias ? bias[i & 511] : 0.f;
+}
+__global__ void init_hist_kernel(int* hist, int hist_ld, const int* const* prompt_ptrs, const int* ly, int B) {
+  int b = blockIdx.x;
+  for (int i = threadIdx.x; i < ly[b]; i += blockDim.x) hist[(long long)b * hist_ld + i] = prompt_ptrs[b][i];
+}
+__global__ void hist_to_i64_kernel(const int* hist, int hist_ld, const int* hist_len, long long* y, int y_ld, int B) {
+  int b = blockIdx.x;
+  int n = hist_len[b];
+  for (int i = threadIdx.x; i < y_ld; i += blockDim.x)
+    y[(long long)b * y_ld + i] = i < n ? hist[(long long)b * hist_ld + i] : 0;
+}
+
+struct StepBufs {
+  float *h, *qkv, *att, *tmp, *h1, *ff, *logits;
+  int *hist, *hist_len, *kv_len, *active, *stop_step;
+  float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld;
+};
+
+// one decode step for every active utterance (stage#[12-1821])
+void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
+  cudaStream_t s = m.stream;
+  launch_decode_embed(w.h, w.hist, w.hist_ld, w.hist_len, w.active, m.audio_emb, m.audio_alpha, m.div_term, B, s);
+  const float scale = 1.0f / std::sqrt(32.0f);
+  for (int l = 0; l < NL; ++l) {
+    const T2SLayer& L = m.layers[l];
+    run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B);
+    launch_kv_scatter(w.qkv, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap, nullptr, w.kv_len,
+                      nullptr, B, w.active, s);
+    launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
+                                w.active, B, w.cap, scale, /*t_add=*/1, s);
+    run_linear(m, L.out, w.att, D, w.tmp, D, B, ACT_NONE, w.h, D);
+    launch_layernorm(w.tmp, nullptr, L.ln1_g, L.ln1_b, w.h1, B, D, s);
+    run_linear(m, L.ff1, w.h1, D, w.ff, 4 * D, B, ACT_RELU);
+    run_linear(m, L.ff2, w.ff, 4 * D, w.tmp, D, B, ACT_NONE, w.h1, D);
+    launch_layernorm(w.tmp, nullptr, L.ln2_g, L.ln2_b, w.h, B, D, s);
+  }
+  run_linear(m, m.predict, w.h, D, w.logits, V, B);
+  SamplerArgs a{};
+  a.logits = w.logits; a.ld = V; a.hist = w.hist; a.hist_ld = w.hist_ld; a.hist_len = w.hist_len;
+  a.kv_len = w.kv_len; a.active = w.active; a.stop_step = w.stop_step; a.B = B;
+  a.top_k = cfg.top_k; a.temperature = cfg.temperature; a.penalty = cfg.penalty; a.greedy = cfg.greedy;
+  a.seed = cfg.seed; a.step = 0; a.honour_stop = cfg.fixed_steps > 0 ? 0 : 1; a.advance_kv = 1; a.check_stop = 1;
+  a.dbg_noise = nullptr;
+  launch_sampler(a, s);
+}
+
+}  // namespace
+
+int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len_in,
+                 const float* text_bert, const SamplingCfg& cfg, const volatile int* cancel, int io_dev,
+                 int64_t* y_out, int y_ld, int* y_len_out, int* idx_out) {
+  GENIE_CHECK(m.finalized, "model not finalized");
+  GENIE_CHECK(B > 0, "empty batch");
+  cudaStream_t s = m.stream;
+  GENIE_CUDA(cudaSetDevice(m.device));
+  const int max_steps = cfg.fixed_steps > 0 ? cfg.fixed_steps : cfg.max_steps;
+
+  // ---- text lengths (device-resident payload: lengths are still host metadata)
+  std::vector<int> text_len(text_len_in, text_len_in + B);
+  Batch bt; bt.B = B;
+  bt.row_off.push_back(0); bt.txt_off.push_back(0);
+  bool any_bert = text_bert != nullptr;
+  for (int b = 0; b < B; ++b) {
+    Prompt* p = prompts[b];
+    GENIE_CHECK(p && p->model == &m, "prompt does not belong to this model");
+    GENIE_CHECK(text_len[b] > 0, "empty text_seq");
+    bt.Lr.push_back(p->Lr); bt.Lt.push_back(text_len[b]); bt.Ly.push_back(p->Ly);
+    bt.Lx.push_back(p->Lr + text_len[b]); bt.S.push_back(p->Lr + text_len[b] + p->Ly);
+    bt.row_off.push_back(bt.row_off.back() + bt.S.back());
+    bt.txt_off.push_back(bt.txt_off.back() + bt.Lx.back());
+    bt.maxS = std::max(bt.maxS, bt.S.back());
+    any_bert = any_bert || p->has_bert;
+  }
+  bt.rows = bt.row_off.back(); bt.txt_rows = bt.txt_off.back();
+  bt.cap = ((bt.maxS + max_steps + 1 + 15) / 16) * 16;
+  int maxLy = *std::max_element(bt.Ly.begin(), bt.Ly.end());
+  bt.hist_ld = maxLy + max_steps + 2;
+  GENIE_CHECK(y_ld >= bt.hist_ld || y_out == nullptr, "y_ld too small: need >= " + std::to_string(bt.hist_ld));
+
+  Workspace& ws = m.ws;
+  const int R = bt.rows;
+  float* X = ws.get<float>("t2s.x", (size_t)R * D);
+  float* QKV = ws.get<float>("t2s.qkv", (size_t)R * 3 * D);
+  float* ATT = ws.get<float>("t2s.att", (size_t)R * D);
+  float* TMP = ws.get<float>("t2s.tmp", (size_t)R * D);
+  float* H1 = ws.get<float>("t2s.h1", (size_t)R * D);
+  float* FF = ws.get<float>("t2s.ff", (size_t)R * 4 * D);
+  float* XT = ws.get<float>("t2s.xtext", (size_t)bt.txt_rows * D);
+  float* BERT = any_bert ? ws.get<float>("t2s.bert", (size_t)bt.txt_rows * 1024) : nullptr;
+  long long* SEQ = ws.get<long long>("t2s.seq", bt.txt_rows);
+  int* IMETA = ws.get<int>("t2s.imeta", (size_t)R * 2 + bt.txt_rows + 8 * (B + 1));
+  float* LAST = ws.get<float>("t2s.last", (size_t)B * D);
+  float* LOGITS = ws.get<float>("t2s.logits", (size_t)B * V);
+  long long* LASTIDX = ws.get<long long>("t2s.lastidx", B);
+  const int** PPTR = ws.get<const int*>("t2s.pptr", B);
+  int* HIST = ws.get<int>("t2s.hist", (size_t)B * bt.hist_ld);
+  long long* Y64 = ws.get<long long>("t2s.y64", (size_t)B * bt.hist_ld);
+  // KV cache [B][layer][K|V][H][cap][32] fp32
+  const long long head_sz = (long long)bt.cap * 32, v_off = H * head_sz, layer_stride = 2 * v_off,
+                  utt_stride = NL * layer_stride;
+  float* KV = ws.get<float>("t2s.kv", (size_t)B * utt_stride);
+
+  // ---- host-built index metadata, one upload
+  //   txt_pos[txt_rows] | row2utt[R] | aud_pos[R] (per audio row; text rows unused) | per-utt arrays
+  std::vector<int> meta((size_t)R * 2 + bt.txt_rows + 8 * (B + 1), 0);
+  int* h_txt_pos = meta.data();
+  int* h_row2utt = h_txt_pos + bt.txt_rows;
+  int* h_aud_tok_pos = h_row2utt + R;           // position (1-based) of audio rows, compacted per utterance
+  int* h_row_off = h_aud_tok_pos + R;           // [B+1]
+  int* h_lx = h_row_off + (B + 1);              // [B]
+  int* h_zero = h_lx + (B + 1);                 // [B] zeros (dst_pos0 for prefill scatter)
+  int* h_kvlen = h_zero + (B + 1);              // [B]
+  int* h_histlen = h_kvlen + (B + 1);           // [B]
+  int* h_active = h_histlen + (B + 1);          // [B]
+  int* h_stop = h_active + (B + 1);             // [B]
+  int* h_ly = h_stop + (B + 1);                 // [B]
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < bt.Lx[b]; ++i) h_txt_pos[bt.txt_off[b] + i] = i + 1;
+    for (int i = 0; i < bt.S[b]; ++i) h_row2utt[bt.row_off[b] + i] = b;
+    for (int i = 0; i < bt.Ly[b]; ++i) h_aud_tok_pos[bt.row_off[b] + bt.Lx[b] + i] = i + 1;
+    h_row_off[b] = bt.row_off[b]; h_lx[b] = bt.Lx[b]; h_kvlen[b] = bt.S[b]; h_histlen[b] = bt.Ly[b];
+    h_active[b] = 1; h_stop[b] = -1; h_ly[b] = bt.Ly[b];
+  }
+  h_row_off[B] = R;
+  GENIE_CUDA(cudaMemcpyAsync(IMETA, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  int* d_txt_pos = IMETA; int* d_row2utt = d_txt_pos + bt.txt_rows; int* d_aud_pos = d_row2utt + R;
+  int* d_row_off = d_aud_pos + R; int* d_lx = d_row_off + (B + 1); int* d_zero = d_lx + (B + 1);
+  int* d_kvlen = d_zero + (B + 1); int* d_histlen = d_kvlen + (B + 1); int* d_active = d_histlen + (B + 1);
+  int* d_stop = d_active + (B + 1); int* d_ly = d_stop + (B + 1);
+
+  cudaEvent_t ev0, ev1, ev2;
+  GENIE_CUDA(cudaEventCreate(&ev0)); GENIE_CUDA(cudaEventCreate(&ev1)); GENIE_CUDA(cudaEventCreate(&ev2));
+  GENIE_CUDA(cudaEventRecord(ev0, s));
+
+  // ---- K1: x = Emb_text[ref||text] + bert_proj(bert) + alpha*PE(1..Lx)   (t2s_encoder#[49-83])
+  const cudaMemcpyKind in_kind = io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  {
+    long long toff = 0;
+    for (int b = 0; b < B; ++b) {
+      Prompt* p = prompts[b];
+      GENIE_CUDA(cudaMemcpyAsync(SEQ + bt.txt_off[b], p->ref_seq, p->Lr * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+      GENIE_CUDA(cudaMemcpyAsync(SEQ + bt.txt_off[b] + p->Lr, text_seq + toff, text_len[b] * sizeof(long long), in_kind, s));
+      if (any_bert) {
+        float* dst = BERT + (long long)bt.txt_off[b] * 1024;
+        if (p->has_bert) GENIE_CUDA(cudaMemcpyAsync(dst, p->ref_bert, (size_t)p->Lr * 1024 * 4, cudaMemcpyDeviceToDevice, s));
+        else GENIE_CUDA(cudaMemsetAsync(dst, 0, (size_t)p->Lr * 1024 * 4, s));
+        dst += (long long)p->Lr * 1024;
+        if (text_bert) GENIE_CUDA(cudaMemcpyAsync(dst, text_bert + toff * 1024, (size_t)text_len[b] * 1024 * 4, in_kind, s));
+        else GENIE_CUDA(cudaMemsetAsync(dst, 0, (size_t)text_len[b] * 1024 * 4, s));
+      }
+      toff += text_len[b];
+    }
+  }
+  if (any_bert) {
+    run_linear(m, m.bert_proj, BERT, 1024, XT, D, bt.txt_rows);
+  } else {
+    // bert features are zeros for ja/en (reference GetPhonesAndBert.py:60,80): bert_proj reduces to its bias
+    fill_rows_kernel<<<(unsigned)(((long long)bt.txt_rows * 512 + 255) / 256), 256, 0, s>>>(XT, m.bert_proj.b, bt.txt_rows);
+    GENIE_LAUNCHED("fill_rows");
+  }
+  launch_text_embed_pe(XT, SEQ, d_txt_pos, m.text_emb, m.text_alpha, m.div_term, bt.txt_rows, s);
+  keep_tensor(m, "x", XT, (long long)bt.txt_rows * D);
+
+  // ---- K3: xy = [x || Emb_audio[prompts] + alpha*PE(1..Ly)]  (first_stage#[5-25])
+  {
+    std::vector<const int*> pp(B);
+    for (int b = 0; b < B; ++b) pp[b] = prompts[b]->prompts;
+    GENIE_CUDA(cudaMemcpyAsync(PPTR, pp.data(), B * sizeof(int*), cudaMemcpyHostToDevice, s));
+    GENIE_CUDA(cudaMemsetAsync(HIST, 0, (size_t)B * bt.hist_ld * sizeof(int), s));
+    init_hist_kernel<<<B, 128, 0, s>>>(HIST, bt.hist_ld, PPTR, d_ly, B);
+    GENIE_LAUNCHED("init_hist");
+    for (int b = 0; b < B; ++b) {
+      GENIE_CUDA(cudaMemcpyAsync(X + (long long)bt.row_off[b] * D, XT + (long long)bt.txt_off[b] * D,
+                                 (size_t)bt.Lx[b] * D * 4, cudaMemcpyDeviceToDevice, s));
+      float* dst = X + (long long)(bt.row_off[b] + bt.Lx[b]) * D;
+      launch_audio_embed_pe(dst, prompts[b]->prompts, d_aud_pos + bt.row_off[b] + bt.Lx[b], m.audio_emb,
+                            m.audio_alpha, m.div_term, bt.Ly[b], s);
+    }
+  }
+
+  // ---- K4: 24 prefill layers over all rows of all utterances
+  const float scale = 1.0f / std::sqrt(32.0f);
+  float* Hcur = X;
+  for (int l = 0; l < NL; ++l) {
+    const T2SLayer& L = m.layers[l];
+    run_linear(m, L.qkv, Hcur, D, QKV, 3 * D, R);
+    launch_kv_scatter(QKV, 3 * D, KV, utt_stride, l * layer_stride, v_off, bt.cap, d_row_off, d_zero, d_row2utt, R,
+                      nullptr, s);
+    Attn a;
+    a.q = QKV; a.ldq = 3 * D; a.k = QKV + D; a.ldk = 3 * D; a.v = QKV + 2 * D; a.ldv = 3 * D;
+    a.o = ATT; a.ldo = D; a.q_off = d_row_off; a.kv_off = d_row_off; a.B = B; a.H = H; a.d = 32; a.max_q = bt.maxS;
+    a.scale = scale; a.mask_mode = 1; a.lx = d_lx;
+    launch_attention(a, s);
+    run_linear(m, L.out, ATT, D, TMP, D, R, ACT_NONE, Hcur, D);
+    launch_layernorm(TMP, nullptr, L.ln1_g, L.ln1_b, H1, R, D, s);
+    run_linear(m, L.ff1, H1, D, FF, 4 * D, R, ACT_RELU);
+    run_linear(m, L.ff2, FF, 4 * D, TMP, D, R, ACT_NONE, H1, D);
+    launch_layernorm(TMP, nullptr, L.ln2_g, L.ln2_b, X, R, D, s);
+    Hcur = X;
+    if (l == 0 && m.keep) {
+      keep_tensor(m, "qkv0", QKV, (long long)R * 3 * D);
+      keep_tensor(m, "h0", X, (long long)R * D);
+    }
+  }
+  // logits for the last row of each utterance (first_stage#[1785-1788])
+  {
+    std::vector<long long> li(B);
+    for (int b = 0; b < B; ++b) li[b] = bt.row_off[b + 1] - 1;
+    GENIE_CUDA(cudaMemcpyAsync(LASTIDX, li.data(), B * sizeof(long long), cudaMemcpyHostToDevice, s));
+    launch_gather_rows(LAST, D, X, D, LASTIDX, B, 1, s);
+    run_linear(m, m.predict, LAST, D, LOGITS, V, B);
+  }
+  std::vector<float>& rec = m.logits_host;
+  rec.clear();
+  auto record = [&]() {
+    if (!m.record_logits) return;
+    size_t o = rec.size();
+    rec.resize(o + (size_t)B * V);
+    GENIE_CUDA(cudaMemcpyAsync(rec.data() + o, LOGITS, (size_t)B * V * 4, cudaMemcpyDeviceToHost, s));
+    GENIE_CUDA(cudaStreamSynchronize(s));
+  };
+  record();
+  {
+    SamplerArgs a{};
+    a.logits = LOGITS; a.ld = V; a.hist = HIST; a.hist_ld = bt.hist_ld; a.hist_len = d_histlen; a.kv_len = d_kvlen;
+    a.active = d_active; a.stop_step = d_stop; a.B = B; a.top_k = cfg.top_k; a.temperature = cfg.temperature;
+    a.penalty = cfg.penalty; a.greedy = cfg.greedy; a.seed = cfg.seed; a.honour_stop = 0; a.advance_kv = 0;
+    a.check_stop = 0;   // the first-stage graph has no stop output
+    launch_sampler(a, s);
+  }
+  GENIE_CUDA(cudaEventRecord(ev1, s));
+
+  // ---- decode loop (Inference.py:95-106)
+  StepBufs w{};
+  w.h = ws.get<float>("t2s.step.h", (size_t)B * D); w.qkv = ws.get<float>("t2s.step.qkv", (size_t)B * 3 * D);
+  w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
+  w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
+  w.logits = LOGITS; w.hist = HIST; w.hist_len = d_histlen; w.kv_len = d_kvlen; w.active = d_active;
+  w.stop_step = d_stop; w.kv = KV; w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off;
+  w.cap = bt.cap; w.hist_ld = bt.hist_ld;
+
+  // the graph bakes pointers and scalar args; re-capture when any of them changes
+  const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (cfg.top_k << 4);
+  const bool can_graph = m.use_graph && !m.record_logits;
+  if (can_graph) {
+    bool stale = !m.step_graph || m.step_graph_B != B || m.step_graph_gen != ws.generation ||
+                 m.step_graph_cap != bt.cap || m.step_graph_flags != flags;
+    // seed / temperature / penalty are baked too: fold them into staleness via a cheap hash
+    if (m.step_graph_seed != cfg.seed || m.step_graph_temp != cfg.temperature || m.step_graph_pen != cfg.penalty)
+      stale = true;
+    if (stale) {
+      if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      unsigned long long launches_before = g_launches;
+      GENIE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        decode_step(m, w, B, cfg);
+      } catch (...) {
+        cudaStreamEndCapture(s, &g);
+        if (g) cudaGraphDestroy(g);
+        throw;
+      }
+      GENIE_CUDA(cudaStreamEndCapture(s, &g));
+      g_launches = launches_before;            // capture does not launch
+      GENIE_CUDA(cudaGraphInstantiate(&m.step_graph, g, 0));
+      cudaGraphDestroy(g);
+      m.step_graph_B = B; m.step_graph_gen = ws.generation; m.step_graph_cap = bt.cap; m.step_graph_flags = flags;
+      m.step_graph_seed = cfg.seed; m.step_graph_temp = cfg.temperature; m.step_graph_pen = cfg.penalty;
+    }
+  }
+  const unsigned long long per_step_launches = 3 + NL * 8ull;
+  int rc = 0;
+  std::vector<int> h_act(B, 1);
+  int steps_done = 0;
+  const int poll_every = 8;
+  for (int step = 0; step < max_steps; ++step) {
+    if (cancel && *cancel) { rc = 2 /* GENIE_CANCELLED */; break; }
+    if (can_graph) {
+      GENIE_CUDA(cudaGraphLaunch(m.step_graph, s));
+      g_launches += per_step_launches;
+    } else {
+      decode_step(m, w, B, cfg);
+    }
+    ++steps_done;
+    record();
+    if (cfg.fixed_steps <= 0 && ((step + 1) % poll_every == 0 || m.record_logits)) {
+      GENIE_CUDA(cudaMemcpyAsync(h_act.data(), d_active, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+      GENIE_CUDA(cudaStreamSynchronize(s));
+      bool any = false;
+      for (int b = 0; b < B; ++b) any = any || h_act[b];
+      if (!any) break;
+    }
+  }
+  GENIE_CUDA(cudaEventRecord(ev2, s));
+
+  // ---- results
+  std::vector<int> h_len(B), h_stopv(B);
+  GENIE_CUDA(cudaMemcpyAsync(h_len.data(), d_histlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  GENIE_CUDA(cudaMemcpyAsync(h_stopv.data(), d_stop, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (y_out) {
+    hist_to_i64_kernel<<<B, 256, 0, s>>>(HIST, bt.hist_ld, d_histlen, Y64, bt.hist_ld, B);
+    GENIE_LAUNCHED("hist_to_i64");
+    GENIE_CUDA(cudaMemcpy2DAsync(y_out, (size_t)y_ld * 8, Y64, (size_t)bt.hist_ld * 8, (size_t)bt.hist_ld * 8, B,
+                                 io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  }
+  GENIE_CUDA(cudaStreamSynchronize(s));
+  for (int b = 0; b < B; ++b) {
+    // reference loop variable at exit: index of the step whose stop flag fired, else last index
+    int idx;
+    if (cfg.fixed_steps > 0 || h_stopv[b] < 0) idx = steps_done - 1;
+    else idx = h_stopv[b] - (bt.Ly[b] + 1);     // stop_step stores the history length before that step's token
+    if (y_len_out) y_len_out[b] = h_len[b];
+    if (idx_out) idx_out[b] = idx < 0 ? 0 : idx;
+  }
+  float t01 = 0, t12 = 0;
+  cudaEventElapsedTime(&t01, ev0, ev1); cudaEventElapsedTime(&t12, ev1, ev2);
+  m.timing[0] = t01; m.timing[1] = t12; m.timing[2] = t01 + t12; m.timing[3] = (float)steps_done;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+  return rc;
+}
+
+}  // namespace genie

@@ -1,0 +1,250 @@
+"""Device-resident model / prompt objects over the C-ABI.
+
+``B200Model`` replaces the five onnxruntime sessions of one character
+(reference: GSVModel, src/genie_tts/ModelManager.py:48-56); ``B200Prompt``
+replaces the per-reference-audio work (src/genie_tts/Audio/ReferenceAudio.py:
+28-76 features + the VQ / ref_enc parts of the graphs).  Batched entry points
+take lists of utterances; the batch-1 ``GENIE.tts`` path is a batch of one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .weights import read_model_dir
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "Data")
+
+
+def load_constants() -> dict:
+    with open(os.path.join(_DATA, "t2s_constants.json")) as f:
+        c = json.load(f)
+    c["pe_div_term"] = np.frombuffer(bytes.fromhex(c["pe_div_term_f32_hex"]), dtype="<f4").copy()
+    return c
+
+
+def _ptr(a) -> C.c_void_p:
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a.data_ptr()))   # torch tensor (device-resident leg)
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a).reshape(-1), dtype=np.int64)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+@dataclass
+class SamplingParams:
+    """Defaults (<=0) fall back to the graph constants: top_k 15, temperature 1.0,
+    repetition_penalty 1.35 (t2s_stage_decoder#[1780-1790]).  ``greedy`` is the
+    test-only switch that makes token sequences comparable with the oracle."""
+    top_k: int = 0
+    temperature: float = 0.0
+    repetition_penalty: float = 0.0
+    greedy: bool = False
+    seed: int = 0
+    max_steps: int = 500
+    fixed_steps: int = 0
+
+    def to_c(self) -> N.Sampling:
+        return N.Sampling(self.top_k, self.temperature, self.repetition_penalty, int(self.greedy),
+                          self.seed & 0xFFFFFFFFFFFFFFFF, self.max_steps, self.fixed_steps)
+
+
+class B200Model:
+    def __init__(self, model_dir: str, device: int = 0):
+        N.require_gpu()
+        tabs = read_model_dir(model_dir)        # raises FileNotFoundError like the reference loader
+        self.model_dir = model_dir
+        self.device = device
+        self.is_v2pp = tabs.is_v2pp
+        self._h = C.c_void_p(0)
+        L = N.lib()
+        N.check(L.genie_model_create(device, C.byref(self._h)))
+        try:
+            for graph, tab in ((N.GRAPH_T2S_ENCODER, tabs.encoder), (N.GRAPH_T2S, tabs.t2s),
+                               (N.GRAPH_VITS, tabs.vits), (N.GRAPH_PROMPT_ENCODER, tabs.prompt_encoder)):
+                if tab is None:
+                    continue
+                for name, arr in tab.tensors.items():
+                    a = np.ascontiguousarray(arr)     # memmap view -> bytes as stored (fp16 stays fp16)
+                    dt = N.F16 if a.dtype == np.float16 else N.F32
+                    if dt == N.F32 and a.dtype != np.float32:
+                        a = a.astype(np.float32)
+                    dims = (C.c_int64 * max(a.ndim, 1))(*a.shape)
+                    N.check(L.genie_model_add_tensor(self._h, graph, name.encode(), _ptr(a), dt, dims, a.ndim))
+            c = load_constants()
+            self.constants = c
+            div = _f32(c["pe_div_term"])
+            N.check(L.genie_model_set_constants(self._h, _ptr(div), c["top_k"], c["repetition_penalty"],
+                                                c["temperature"], c["vits_noise_scale"]))
+            N.check(L.genie_model_finalize(self._h))
+        except Exception:
+            L.genie_model_destroy(self._h)
+            self._h = C.c_void_p(0)
+            raise
+
+    # -- lifecycle -----------------------------------------------------------
+    def close(self) -> None:
+        if self._h:
+            N.lib().genie_model_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        v, wb, sb = C.c_int(0), C.c_longlong(0), C.c_longlong(0)
+        N.check(N.lib().genie_model_info(self._h, C.byref(v), C.byref(wb), C.byref(sb)))
+        return {"is_v2pp": bool(v.value), "weight_bytes": wb.value, "workspace_bytes": sb.value}
+
+    def set_option(self, key: str, value: int) -> None:
+        N.check(N.lib().genie_set_option(self._h, key.encode(), int(value)))
+
+    # -- prompt ----------------------------------------------------------------
+    def make_prompt(self, ref_seq, ref_bert, ssl_content, ref_audio_32k=None, sv_emb=None,
+                    ge=None, ge_advanced=None) -> "B200Prompt":
+        return B200Prompt(self, ref_seq, ref_bert, ssl_content, ref_audio_32k, sv_emb, ge, ge_advanced)
+
+    # -- T2S --------------------------------------------------------------------
+    def t2s_generate(self, prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
+                     text_berts: Optional[Sequence[Optional[np.ndarray]]] = None,
+                     sampling: Optional[SamplingParams] = None, cancel_flag: Optional[C.c_int] = None
+                     ) -> Tuple[List[np.ndarray], List[int]]:
+        """Returns (y_full per utterance: prompt tokens + every generated token, idx per utterance)."""
+        sp = sampling or SamplingParams()
+        B = len(prompts)
+        seqs = [_i64(t) for t in text_seqs]
+        lens = np.asarray([len(t) for t in seqs], dtype=np.int32)
+        cat = np.concatenate(seqs)
+        bert = None
+        if text_berts is not None and any(b is not None and np.any(b) for b in text_berts):
+            bert = np.concatenate([_f32(b) if b is not None else np.zeros((len(s), 1024), np.float32)
+                                   for b, s in zip(text_berts, seqs)], axis=0)
+        steps = sp.fixed_steps if sp.fixed_steps > 0 else (sp.max_steps if sp.max_steps > 0 else 500)
+        y_ld = max(p.n_prompt_tokens for p in prompts) + steps + 2
+        y = np.zeros((B, y_ld), dtype=np.int64)
+        y_len = np.zeros(B, dtype=np.int32)
+        idx = np.zeros(B, dtype=np.int32)
+        hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        csp = sp.to_c()
+        rc = N.lib().genie_t2s_generate(self._h, hs, B, _ptr(cat), _ptr(lens), _ptr(bert), C.byref(csp),
+                                        C.cast(C.pointer(cancel_flag), C.c_void_p) if cancel_flag is not None else None,
+                                        0, _ptr(y), y_ld, _ptr(y_len), _ptr(idx))
+        if rc == N.CANCELLED:
+            return [], []
+        N.check(rc)
+        return [y[b, :y_len[b]].copy() for b in range(B)], [int(i) for i in idx]
+
+    # -- SoVITS -----------------------------------------------------------------
+    def vits_decode(self, prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
+                    semantic: Sequence[np.ndarray], zp_noise: Optional[Sequence[np.ndarray]] = None,
+                    seed: int = 0, noise_scale: float = -1.0) -> List[np.ndarray]:
+        B = len(prompts)
+        seqs = [_i64(t) for t in text_seqs]
+        sems = [_i64(t) for t in semantic]
+        tl = np.asarray([len(t) for t in seqs], dtype=np.int32)
+        sl = np.asarray([len(t) for t in sems], dtype=np.int32)
+        for s_ in sems:
+            if len(s_) == 0 or s_.max() >= 1024 or s_.min() < 0:
+                raise ValueError("semantic tokens must be non-empty ids in [0, 1024)")
+        noise = None
+        if zp_noise is not None:
+            noise = np.concatenate([_f32(np.asarray(z).reshape(192, -1)[:, :2 * len(s_)]).reshape(-1)
+                                    for z, s_ in zip(zp_noise, sems)])
+        audio = np.zeros(int(sl.sum()) * 1280, dtype=np.float32)
+        alen = np.zeros(B, dtype=np.int32)
+        hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        N.check(N.lib().genie_vits_decode(self._h, hs, B, _ptr(np.concatenate(seqs)), _ptr(tl),
+                                          _ptr(np.concatenate(sems)), _ptr(sl), _ptr(noise), seed & (2 ** 64 - 1),
+                                          noise_scale, 0, _ptr(audio), _ptr(alen)))
+        out, o = [], 0
+        for b in range(B):
+            out.append(audio[o:o + alen[b]].copy())
+            o += alen[b]
+        return out
+
+    # -- debug ------------------------------------------------------------------
+    def record_logits(self, enable: bool) -> None:
+        N.check(N.lib().genie_debug_record_logits(self._h, int(enable)))
+
+    def read_logits(self) -> np.ndarray:
+        n = C.c_int(0)
+        N.check(N.lib().genie_debug_read_logits(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.float32)
+        N.check(N.lib().genie_debug_read_logits(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def keep(self, enable: bool) -> None:
+        N.check(N.lib().genie_debug_keep(self._h, int(enable)))
+
+    def read_kept(self, what: str) -> np.ndarray:
+        n = C.c_longlong(0)
+        N.check(N.lib().genie_debug_read(self._h, what.encode(), None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.float32)
+        N.check(N.lib().genie_debug_read(self._h, what.encode(), _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def last_timing(self) -> dict:
+        t = np.zeros(8, dtype=np.float32)
+        N.check(N.lib().genie_last_timing(self._h, _ptr(t), 8))
+        return {"prefill_ms": float(t[0]), "decode_ms": float(t[1]), "t2s_ms": float(t[2]), "steps": int(t[3])}
+
+
+class B200Prompt:
+    def __init__(self, model: B200Model, ref_seq, ref_bert, ssl_content, ref_audio_32k=None, sv_emb=None,
+                 ge=None, ge_advanced=None):
+        self.model = model
+        self._h = C.c_void_p(0)
+        seq = _i64(ref_seq)
+        bert = None
+        if ref_bert is not None and np.any(ref_bert):
+            bert = _f32(ref_bert).reshape(len(seq), 1024)
+        ssl = _f32(ssl_content).reshape(768, -1)
+        L = N.lib()
+        if ge is not None:
+            g = _f32(ge).reshape(-1)
+            ga = _f32(ge_advanced).reshape(-1) if ge_advanced is not None else None
+            N.check(L.genie_prompt_create_with_ge(model._h, _ptr(seq), len(seq), _ptr(bert), _ptr(ssl), ssl.shape[1],
+                                                  _ptr(g), len(g), _ptr(ga), C.byref(self._h)))
+        else:
+            au = _f32(ref_audio_32k).reshape(-1)
+            sv = _f32(sv_emb).reshape(-1) if sv_emb is not None else None
+            N.check(L.genie_prompt_create(model._h, _ptr(seq), len(seq), _ptr(bert), _ptr(ssl), ssl.shape[1],
+                                          _ptr(au), len(au), _ptr(sv), C.byref(self._h)))
+        n, gd, lr = C.c_int(0), C.c_int(0), C.c_int(0)
+        N.check(L.genie_prompt_info(self._h, C.byref(n), C.byref(gd), C.byref(lr)))
+        self.n_prompt_tokens, self.ge_dim, self.ref_len = n.value, gd.value, lr.value
+
+    def read(self):
+        pr = np.zeros(self.n_prompt_tokens, dtype=np.int64)
+        ge = np.zeros(self.ge_dim, dtype=np.float32)
+        gea = np.zeros(512, dtype=np.float32)
+        N.check(N.lib().genie_prompt_read(self._h, _ptr(pr), _ptr(ge), _ptr(gea)))
+        return pr, ge, gea
+
+    def close(self) -> None:
+        if self._h:
+            N.lib().genie_prompt_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,129 @@
+/* genie_b200 — C-ABI of the B200-native GPT-SoVITS synthesis hot path.
+ *
+ * Drop-in boundary: the reference (Genie-TTS) has no FFI of its own; its operator
+ * boundary is the onnxruntime.InferenceSession duck type held in GSVModel
+ * (/root/reference/src/genie_tts/ModelManager.py:48-56) and called at
+ * src/genie_tts/Core/Inference.py:47,55,76,88,102 and
+ * src/genie_tts/Audio/ReferenceAudio.py:72-73.  This library replaces those
+ * sessions one level up: one entry point per *stage group*
+ * instead of one run() per decode step with 48 KV tensors through numpy.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure and
+ * never aborts; genie_last_error() returns the message of the last failure on
+ * the calling thread.  Plain pointers and sizes only.  Pointers are HOST
+ * pointers unless the `io_on_device` argument of the call is 1, in which case
+ * the in/out payload pointers are device pointers on the model's GPU (used by
+ * bench.py's HBM-resident `value` leg).  All integer token ids are int64 to
+ * match the reference's numpy feeds.  One model handle belongs to one GPU and
+ * must be driven by one thread at a time.
+ */
+#ifndef GENIE_B200_H
+#define GENIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct genie_model genie_model;
+typedef struct genie_prompt genie_prompt;
+
+/* which graph file of the model directory a tensor belongs to
+ * (src/genie_tts/ModelManager.py:26-45: GSVModelFile) */
+enum { GENIE_GRAPH_T2S_ENCODER = 0, GENIE_GRAPH_T2S = 1, GENIE_GRAPH_VITS = 2, GENIE_GRAPH_PROMPT_ENCODER = 3 };
+enum { GENIE_F32 = 0, GENIE_F16 = 1 };
+
+const char* genie_last_error(void);
+int genie_version(void);
+/* kernels launched by this library since load (bench.py: gpu_launches) */
+unsigned long long genie_launch_count(void);
+int genie_device_count(void);
+
+/* ---- model store: replaces ModelManager.load_character / load_session_with_fp16_conversion
+ * (src/genie_tts/ModelManager.py:59-114, 231-310).  The host side parses the .onnx
+ * initialiser tables and hands each tensor's bytes AS STORED (fp16 for the fp16 bins,
+ * fp32 for t2s_encoder_fp32.bin); nothing is up-cast on the host. */
+int genie_model_create(int device, genie_model** out);
+int genie_model_add_tensor(genie_model* m, int graph, const char* name, const void* host_data, int dtype,
+                           const int64_t* dims, int ndim);
+/* architecture constants that live in Constant nodes of the graphs:
+ * sinusoidal div_term (t2s_stage_decoder#[21]), top_k 15 (#[1788]), repetition penalty 1.35
+ * (#[1780]), temperature 1.0 (#[1786]), vocoder noise scale 0.5 (vits#[6494]) */
+int genie_model_set_constants(genie_model* m, const float* pe_div_term_256, int top_k, float repetition_penalty,
+                              float temperature, float noise_scale);
+/* folds weight-norm (vits#[6508-6510] x131, once instead of per call), repacks conv weights
+ * channels-last, builds per-layer tables.  V2 vs V2ProPlus is decided by the presence of
+ * prompt-encoder tensors (ModelManager.py:287-293). */
+int genie_model_finalize(genie_model* m);
+int genie_model_info(const genie_model* m, int* is_v2pp, long long* weight_bytes, long long* workspace_bytes);
+void genie_model_destroy(genie_model* m);
+
+/* ---- prompt: replaces the per-reference-audio work the reference redoes in every call:
+ * the VQ of ssl_content (t2s_encoder#[2-48]), the V2 ref_enc spectrogram path (vits#[3-271])
+ * or the V2ProPlus prompt_encoder graph (ReferenceAudio.py:68-76), plus ge-only conditioning.
+ *   ref_seq   int64[Lr]          ReferenceAudio.phonemes_seq
+ *   ref_bert  f32[Lr,1024]|NULL  ReferenceAudio.text_bert (NULL == zeros, ja/en)
+ *   ssl       f32[768,Ts]        ReferenceAudio.ssl_content[0]
+ *   ref_audio f32[n_audio]       ReferenceAudio.audio_32k[0]
+ *   sv_emb    f32[20480]|NULL    speaker-verification embedding (V2ProPlus only) */
+int genie_prompt_create(genie_model* m, const int64_t* ref_seq, int Lr, const float* ref_bert, const float* ssl,
+                        int Ts, const float* ref_audio, int n_audio, const float* sv_emb, genie_prompt** out);
+/* V2ProPlus alternative: global embeddings already computed (the reference's vits graph inputs
+ * `ge` f32[1024], `ge_advanced` f32[512]) */
+int genie_prompt_create_with_ge(genie_model* m, const int64_t* ref_seq, int Lr, const float* ref_bert,
+                                const float* ssl, int Ts, const float* ge, int ge_dim, const float* ge_advanced,
+                                genie_prompt** out);
+int genie_prompt_info(const genie_prompt* p, int* n_prompt_tokens, int* ge_dim, int* ref_len);
+/* prompts int64[n_prompt_tokens], ge f32[ge_dim], ge_advanced f32[512] (V2ProPlus) — any may be NULL */
+int genie_prompt_read(const genie_prompt* p, int64_t* prompts, float* ge, float* ge_advanced);
+void genie_prompt_destroy(genie_prompt* p);
+
+/* ---- T2S: replaces encoder.run + first_stage_decoder.run + <=500 x stage_decoder.run
+ * (src/genie_tts/Core/Inference.py:76-106) for a batch of independent utterances. */
+typedef struct genie_sampling {
+  int top_k;                  /* <=0: model constant (15) */
+  float temperature;          /* <=0: model constant (1.0) */
+  float repetition_penalty;   /* <=0: model constant (1.35) */
+  int greedy;                 /* 1: sampler noise == 1 (bit-comparable mode); 0: Philox N(0,1) */
+  unsigned long long seed;
+  int max_steps;              /* decode-loop bound, reference 500 (Inference.py:95); <=0: 500 */
+  int fixed_steps;            /* >0: ignore stop flags and run exactly this many loop iterations */
+} genie_sampling;
+
+/* text_seq: int64 concat over utterances (sum text_len); text_bert: f32 [sum text_len,1024] or NULL.
+ * Outputs (host unless io_on_device): y int64[B, y_ld] = prompt tokens followed by every generated
+ * token (the reference's `y` before `y[0,-1]=0; y[:, -idx:]`, Inference.py:108-109, which the host
+ * mirror applies), y_len[B] valid entries, idx[B] = value of the reference's loop variable at exit.
+ * cancel: optional host flag polled between decode steps (Inference.py:96-97); returns
+ * GENIE_CANCELLED. */
+#define GENIE_CANCELLED 2
+int genie_t2s_generate(genie_model* m, genie_prompt* const* prompts, int B, const int64_t* text_seq,
+                       const int* text_len, const float* text_bert, const genie_sampling* sampling,
+                       const volatile int* cancel, int io_on_device, int64_t* y, int y_ld, int* y_len, int* idx);
+
+/* ---- SoVITS: replaces vocoder.run (Inference.py:46-61) for a batch.
+ * sem: int64 concat of semantic tokens (sum sem_len, every id < 1024);
+ * zp_noise: f32 concat per utterance of [192, 2*sem_len[b]] (the graph's RandomNormalLike
+ * layout, vits#[6490]) or NULL -> Philox N(0,1) from `seed`; noise_scale < 0 -> model constant.
+ * audio: f32 concat, 1280 samples per semantic token; audio_len[B]. */
+int genie_vits_decode(genie_model* m, genie_prompt* const* prompts, int B, const int64_t* text_seq,
+                      const int* text_len, const int64_t* sem, const int* sem_len, const float* zp_noise,
+                      unsigned long long seed, float noise_scale, int io_on_device, float* audio, int* audio_len);
+
+/* ---- introspection for parity tests (host pointers only) */
+/* logits of the last T2S call: f32[B, n_steps+1, 1025] when recording was enabled */
+int genie_debug_record_logits(genie_model* m, int enable);
+int genie_debug_read_logits(genie_model* m, float* out, int max_floats, int* n_floats);
+/* intermediate tensors of the last T2S / VITS call by name ("x", "k0", "m_p", "z", ...) */
+int genie_debug_read(genie_model* m, const char* what, float* out, long long max_floats, long long* n_floats);
+int genie_debug_keep(genie_model* m, int enable);
+/* timing of the last call's stages in milliseconds (CUDA events): prefill, decode, total */
+int genie_last_timing(genie_model* m, float* ms, int n);
+/* use CUDA-graph replay for the decode step (default 1) */
+int genie_set_option(genie_model* m, const char* key, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENIE_B200_H */
