@@ -45,7 +45,9 @@ void run_convt(Model& m, const ConvT& c, const float* x, float* y, const Seg& in
     p.w_tap_stride = c.stride * tap_sz; p.bias = c.b; p.y = y; p.ldy = c.Cout;
     p.Cin = c.Cin; p.Cout = c.Cout; p.ntaps = ntaps; p.in_shift0 = 0; p.in_shift_step = -1;
     p.out_mul = c.stride; p.out_add = r - c.pad; p.pre_slope = pre_slope;
-    p.in_off = in.off; p.out_off = out.off; p.B = in.B; p.M = in.maxT; p.M_out = out.maxT; p.q_extra = 1;
+    // t_out = q*s + r - pad < T_in*s  =>  q <= T_in - 1 + floor((s - 1 + pad - r) / s)
+    p.in_off = in.off; p.out_off = out.off; p.B = in.B; p.M = in.maxT; p.M_out = out.maxT;
+    p.q_extra = (c.stride - 1 + c.pad - r) / c.stride;
     launch_conv_gemm(p, m.stream);
   }
 }
@@ -358,6 +360,7 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   {
     ConvOpt o; o.bias2 = DCOND; o.ldb2 = C0;
     run_conv(m, m.dec_pre, Z, 192, GX, C0, s2, o);
+    keep_tensor(m, "g_pre", GX, (long long)R2 * C0);
   }
   for (int i = 0; i < m.n_up; ++i) {
     const ConvT& U = m.ups[i];
@@ -381,6 +384,10 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
           run_conv(m, Rb.c2[c], GA, C, GX, C, S, b2);
         }
       }
+    }
+    if (m.keep) {
+      keep_tensor(m, ("g_up" + std::to_string(i)).c_str(), UP, (long long)S.rows * C);
+      keep_tensor(m, ("g_s" + std::to_string(i)).c_str(), GX, (long long)S.rows * C);
     }
   }
   float* AUD = ws.get<float>("v.audio", (size_t)R2 * 640);

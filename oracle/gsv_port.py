@@ -401,11 +401,13 @@ def flow_reverse(m: PortModel, z: torch.Tensor, g: torch.Tensor) -> torch.Tensor
     return z
 
 
-def generator(m: PortModel, z: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+def generator(m: PortModel, z: torch.Tensor, g: torch.Tensor, collect: Optional[dict] = None) -> torch.Tensor:
     """vits#[7822-8452] HiFi-GAN; z [192,T] -> audio [T*640]."""
     w = m.vits
     x = F.conv1d(z.unsqueeze(0), w["dec.conv_pre.weight"], w["dec.conv_pre.bias"], padding=3)
     x = x + (w["dec.cond.weight"][:, :, 0] @ g + w["dec.cond.bias"][:, None]).unsqueeze(0)
+    if collect is not None:
+        collect["g_pre"] = x[0].t().contiguous()
     n_up = sum(1 for k in w if k.startswith("dec.ups.") and k.endswith("weight_g"))
     for i in range(n_up):
         x = F.leaky_relu(x, 0.1)
@@ -427,13 +429,16 @@ def generator(m: PortModel, z: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
                 r = t + r
             xs = r if xs is None else xs + r
         x = xs / 3.0
+        if collect is not None:
+            collect[f"g_s{i}"] = xs[0].t().contiguous()
     x = F.leaky_relu(x, 0.01)                                            # #[8450]
     x = F.conv1d(x, w["dec.conv_post.weight"], None, padding=3)          # no bias, #[8451]
     return torch.tanh(x)[0, 0]
 
 
 def vits_decode(m: PortModel, text_seq, pred_semantic, ge: torch.Tensor, ge_advanced: Optional[torch.Tensor] = None,
-                zp_noise: Optional[torch.Tensor] = None, noise_scale: float = 0.5) -> np.ndarray:
+                zp_noise: Optional[torch.Tensor] = None, noise_scale: float = 0.5,
+                collect: Optional[dict] = None) -> np.ndarray:
     """vits#[273-8452] given the global embedding(s).  V2: ge [1,512,1] everywhere.
     V2ProPlus: MRTE gets ge_advanced [1,512,1]; flow and generator get ge [1,1024,1]."""
     codes = torch.as_tensor(pred_semantic).reshape(-1)
@@ -445,4 +450,6 @@ def vits_decode(m: PortModel, text_seq, pred_semantic, ge: torch.Tensor, ge_adva
     noise = torch.zeros_like(m_p) if zp_noise is None else torch.as_tensor(zp_noise).reshape(192, -1)[:, :m_p.shape[1]]
     z_p = m_p + noise * torch.exp(logs_p) * noise_scale                   # #[6490-6495]
     z = flow_reverse(m, z_p, g)
-    return generator(m, z, g).numpy()
+    if collect is not None:
+        collect["z"] = z.t().contiguous()
+    return generator(m, z, g, collect).numpy()

@@ -73,7 +73,10 @@ def run(version, fseed, pkw, tkw, steps):
     sem = sem[sem < 1024][:steps]
     zp = make_zp_noise(7, len(sem))
     audio = m.vits_decode([prompt], [tx["text_seq"]], [sem], [zp])[0]
-    ref_audio = P.vits_decode(pm, tx["text_seq"], sem, rge, rgea, zp_noise=torch.as_tensor(zp))
+    col = {}
+    ref_audio = P.vits_decode(pm, tx["text_seq"], sem, rge, rgea, zp_noise=torch.as_tensor(zp), collect=col)
+    for k in ("z", "g_pre", "g_s0", "g_s1", "g_s2", "g_s3", "g_s4"):
+        err(k, m.read_kept(k), col[k].numpy())
     # intermediate
     mp, logs = P.enc_p(pm, torch.as_tensor(sem), torch.as_tensor(tx["text_seq"]).reshape(-1),
                        (rgea if rgea is not None else rge).reshape(-1, 1))
