@@ -1,0 +1,237 @@
+"""CPU-only suite: oracle vs golden vectors, model-dir format, host logic, C-ABI exports."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from synth import make_prompt_inputs, make_text_inputs, make_zp_noise
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+PKG = os.path.join(ROOT, "genie-tts_b200")
+
+
+# ---------------------------------------------------------------- model-dir format
+def test_fixture_layout_matches_converter_sizes(v2_dir, v2pp_dir):
+    sz = lambda d, f: os.path.getsize(os.path.join(d, f))  # noqa: E731
+    assert sz(v2_dir, "t2s_shared_fp16.bin") == 153413634
+    assert sz(v2_dir, "vits_fp16.bin") == 80843520
+    assert sz(v2_dir, "t2s_encoder_fp32.bin") == 11465732
+    assert sz(v2pp_dir, "vits_fp16.bin") == 124345856
+    assert sz(v2pp_dir, "prompt_encoder_fp16.bin") == 44262912
+
+
+def test_weight_tables(v2_dir, v2pp_dir):
+    from genie_tts.weights import read_model_dir
+    t = read_model_dir(v2_dir)
+    assert not t.is_v2pp and len(t.t2s.tensors) == 291 and len(t.vits.tensors) == 668 and len(t.encoder.tensors) == 7
+    w = t.t2s["transformer_encoder.layers.3.self_attn.in_proj_weight"]
+    assert w.dtype == np.float16 and w.shape == (1536, 512)
+    assert t.encoder["encoder.bert_proj.weight"].dtype == np.float32
+    t2 = read_model_dir(v2pp_dir)
+    assert t2.is_v2pp and len(t2.vits.tensors) == 650 and len(t2.prompt_encoder.tensors) == 23
+    with pytest.raises(FileNotFoundError):
+        read_model_dir(os.path.join(v2_dir, "missing"))
+
+
+def test_weights_only_onnx_roundtrip(tmp_path):
+    from genie_tts.onnx_reader import load_model, write_weights_only_model
+    p = str(tmp_path / "w.onnx")
+    rows = [("a.weight", [3, 4], 1, "x.bin", 0, 48), ("b.bias", [5], 1, "x.bin", 48, 20)]
+    write_weights_only_model(p, rows)
+    m = load_model(p)
+    got = [(t.name, list(t.dims), t.data_type, t.external["location"], int(t.external["offset"]),
+            int(t.external["length"])) for t in m.graph.initializers]
+    assert got == [tuple(r) for r in rows] and all(t.is_external for t in m.graph.initializers)
+
+
+def test_reader_on_reference_graph_templates():
+    from fixture_models import have_templates, template_path
+    if not have_templates("v2"):
+        pytest.skip("reference graph templates not staged (oracle/_ref/graphs)")
+    from genie_tts.onnx_reader import load_model
+    m = load_model(template_path("v2", "t2s_stage_decoder_fp32"))
+    assert len(m.graph.nodes) == 1822 and len(m.graph.initializers) == 291 and m.opset == 20
+    assert [i.name for i in m.graph.inputs][:3] == ["iy", "iy_emb", "past_k_layer_0"]
+
+
+# ---------------------------------------------------------------- oracle pinned on golden vectors
+@pytest.mark.parametrize("case,ver", [("v2_small", "v2"), ("v2pp_small", "v2pp")])
+def test_port_matches_golden(case, ver, v2_dir, v2pp_dir):
+    """oracle/gsv_port.py (the travelling oracle) vs vectors produced by the reference's graph files."""
+    from oracle import gsv_port as P
+    from test_gpu_parity import CASES
+    d = v2pp_dir if ver == "v2pp" else v2_dir
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    pkw, tkw, steps = CASES[case]
+    pr, tx = make_prompt_inputs(**pkw), make_text_inputs(**tkw)
+    pm = P.PortModel(d)
+    r = P.t2s_generate(pm, pr["ref_seq"], pr["ref_bert"], tx["text_seq"], tx["text_bert"], pr["ssl_content"],
+                       max_steps=steps, keep_logits=True)
+    assert np.array_equal(r.y_full[0], g["y_full"]) and r.idx == int(g["idx"])
+    assert np.array_equal(r.tokens, g["tokens"])
+    assert np.abs(r.logits[0] - g["logits_first"]).max() < 1e-4
+    assert np.abs(r.logits[-1] - g["logits_last"]).max() < 1e-4
+    zp = make_zp_noise(pkw["seed"] + 100, steps + 2)
+    if pm.is_v2pp:
+        ge, gea = P.prompt_encoder_v2pp(pm, pr["ref_audio"], pr["sv_emb"])
+        assert np.abs(ge.numpy().reshape(-1) - g["ge"]).max() < 1e-4
+    else:
+        ge, gea = P.ref_enc_v2(pm, pr["ref_audio"]), None
+    audio = P.vits_decode(pm, tx["text_seq"], g["semantic"], ge, gea, zp_noise=torch.as_tensor(zp))
+    assert np.abs(audio - g["audio"]).max() < 1e-4
+
+
+def test_interpreter_reproduces_golden(v2_dir):
+    """The graph interpreter on the reference's own graph files regenerates the committed vectors."""
+    from fixture_models import have_templates
+    if not have_templates("v2"):
+        pytest.skip("reference graph templates not staged (oracle/_ref/graphs)")
+    from oracle import ref_pipeline as R
+    from test_gpu_parity import CASES
+    pkw, tkw, steps = CASES["v2_small"]
+    g = np.load(os.path.join(GOLD, "v2_small.npz"))
+    pr, tx = make_prompt_inputs(**pkw), make_text_inputs(**tkw)
+    s = R.load_sessions(v2_dir)
+    R.set_sampler_mode(s, greedy=True, zp_noise=make_zp_noise(pkw["seed"] + 100, steps + 2))
+    toks = R.t2s_cpu(s, pr["ref_seq"], pr["ref_bert"], tx["text_seq"], tx["text_bert"], pr["ssl_content"],
+                     max_steps=steps)
+    assert np.array_equal(toks, g["tokens"])
+    audio = R.vocode(s, tx["text_seq"], R.strip_eos(toks), ref_audio_32k=pr["ref_audio"])
+    assert np.abs(audio - g["audio"]).max() < 1e-5
+
+
+def test_sampler_semantics_of_port():
+    """stage#[1775-1821]: penalty once per distinct token from the raw logit; ties kept by top-k."""
+    from oracle.gsv_port import sample_token
+    lg = torch.zeros(1025)
+    lg[5], lg[7], lg[9] = 2.0, 2.0 * 1.35, -1.0
+    tok, stop = sample_token(lg.clone(), torch.tensor([7, 7, 7]))        # 7 penalised once -> 2.0, tie with 5
+    assert tok == 5 and not stop
+    lg2 = torch.zeros(1025); lg2[1024] = 9.0
+    assert sample_token(lg2, torch.tensor([0]))[1] is True
+
+
+# ---------------------------------------------------------------- host logic
+def test_loop_quirks_and_eos_strip():
+    from genie_tts.Core.Inference import finish_t2s, strip_eos
+    y = np.arange(100, 120)
+    assert finish_t2s(y, 0).shape == (1, 1, 20) and finish_t2s(y, 0)[0, 0, -1] == 0       # idx 0 -> whole y
+    assert finish_t2s(y, 5).tolist() == [[[115, 116, 117, 118, 0]]]
+    t = np.array([[[3, 4, 1024, 5, 1024]]])
+    assert strip_eos(t).tolist() == [[[3, 4]]]
+    assert strip_eos(np.array([[[3, 4]]])).tolist() == [[[3, 4]]]
+
+
+def test_utils_and_language():
+    from genie_tts.Utils.Language import normalize_language
+    from genie_tts.Utils.Utils import LRUCacheDict
+    assert normalize_language("JA") == "Japanese" and normalize_language("zh-CN") == "Chinese"
+    assert normalize_language("klingon") == "klingon"
+    c = LRUCacheDict(2)
+    c["a"], c["b"] = 1, 2
+    _ = c["a"]
+    c["c"] = 3
+    assert list(c.keys()) == ["a", "c"]
+
+
+def test_text_splitter():
+    from genie_tts.Utils.TextSplitter import TextSplitter
+    s = TextSplitter()
+    assert s.split("") == []
+    assert s.split("こんにちは。今日はいい天気ですね、散歩に行きましょう！はい") == \
+        ["こんにちは。", "今日はいい天気ですね、散歩に行きましょう！", "はい"]
+    assert s.split("a.b.c") == ["a.b.c"]                    # below min_len: merged
+
+
+def test_public_api_surface_and_errors(tmp_path):
+    import genie_tts as genie
+    for name in ["load_character", "unload_character", "set_reference_audio", "tts_async", "tts", "stop",
+                 "convert_to_onnx", "clear_reference_audio_cache", "start_server", "wait_for_playback_done",
+                 "load_predefined_character", "download_genie_data"]:           # reference __init__.py:16-29
+        assert callable(getattr(genie, name))
+    with pytest.raises(FileNotFoundError):
+        genie.load_character("x", str(tmp_path / "nope"), "ja")
+    (tmp_path / "empty").mkdir()
+    with pytest.raises(FileNotFoundError):
+        genie.load_character("x", str(tmp_path / "empty"), "ja")
+    with pytest.raises(ValueError):
+        genie.set_reference_audio("nobody", "a.wav", "text")      # no language, unknown character
+
+
+def test_product_fails_loudly_without_gpu(v2_dir):
+    from genie_tts import _native as N
+    if N.lib().genie_device_count() > 0:
+        pytest.skip("GPU present")
+    from genie_tts.engine import B200Model
+    with pytest.raises(N.GenieNativeError):
+        B200Model(v2_dir)
+    import genie_tts as genie
+    with pytest.raises(ValueError):
+        genie.load_character("c", v2_dir, "xx")
+    from genie_tts.ModelManager import model_manager
+    assert model_manager.load_character("c", v2_dir, "Japanese") is False      # logged, not raised (reference :304-309)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "gsv_port" in src or "onnx_interp" in src:
+                    bad.append(f)
+    assert not bad, bad
+
+
+# ---------------------------------------------------------------- C-ABI
+def test_cabi_exports_every_declared_symbol():
+    from genie_tts import _native as N
+    hdr = open(os.path.join(ROOT, "include", "genie_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(genie_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = N.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(N.SIGNATURES), declared ^ set(N.SIGNATURES)
+    assert lib.genie_version() >= 100
+
+
+# ---------------------------------------------------------------- multi-process (gloo, world_size 2)
+def test_partition_covers():
+    from genie_tts.dispatch import least_loaded, partition
+    for n in (0, 1, 7, 100):
+        for w in (1, 2, 3, 8):
+            spans = [partition(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    assert sorted(least_loaded([0, 0], [5, 4, 3, 2])) == [0, 0, 1, 1]
+
+
+def test_gloo_world_size_2_sharding(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {PKG!r})\n"
+        "from genie_tts.dispatch import partition\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "a, b = partition(101, w, r)\n"
+        "mine = torch.zeros(101); mine[a:b] = 1\n"
+        "dist.all_reduce(mine)\n"
+        "t = torch.tensor([float(b - a) * (r + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX)\n"
+        "assert bool((mine == 1).all()), 'shards must tile the request list exactly once'\n"
+        "assert t.item() == 100.0\n"
+        "dist.barrier(); print('ok', r)\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
