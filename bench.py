@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the GPT-SoVITS synthesis hot path (BASELINE.json metric: audio-sec/sec).
+
+Workload (BASELINE.json configs[1], README latency-set shape): GPT-SoVITS V2,
+random-init weights in the converter's on-disk layout, 100 Japanese-shaped
+sentences per GPU (ref 60 phones, target 40-60 phones, 264 HuBERT frames -> 132
+prompt tokens, fixed budget of 90 semantic tokens = 3.6 s audio each), synthetic
+inputs at the G2P/HuBERT boundary.  One step = one pass of the
+whole path (T2S encode + prefill + 90 decode steps with Philox sampling + SoVITS
+decode) over the batch.
+
+  value : whole-job audio-sec/sec with inputs resident in HBM (C-ABI io_on_device=1)
+  e2e   : same metric through the reference-facing call GENIE.tts_batch with HOST
+          numpy buffers (H2D of phoneme ids, D2H of tokens and float32 audio inside
+          the timed region)
+  --impl reference : the reference's own CPU path (its ONNX graph files executed
+          by oracle/onnx_interp.py over the restated host loop; falls back to the
+          torch port if the graphs were not staged) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "genie-tts_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "audio-sec/sec"
+N_SENT = 100
+TOKENS = 90
+WORKLOAD = "GPT-SoVITS V2, 100 sentences x ~20 chars (Lr=60, Lt~U{40..60}, 132 prompt tokens, 90-token budget), 1 B200"
+# algorithmic work (measured on the reference graphs)
+GEN_GFLOP_PER_AUDIO_S = 8.26 + 16.52 + 8.26 + 4.13 + 2.06 + 1.36   # HiFi-GAN stages 0-4 + ups
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def make_workload(n_sent, seed0=1234):
+    from synth import make_prompt_inputs, make_text_inputs
+    pr = make_prompt_inputs(seed=seed0, Lr=60, Ts=264, n_audio=169600)
+    rng = np.random.default_rng(seed0 + 1)
+    texts = [make_text_inputs(seed=seed0 + 10 + i, Lt=int(rng.integers(40, 61))) for i in range(n_sent)]
+    return pr, texts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_step(pr, tx, sessions_or_port, kind, tokens):
+    """One sentence through the reference CPU path; returns audio seconds produced."""
+    import torch
+    if kind == "reference":
+        from oracle import ref_pipeline as R
+        s = sessions_or_port
+        toks = R.t2s_cpu(s, pr["ref_seq"], pr["ref_bert"], tx["text_seq"], tx["text_bert"], pr["ssl_content"],
+                         max_steps=tokens)
+        sem = R.strip_eos(toks)
+        sem = np.where(sem >= 1024, 0, sem)
+        audio = R.vocode(s, tx["text_seq"], sem, ref_audio_32k=pr["ref_audio"])
+    else:
+        from oracle import gsv_port as P
+        pm = sessions_or_port
+        r = P.t2s_generate(pm, pr["ref_seq"], pr["ref_bert"], tx["text_seq"], tx["text_bert"], pr["ssl_content"],
+                           max_steps=tokens, force_tokens=tokens,
+                           noise_fn=lambda i: torch.randn(1025))
+        sem = r.tokens.reshape(-1)
+        sem = sem[sem < 1024]
+        audio = P.vits_decode(pm, tx["text_seq"], sem, P.ref_enc_v2(pm, pr["ref_audio"]), None,
+                              zp_noise=torch.randn(1, 192, 2 * len(sem)))
+    return len(audio) / 32000.0
+
+
+def load_cpu_reference(model_dir):
+    import torch
+    from fixture_models import have_templates
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if have_templates("v2") and os.path.getsize(os.path.join(model_dir, "vits_fp32.onnx")) > 100000:
+        from oracle import ref_pipeline as R
+        s = R.load_sessions(model_dir)
+        R.set_sampler_mode(s, greedy=False)
+        return s, "reference"
+    from oracle import gsv_port as P
+    return P.PortModel(model_dir), "port"
+
+
+def run_reference_arm(args, model_dir, rank):
+    import torch
+    if rank != 0:
+        return
+    pr, texts = make_workload(4)
+    obj, kind = load_cpu_reference(model_dir)
+    cores = torch.get_num_threads()
+    sample = (f"1 sentence of the workload per step ({TOKENS}-token budget, batch 1: the reference path is "
+              f"single-stream by construction), {'reference ONNX graphs on the torch-CPU interpreter' if kind == 'reference' else 'torch port'}"
+              " (onnxruntime 1.22.1 unavailable offline)")
+    for i in range(args.warmup):
+        cpu_reference_step(pr, texts[i % len(texts)], obj, kind, TOKENS)
+    t0 = time.perf_counter()
+    audio_s = 0.0
+    for i in range(args.steps):
+        audio_s += cpu_reference_step(pr, texts[i % len(texts)], obj, kind, TOKENS)
+    dt = time.perf_counter() - t0
+    v = audio_s / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sentences", type=int, default=N_SENT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from conftest import fixture_dir
+    # rank 0 writes the fixture once; other ranks wait on the marker
+    if local_rank == 0:
+        model_dir = fixture_dir("v2", 0)
+    else:
+        from conftest import FIXTURE_ROOT
+        model_dir = os.path.join(FIXTURE_ROOT, "v2_seed0")
+        while not os.path.exists(os.path.join(model_dir, ".complete")):
+            time.sleep(0.5)
+
+    if args.impl == "reference":
+        run_reference_arm(args, model_dir, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from genie_tts import _native as N
+    from genie_tts.Core.Inference import GENIE, finish_t2s, strip_eos
+    from genie_tts.engine import B200Model, SamplingParams
+    N.require_gpu()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = B200Model(model_dir, device=local_rank)
+    pr, texts = make_workload(args.sentences, seed0=1234 + 1000 * rank)
+    prompt = model.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"])   # untimed
+    B = len(texts)
+    prompts = [prompt] * B
+    seqs = [t["text_seq"].reshape(-1) for t in texts]
+    lens = np.asarray([len(s) for s in seqs], dtype=np.int32)
+    sp = SamplingParams(greedy=False, seed=2026, max_steps=TOKENS, fixed_steps=TOKENS)
+    genie = GENIE()
+
+    # ---- device-resident leg
+    dev = torch.device("cuda", local_rank)
+    seq_dev = torch.from_numpy(np.concatenate(seqs)).to(dev)
+    y_ld = prompt.n_prompt_tokens + TOKENS + 2
+    y_dev = torch.zeros((B, y_ld), dtype=torch.int64, device=dev)
+    audio_dev = torch.zeros(B * TOKENS * 1280, dtype=torch.float32, device=dev)
+    stage_ms = {"prefill": [], "decode": [], "vits": [], "generator": []}
+
+    def step_device():
+        y_len, idx = model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev)
+        t = model.last_timing()
+        # host glue of the reference (Inference.py:41-44,108-109) on the small token matrix
+        y = y_dev.cpu().numpy()
+        sems = [strip_eos(finish_t2s(y[b, :y_len[b]], int(idx[b]))).reshape(-1) for b in range(B)]
+        sems = [s if len(s) else np.zeros(1, np.int64) for s in sems]
+        sl = np.asarray([len(s) for s in sems], dtype=np.int32)
+        sem_dev = torch.from_numpy(np.concatenate(sems)).to(dev)
+        alen = model.vits_decode_device(prompts, seq_dev, lens, sem_dev, sl, audio_dev, seed=sp.seed)
+        t2 = model.last_timing()
+        stage_ms["prefill"].append(t["prefill_ms"]); stage_ms["decode"].append(t["decode_ms"])
+        stage_ms["vits"].append(t2["vits_ms"]); stage_ms["generator"].append(t2["generator_ms"])
+        return float(alen.sum()) / 32000.0, t2
+
+    def step_host():
+        auds = genie.tts_batch(model, prompts, seqs, None, sampling=sp)
+        return sum(len(a) for a in auds) / 32000.0, sum(a.nbytes for a in auds)
+
+    for _ in range(args.warmup):
+        step_device()
+    for k in stage_ms:
+        stage_ms[k].clear()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = N.lib().genie_launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    audio_s = 0.0
+    last_t = None
+    for _ in range(args.steps):
+        a, last_t = step_device()
+        audio_s += a
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = N.lib().genie_launch_count() - launches0
+    clk = clocks.stop()
+
+    # ---- e2e leg (host buffers through the reference-facing call)
+    step_host()
+    barrier()
+    t1 = time.perf_counter()
+    e_audio, d2h = 0.0, 0
+    for _ in range(args.steps):
+        a, nb = step_host()
+        e_audio += a
+        d2h = nb + B * y_ld * 8
+    barrier()
+    dt_e = time.perf_counter() - t1
+
+    tt = torch.tensor([dt, dt_e], dtype=torch.float64, device=dev)
+    aa = torch.tensor([audio_s, e_audio], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(aa, op=dist.ReduceOp.SUM)
+    dt, dt_e = tt.tolist()
+    audio_s, e_audio = aa.tolist()
+
+    if rank == 0:
+        hbm_peak, tf_peak, which = peaks()
+        gen_ms = float(np.mean(stage_ms["generator"]))
+        audio_per_step = audio_s / args.steps / world
+        gen_flops = GEN_GFLOP_PER_AUDIO_S * 1e9 * audio_per_step
+        n_gen = max(1, last_t["generator_launches"])
+        achieved = gen_flops / (gen_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sentences_per_gpu": B, "tokens_per_sentence": TOKENS,
+                       "sampling": "top_k=15 T=1.0 rep=1.35 Philox", "l2": "working set (KV cache, vocoder "
+                       "activations) >> 126 MB L2, no explicit flush", "parallelism": f"dp{world} by utterance"},
+            "e2e": {"value": e_audio / dt_e, "unit": "audio-s/s",
+                    "h2d_bytes_per_step": int(sum(s.nbytes for s in seqs) + lens.nbytes),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "t2s_tokens_per_s": world * B * TOKENS * args.steps / (np.sum(stage_ms["decode"]) * 1e-3) / 1.0
+            if stage_ms["decode"] else None,
+            "stage_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (HiFi-GAN generator convs, fp32 SIMT)",
+                         "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                         "peak_source": which, "launches_per_step": n_gen,
+                         "avg_launch_ms": gen_ms / n_gen, "traffic": None},
+        }
+        if not args.no_cpu_baseline:
+            obj, kind = load_cpu_reference(model_dir)
+            tcpu = time.perf_counter()
+            a = cpu_reference_step(pr, texts[0], obj, kind, TOKENS)
+            dcpu = time.perf_counter() - tcpu
+            line["cpu_baseline"] = {"value": a / dcpu, "unit": "audio-s/s", "cores": torch.get_num_threads(),
+                                    "kind": kind, "sample": f"1 sentence ({TOKENS} tokens, batch 1), {dcpu:.1f} s of CPU work"}
+        print(json.dumps(line))
+    prompt.close()
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,9 +26,18 @@ struct Error { std::string msg; };
     if (!(cond)) throw ::genie::Error{std::string(msg) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"}; \
   } while (0)
 
+extern int g_sync_debug;   // GENIE_SYNC_DEBUG=1: synchronise after every launch and name the failing kernel
 inline void check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw Error{std::string(what) + " launch failed: " + cudaGetErrorString(e)};
+  if (g_sync_debug) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaError_t e2 = cudaDeviceSynchronize();
+    if (e2 != cudaSuccess && e2 != cudaErrorStreamCaptureUnsupported)
+      throw Error{std::string(what) + " failed at run time: " + cudaGetErrorString(e2)};
+    (void)st;
+    cudaGetLastError();
+  }
 }
 
 // global kernel-launch counter (bench.py reports it as gpu_launches)

@@ -109,7 +109,7 @@ struct Model {
   Workspace ws;
   // decode-step CUDA graph cache
   cudaGraphExec_t step_graph = nullptr; int step_graph_B = 0; unsigned long long step_graph_gen = 0;
-  int step_graph_cap = 0; int step_graph_flags = 0;
+  int step_graph_cap = 0; int step_graph_flags = 0; int step_graph_hist_ld = 0;
   unsigned long long step_graph_seed = 0; float step_graph_temp = 0.f, step_graph_pen = 0.f;
   int use_graph = 1;
   // debug

@@ -126,10 +126,9 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   // ---- host-built index metadata, one upload
   //   txt_pos[txt_rows] | row2utt[R] | aud_pos[R] (per audio row; text rows unused) | per-utt arrays
   std::vector<int> meta((size_t)R * 2 + bt.txt_rows + 8 * (B + 1), 0);
-  int* h_txt_pos = meta.data();
-  int* h_row2utt = h_txt_pos + bt.txt_rows;
-  int* h_aud_tok_pos = h_row2utt + R;           // position (1-based) of audio rows, compacted per utterance
-  int* h_row_off = h_aud_tok_pos + R;           // [B+1]
+  // per-utterance state first: its device addresses (baked into the decode-step graph) then
+  // depend only on the buffer base and B, not on this call's row counts
+  int* h_row_off = meta.data();                 // [B+1]
   int* h_lx = h_row_off + (B + 1);              // [B]
   int* h_zero = h_lx + (B + 1);                 // [B] zeros (dst_pos0 for prefill scatter)
   int* h_kvlen = h_zero + (B + 1);              // [B]
@@ -137,6 +136,9 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   int* h_active = h_histlen + (B + 1);          // [B]
   int* h_stop = h_active + (B + 1);             // [B]
   int* h_ly = h_stop + (B + 1);                 // [B]
+  int* h_txt_pos = h_ly + (B + 1);
+  int* h_row2utt = h_txt_pos + bt.txt_rows;
+  int* h_aud_tok_pos = h_row2utt + R;           // position (1-based) of audio rows
   for (int b = 0; b < B; ++b) {
     for (int i = 0; i < bt.Lx[b]; ++i) h_txt_pos[bt.txt_off[b] + i] = i + 1;
     for (int i = 0; i < bt.S[b]; ++i) h_row2utt[bt.row_off[b] + i] = b;
@@ -146,10 +148,10 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   }
   h_row_off[B] = R;
   GENIE_CUDA(cudaMemcpyAsync(IMETA, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-  int* d_txt_pos = IMETA; int* d_row2utt = d_txt_pos + bt.txt_rows; int* d_aud_pos = d_row2utt + R;
-  int* d_row_off = d_aud_pos + R; int* d_lx = d_row_off + (B + 1); int* d_zero = d_lx + (B + 1);
+  int* d_row_off = IMETA; int* d_lx = d_row_off + (B + 1); int* d_zero = d_lx + (B + 1);
   int* d_kvlen = d_zero + (B + 1); int* d_histlen = d_kvlen + (B + 1); int* d_active = d_histlen + (B + 1);
   int* d_stop = d_active + (B + 1); int* d_ly = d_stop + (B + 1);
+  int* d_txt_pos = d_ly + (B + 1); int* d_row2utt = d_txt_pos + bt.txt_rows; int* d_aud_pos = d_row2utt + R;
 
   cudaEvent_t ev0, ev1, ev2;
   GENIE_CUDA(cudaEventCreate(&ev0)); GENIE_CUDA(cudaEventCreate(&ev1)); GENIE_CUDA(cudaEventCreate(&ev2));
@@ -264,10 +266,10 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
 
   // the graph bakes pointers and scalar args; re-capture when any of them changes
   const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (cfg.top_k << 4);
-  const bool can_graph = m.use_graph && !m.record_logits;
+  const bool can_graph = m.use_graph && !m.record_logits && !g_sync_debug;
   if (can_graph) {
     bool stale = !m.step_graph || m.step_graph_B != B || m.step_graph_gen != ws.generation ||
-                 m.step_graph_cap != bt.cap || m.step_graph_flags != flags;
+                 m.step_graph_cap != bt.cap || m.step_graph_flags != flags || m.step_graph_hist_ld != bt.hist_ld;
     // seed / temperature / penalty are baked too: fold them into staleness via a cheap hash
     if (m.step_graph_seed != cfg.seed || m.step_graph_temp != cfg.temperature || m.step_graph_pen != cfg.penalty)
       stale = true;
@@ -287,7 +289,7 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       g_launches = launches_before;            // capture does not launch
       GENIE_CUDA(cudaGraphInstantiate(&m.step_graph, g, 0));
       cudaGraphDestroy(g);
-      m.step_graph_B = B; m.step_graph_gen = ws.generation; m.step_graph_cap = bt.cap; m.step_graph_flags = flags;
+      m.step_graph_B = B; m.step_graph_gen = ws.generation; m.step_graph_cap = bt.cap; m.step_graph_flags = flags; m.step_graph_hist_ld = bt.hist_ld;
       m.step_graph_seed = cfg.seed; m.step_graph_temp = cfg.temperature; m.step_graph_pen = cfg.penalty;
     }
   }

@@ -224,6 +224,9 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   cudaStream_t s = m.stream;
   Workspace& ws = m.ws;
   if (noise_scale < 0.f) noise_scale = m.noise_scale;
+  cudaEvent_t ev0, ev1, ev2;
+  GENIE_CUDA(cudaEventCreate(&ev0)); GENIE_CUDA(cudaEventCreate(&ev1)); GENIE_CUDA(cudaEventCreate(&ev2));
+  GENIE_CUDA(cudaEventRecord(ev0, s));
   const cudaMemcpyKind in_kind = io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 
   // ---- segment tables: latent rows (2 per token), text rows, and the 5 generator stages
@@ -353,6 +356,8 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   const size_t gen_floats = (size_t)R2 * 640 * m.c_last;   // every stage output has R2*10240 (V2) floats at most
   const size_t s0_floats = (size_t)R2 * C0;
   float* GX = ws.get<float>("v.gx", std::max(gen_floats, s0_floats));    // running stage input / xs
+  GENIE_CUDA(cudaEventRecord(ev1, s));
+  const unsigned long long launches_before_gen = g_launches;
   float* UP = ws.get<float>("v.up", gen_floats);
   float* GA = ws.get<float>("v.ga", gen_floats);
   float* GB = ws.get<float>("v.gb", gen_floats);
@@ -392,10 +397,16 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   }
   float* AUD = ws.get<float>("v.audio", (size_t)R2 * 640);
   launch_conv_post_tanh(GX, m.c_last, m.conv_post, AUD, sg[5].off, B, sg[5].maxT, s);
+  GENIE_CUDA(cudaEventRecord(ev2, s));
+  const unsigned long long gen_launches = g_launches - launches_before_gen;
   if (audio)
     GENIE_CUDA(cudaMemcpyAsync(audio, AUD, (size_t)R2 * 640 * 4, io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   GENIE_CUDA(cudaStreamSynchronize(s));
   if (audio_len) for (int b = 0; b < B; ++b) audio_len[b] = sem_len[b] * 1280;
+  float t01 = 0.f, t12 = 0.f;
+  cudaEventElapsedTime(&t01, ev0, ev1); cudaEventElapsedTime(&t12, ev1, ev2);
+  m.timing[4] = t01 + t12; m.timing[5] = t12; m.timing[6] = (float)gen_launches; m.timing[7] = (float)R2;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
 }
 
 }  // namespace genie

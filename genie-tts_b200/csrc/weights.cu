@@ -5,10 +5,12 @@
 // weights are weight-norm-folded once (the reference redoes vits#[6508-6510] x131
 // in every call) and repacked [Cout][k][Cin] for channels-last implicit GEMM.
 #include "model.h"
+#include <cstdlib>
 
 namespace genie {
 
 unsigned long long g_launches = 0;
+int g_sync_debug = []() { const char* e = getenv("GENIE_SYNC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
 
 Model::~Model() {
   if (step_graph) cudaGraphExecDestroy(step_graph);

@@ -170,14 +170,40 @@ class B200Model:
         audio = np.zeros(int(sl.sum()) * 1280, dtype=np.float32)
         alen = np.zeros(B, dtype=np.int32)
         hs = (C.c_void_p * B)(*[p._h for p in prompts])
-        N.check(N.lib().genie_vits_decode(self._h, hs, B, _ptr(np.concatenate(seqs)), _ptr(tl),
-                                          _ptr(np.concatenate(sems)), _ptr(sl), _ptr(noise), seed & (2 ** 64 - 1),
+        seq_cat, sem_cat = np.concatenate(seqs), np.concatenate(sems)   # keep alive across the call
+        N.check(N.lib().genie_vits_decode(self._h, hs, B, _ptr(seq_cat), _ptr(tl),
+                                          _ptr(sem_cat), _ptr(sl), _ptr(noise), seed & (2 ** 64 - 1),
                                           noise_scale, 0, _ptr(audio), _ptr(alen)))
         out, o = [], 0
         for b in range(B):
             out.append(audio[o:o + alen[b]].copy())
             o += alen[b]
         return out
+
+    # -- device-resident payload variants (bench `value` leg: inputs/outputs stay in HBM) ------
+    def t2s_generate_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sampling: SamplingParams, y_out):
+        """text_seq_cat: int64 CUDA tensor (concat); y_out: int64 CUDA tensor [B, y_ld].  Lengths and the
+        small per-utterance results (y_len, idx) are host metadata."""
+        B = len(prompts)
+        lens = np.ascontiguousarray(text_lens, dtype=np.int32)
+        y_len = np.zeros(B, dtype=np.int32)
+        idx = np.zeros(B, dtype=np.int32)
+        hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        csp = sampling.to_c()
+        N.check(N.lib().genie_t2s_generate(self._h, hs, B, _ptr(text_seq_cat), _ptr(lens), None, C.byref(csp), None,
+                                           1, _ptr(y_out), int(y_out.shape[1]), _ptr(y_len), _ptr(idx)))
+        return y_len, idx
+
+    def vits_decode_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sem_cat, sem_lens: np.ndarray,
+                           audio_out, seed: int = 0) -> np.ndarray:
+        B = len(prompts)
+        tl = np.ascontiguousarray(text_lens, dtype=np.int32)
+        sl = np.ascontiguousarray(sem_lens, dtype=np.int32)
+        alen = np.zeros(B, dtype=np.int32)
+        hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        N.check(N.lib().genie_vits_decode(self._h, hs, B, _ptr(text_seq_cat), _ptr(tl), _ptr(sem_cat), _ptr(sl), None,
+                                          seed & (2 ** 64 - 1), -1.0, 1, _ptr(audio_out), _ptr(alen)))
+        return alen
 
     # -- debug ------------------------------------------------------------------
     def record_logits(self, enable: bool) -> None:
@@ -203,7 +229,9 @@ class B200Model:
     def last_timing(self) -> dict:
         t = np.zeros(8, dtype=np.float32)
         N.check(N.lib().genie_last_timing(self._h, _ptr(t), 8))
-        return {"prefill_ms": float(t[0]), "decode_ms": float(t[1]), "t2s_ms": float(t[2]), "steps": int(t[3])}
+        return {"prefill_ms": float(t[0]), "decode_ms": float(t[1]), "t2s_ms": float(t[2]), "steps": int(t[3]),
+                "vits_ms": float(t[4]), "generator_ms": float(t[5]), "generator_launches": int(t[6]),
+                "latent_rows": int(t[7])}
 
 
 class B200Prompt:
