@@ -240,6 +240,17 @@ int genie_debug_read(genie_model* h, const char* what, float* out, long long max
     return 0;
   });
 }
+namespace genie {
+void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err, float* ref_max);
+}
+int genie_debug_tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err,
+                            float* ref_max) {
+  return guarded([&] {
+    GENIE_CHECK(max_err && ref_max, "null argument");
+    tc_selftest(M, Cin, Cout, ntaps, dil, mode, exact_w, max_err, ref_max);
+    return 0;
+  });
+}
 int genie_last_timing(genie_model* h, float* ms, int n) {
   if (!h || !ms) return 1;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->m.timing[i];
@@ -248,6 +259,9 @@ int genie_last_timing(genie_model* h, float* ms, int n) {
 int genie_set_option(genie_model* h, const char* key, int value) {
   if (!h || !key) return 1;
   if (std::strcmp(key, "use_graph") == 0) { h->m.use_graph = value; return 0; }
+  if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
+  if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
+  if (std::strcmp(key, "tc_min_rows") == 0) { h->m.tc_min_rows = value; h->m.step_graph_flags = -1; return 0; }
   g_err = std::string("unknown option ") + key;
   return 1;
 }

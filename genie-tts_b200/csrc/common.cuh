@@ -73,8 +73,16 @@ struct ConvGemm {
   const int* in_off = nullptr; const int* out_off = nullptr;
   int B = 1; int M = 0; int M_out = 0;         // M: max #q per segment (grid sizing); single-segment row counts
   int q_extra = 0;                             // q ranges over [0, T_in + q_extra)
+  // tcgen05 path (tc_gemm.cu): weights pre-packed as fp16 [Cout][tc_kpad], K index = tap*Cin + ci,
+  // zero padded to a multiple of 64; optional low part (w - fp16(w)); tc_split_a: x = x_hi + x_lo
+  const __half* tc_w = nullptr; const __half* tc_wlo = nullptr; int tc_kpad = 0; int tc_split_a = 0;
+  int tc_nt = 0;                               // force the N tile (0 = by Cout)
+  // split-K: CTA (n-tile, ks) reduces k-blocks [ks*KB/ksplit, (ks+1)*KB/ksplit) and stores the raw partial
+  // at y + ks*split_stride; bias / residual / activation are then applied by the consumer (layernorm)
+  int ksplit = 1; long long split_stride = 0;
 };
 void launch_conv_gemm(const ConvGemm& p, cudaStream_t s);
+void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // attention

@@ -8,9 +8,12 @@ namespace {
 inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 // ---- LayerNorm (+residual), one warp per row --------------------------------
+// x may be `nsplit` split-K partial sums `split_stride` floats apart; `lin_bias` is the producing
+// linear layer's bias (deferred from the split-K GEMM epilogue)
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                  const float* __restrict__ g, const float* __restrict__ b,
-                                 float* __restrict__ y, int rows, int C) {
+                                 float* __restrict__ y, int rows, int C, int nsplit, long long split_stride,
+                                 const float* __restrict__ lin_bias) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -23,6 +26,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   for (int i = 0; i < 32; ++i) {
     if (i < n) {
       float t = xr[lane + 32 * i];
+      for (int sp = 1; sp < nsplit; ++sp) t += xr[sp * split_stride + lane + 32 * i];
+      if (lin_bias) t += lin_bias[lane + 32 * i];
       if (rr) t += rr[lane + 32 * i];
       v[i] = t; sum += t;
     }
@@ -285,10 +290,10 @@ __global__ void transpose_kernel(const float* src, int rows, int cols, float* ds
 }  // namespace
 
 void launch_layernorm(const float* x, const float* res, const float* g, const float* b, float* y, int rows, int C,
-                      cudaStream_t s) {
+                      cudaStream_t s, int nsplit, long long split_stride, const float* lin_bias) {
   if (rows <= 0) return;
   GENIE_CHECK(C % 32 == 0 && C <= 1024, "layernorm: bad C");
-  layernorm_kernel<<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, C);
+  layernorm_kernel<<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, C, nsplit, split_stride, lin_bias);
   GENIE_LAUNCHED("layernorm");
 }
 void launch_text_embed_pe(float* x, const long long* seq, const int* pos, const float* emb, const float* alpha,

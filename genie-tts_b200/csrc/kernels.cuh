@@ -9,8 +9,10 @@ void launch_decode_attention_raw(const float* q, float* o, const float* kv_base,
                                  int B, int cap, float scale, int t_add, cudaStream_t s);
 
 // y[r,:] = LN(x[r,:] (+ res[r,:])) * g + b   (eps 1e-5), C multiple of 32, C <= 1024
+// x may be nsplit split-K partials (split_stride apart) with the producer's bias deferred to here
 void launch_layernorm(const float* x, const float* res, const float* g, const float* b, float* y,
-                      int rows, int C, cudaStream_t s);
+                      int rows, int C, cudaStream_t s, int nsplit = 1, long long split_stride = 0,
+                      const float* lin_bias = nullptr);
 
 // x[r,:] += emb[seq[r],:] + alpha * PE(pos[r])     (text rows; pos is 1-based per utterance)
 void launch_text_embed_pe(float* x, const long long* seq, const int* pos, const float* emb, const float* alpha,

@@ -32,14 +32,17 @@ struct RawTensor {
   void* d = nullptr; int f16 = 0; std::vector<int64_t> dims; long long numel = 0;
 };
 
+// tcgen05 operand: fp16 [Cout][kpad] (K = tap*Cin + ci, zero padded to x64) + optional low part
+struct TcW { const __half* hi = nullptr; const __half* lo = nullptr; int kpad = 0; };
 struct Linear {            // y = x W^T + b ; W [N,K] row-major
-  const void* w = nullptr; int w_f16 = 0; const float* b = nullptr; int N = 0, K = 0;
+  const void* w = nullptr; int w_f16 = 0; const float* b = nullptr; int N = 0, K = 0; TcW tc;
 };
 struct Conv {              // repacked [Cout][k][Cin] fp32 (weight-norm folded)
-  const float* w = nullptr; const float* b = nullptr; int Cout = 0, Cin = 0, k = 1;
+  const float* w = nullptr; const float* b = nullptr; int Cout = 0, Cin = 0, k = 1; TcW tc;
 };
 struct ConvT {             // repacked [k][Cout][Cin] fp32
   const float* w = nullptr; const float* b = nullptr; int Cout = 0, Cin = 0, k = 0, stride = 0, pad = 0;
+  TcW tc[10];              // one packed matrix per output phase r = (t_out + pad) mod stride
 };
 
 struct T2SLayer {
@@ -112,6 +115,10 @@ struct Model {
   int step_graph_cap = 0; int step_graph_flags = 0; int step_graph_hist_ld = 0;
   unsigned long long step_graph_seed = 0; float step_graph_temp = 0.f, step_graph_pen = 0.f;
   int use_graph = 1;
+  // tcgen05 path: 0 = exact SIMT everywhere; T2S always runs x_hi+x_lo against fp16-exact weights;
+  // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo
+  int use_tc = 1, tc_vits = 1, tc_min_rows = 9;
+  int* tc_err = nullptr;
   // debug
   bool record_logits = false, keep = false;
   std::vector<float> logits_host;
@@ -153,8 +160,10 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
 
 // helpers shared by the stage files
 void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, int ldy, int M, int act = ACT_NONE,
-                const float* res = nullptr, int ldr = 0);
+                const float* res = nullptr, int ldr = 0, int nt = 0, int ksplit = 1, long long split_stride = 0);
+inline bool tc_linear_ok(const Model& m, const Linear& L, int M) { return m.use_tc && L.tc.hi && M >= m.tc_min_rows; }
 void keep_tensor(Model& m, const char* name, const float* dev, long long n);
+void check_tc_error(Model& m);
 template <typename T> T* dev_alloc(std::vector<void*>& owned, size_t count) {
   void* p = nullptr;
   GENIE_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));

@@ -34,7 +34,7 @@ __global__ void hist_to_i64_kernel(const int* hist, int hist_ld, const int* hist
 }
 
 struct StepBufs {
-  float *h, *qkv, *att, *tmp, *h1, *ff, *logits;
+  float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part;
   int *hist, *hist_len, *kv_len, *active, *stop_step;
   float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld;
 };
@@ -46,16 +46,28 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   const float scale = 1.0f / std::sqrt(32.0f);
   for (int l = 0; l < NL; ++l) {
     const T2SLayer& L = m.layers[l];
-    run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B);
+    // tcgen05 path for a small batch: 64-wide N tiles and split-K spread each GEMM over more SMs; the
+    // split-K partials, the linear bias and the residual are summed inside the following LayerNorm
+    const bool tc = tc_linear_ok(m, L.out, B) && B <= 128;
+    const long long ps = (long long)B * D;
+    run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B, ACT_NONE, nullptr, 0, tc ? 64 : 0);
     launch_kv_scatter(w.qkv, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap, nullptr, w.kv_len,
                       nullptr, B, w.active, s);
     launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
                                 w.active, B, w.cap, scale, /*t_add=*/1, s);
-    run_linear(m, L.out, w.att, D, w.tmp, D, B, ACT_NONE, w.h, D);
-    launch_layernorm(w.tmp, nullptr, L.ln1_g, L.ln1_b, w.h1, B, D, s);
-    run_linear(m, L.ff1, w.h1, D, w.ff, 4 * D, B, ACT_RELU);
-    run_linear(m, L.ff2, w.ff, 4 * D, w.tmp, D, B, ACT_NONE, w.h1, D);
-    launch_layernorm(w.tmp, nullptr, L.ln2_g, L.ln2_b, w.h, B, D, s);
+    if (tc) {
+      run_linear(m, L.out, w.att, D, w.part, D, B, ACT_NONE, nullptr, 0, 64, 4, ps);
+      launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 4, ps, L.out.b);
+      run_linear(m, L.ff1, w.h1, D, w.ff, 4 * D, B, ACT_RELU, nullptr, 0, 64);
+      run_linear(m, L.ff2, w.ff, 4 * D, w.part, D, B, ACT_NONE, nullptr, 0, 64, 8, ps);
+      launch_layernorm(w.part, w.h1, L.ln2_g, L.ln2_b, w.h, B, D, s, 8, ps, L.ff2.b);
+    } else {
+      run_linear(m, L.out, w.att, D, w.tmp, D, B, ACT_NONE, w.h, D);
+      launch_layernorm(w.tmp, nullptr, L.ln1_g, L.ln1_b, w.h1, B, D, s);
+      run_linear(m, L.ff1, w.h1, D, w.ff, 4 * D, B, ACT_RELU);
+      run_linear(m, L.ff2, w.ff, 4 * D, w.tmp, D, B, ACT_NONE, w.h1, D);
+      launch_layernorm(w.tmp, nullptr, L.ln2_g, L.ln2_b, w.h, B, D, s);
+    }
   }
   run_linear(m, m.predict, w.h, D, w.logits, V, B);
   SamplerArgs a{};
@@ -260,12 +272,14 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   w.h = ws.get<float>("t2s.step.h", (size_t)B * D); w.qkv = ws.get<float>("t2s.step.qkv", (size_t)B * 3 * D);
   w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
   w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
+  w.part = ws.get<float>("t2s.step.part", (size_t)8 * B * D);
   w.logits = LOGITS; w.hist = HIST; w.hist_len = d_histlen; w.kv_len = d_kvlen; w.active = d_active;
   w.stop_step = d_stop; w.kv = KV; w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off;
   w.cap = bt.cap; w.hist_ld = bt.hist_ld;
 
   // the graph bakes pointers and scalar args; re-capture when any of them changes
-  const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (cfg.top_k << 4);
+  const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (m.use_tc ? 4 : 0) | (cfg.top_k << 4) |
+                    (m.tc_min_rows << 16);
   const bool can_graph = m.use_graph && !m.record_logits && !g_sync_debug;
   if (can_graph) {
     bool stale = !m.step_graph || m.step_graph_B != B || m.step_graph_gen != ws.generation ||
@@ -329,6 +343,7 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
                                  io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   }
   GENIE_CUDA(cudaStreamSynchronize(s));
+  check_tc_error(m);
   for (int b = 0; b < B; ++b) {
     // reference loop variable at exit: index of the step whose stop flag fired, else last index
     int idx;

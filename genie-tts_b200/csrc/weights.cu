@@ -60,6 +60,22 @@ __global__ void prep_weight_kernel(const void* v, int v_f16, const void* g, int 
   }
 }
 
+// fp32 weights addressed like ConvGemm (co*co_stride + tap*tap_stride + ci) -> fp16 hi (+lo) [Cout][kpad]
+__global__ void pack_tc_kernel(const float* __restrict__ w, long long co_stride, long long tap_stride, int ntaps,
+                               int Cin, int Cout, int kpad, __half* __restrict__ hi, __half* __restrict__ lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * kpad) return;
+  const int co = (int)(i / kpad), kk = (int)(i % kpad);
+  float v = 0.f;
+  if (kk < ntaps * Cin) {
+    const int tap = kk / Cin, ci = kk - tap * Cin;
+    v = w[co * co_stride + tap * tap_stride + ci];
+  }
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2half_rn(v - __half2float(h));
+}
+
 struct Finalizer {
   Model& m;
   cudaStream_t s;
@@ -150,6 +166,59 @@ struct Finalizer {
     return e;
   }
 
+  TcW pack(const float* w, long long co_stride, long long tap_stride, int ntaps, int Cin, int Cout) {
+    TcW t;
+    t.kpad = ((ntaps * Cin + 63) / 64) * 64;
+    const long long n = (long long)Cout * t.kpad;
+    __half* hi = dev_alloc<__half>(m.owned, n);
+    __half* lo = dev_alloc<__half>(m.owned, n);
+    m.weight_bytes += n * 4;
+    pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, co_stride, tap_stride, ntaps, Cin, Cout, t.kpad, hi, lo);
+    GENIE_LAUNCHED("pack_tc");
+    t.hi = hi; t.lo = lo;
+    return t;
+  }
+  void pack_conv(Conv& c) { c.tc = pack(c.w, (long long)c.k * c.Cin, c.Cin, c.k, c.Cin, c.Cout); }
+  void pack_convt(ConvT& c) {
+    const long long tap_sz = (long long)c.Cout * c.Cin;
+    for (int r = 0; r < c.stride && r < 10; ++r) {
+      const int ntaps = (c.k - r + c.stride - 1) / c.stride;
+      if (ntaps > 0) c.tc[r] = pack(c.w + r * tap_sz, c.Cin, c.stride * tap_sz, ntaps, c.Cin, c.Cout);
+    }
+  }
+  void pack_linear(Linear& L) {
+    if (L.w_f16 && L.K % 64 == 0) { L.tc.hi = reinterpret_cast<const __half*>(L.w); L.tc.lo = nullptr; L.tc.kpad = L.K; }
+  }
+  void pack_enc(VitsEncLayer* L, int n) {
+    for (int i = 0; i < n; ++i) {
+      pack_conv(L[i].q); pack_conv(L[i].k); pack_conv(L[i].v); pack_conv(L[i].o);
+      pack_conv(L[i].ff1); pack_conv(L[i].ff2);
+    }
+  }
+  void pack_all() {
+    for (int i = 0; i < 24; ++i) {
+      pack_linear(m.layers[i].qkv); pack_linear(m.layers[i].out);
+      pack_linear(m.layers[i].ff1); pack_linear(m.layers[i].ff2);
+    }
+    pack_linear(m.predict);
+    pack_conv(m.ssl_proj); pack_conv(m.enc_proj);
+    pack_enc(m.enc_ssl, 3); pack_enc(m.enc_text, 6); pack_enc(m.enc2, 3);
+    pack_conv(m.mrte_c_pre); pack_conv(m.mrte_text_pre); pack_conv(m.mrte_q); pack_conv(m.mrte_k);
+    pack_conv(m.mrte_v); pack_conv(m.mrte_o); pack_conv(m.mrte_c_post);
+    for (int f = 0; f < 4; ++f) {
+      pack_conv(m.flow[f].pre); pack_conv(m.flow[f].post);
+      for (int l = 0; l < 4; ++l) { pack_conv(m.flow[f].wn[l].in); pack_conv(m.flow[f].wn[l].rs); }
+    }
+    pack_conv(m.dec_pre);
+    for (int i = 0; i < m.n_up; ++i) {
+      pack_convt(m.ups[i]);
+      for (int j = 0; j < 3; ++j)
+        for (int c = 0; c < 3; ++c) { pack_conv(m.res[i * 3 + j].c1[c]); pack_conv(m.res[i * 3 + j].c2[c]); }
+    }
+    m.tc_err = dev_alloc<int>(m.owned, 1);
+    GENIE_CUDA(cudaMemsetAsync(m.tc_err, 0, sizeof(int), s));
+  }
+
   void run() {
     const int E = GENIE_GRAPH_T2S_ENCODER, T = GENIE_GRAPH_T2S, V = GENIE_GRAPH_VITS, P = GENIE_GRAPH_PROMPT_ENCODER;
     m.v2pp = !m.raw[P].empty();
@@ -232,6 +301,7 @@ struct Finalizer {
     } else {
       m.ref_enc = mel_style(V, q + "ref_enc.");
     }
+    pack_all();
     m.dft = dev_alloc<float>(m.owned, 1408LL * 2048);
     launch_dft_matrix(m.dft, s);
     GENIE_CUDA(cudaStreamSynchronize(s));
@@ -247,12 +317,30 @@ void model_finalize(Model& m) {
 }
 
 void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, int ldy, int M, int act,
-                const float* res, int ldr) {
+                const float* res, int ldr, int nt, int ksplit, long long split_stride) {
   ConvGemm p;
   p.x = x; p.ldx = ldx; p.w = L.w; p.w_f16 = L.w_f16; p.w_co_stride = L.K; p.w_tap_stride = 0;
   p.bias = L.b; p.y = y; p.ldy = ldy; p.Cin = L.K; p.Cout = L.N; p.M = M; p.M_out = M; p.act = act;
   p.res = res; p.ldr = ldr;
+  if (m.use_tc && L.tc.hi && M >= m.tc_min_rows) {
+    // fp16-exact weights: (x_hi + x_lo) . w keeps the fp32 graphs' token parity
+    p.tc_w = L.tc.hi; p.tc_wlo = L.tc.lo; p.tc_kpad = L.tc.kpad; p.tc_split_a = 1;
+    p.tc_nt = nt; p.ksplit = ksplit; p.split_stride = split_stride;
+    launch_tc_conv_gemm(p, m.tc_err, m.stream);
+    return;
+  }
+  GENIE_CHECK(ksplit == 1, "run_linear: split-K needs the tcgen05 path");
   launch_conv_gemm(p, m.stream);
+}
+
+void check_tc_error(Model& m) {
+  if (!m.tc_err) return;
+  int h = 0;
+  GENIE_CUDA(cudaMemcpy(&h, m.tc_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h) {
+    cudaMemset(m.tc_err, 0, sizeof(int));
+    throw Error{"tcgen05 pipeline timed out waiting on an mbarrier (tc_gemm.cu)"};
+  }
 }
 
 void keep_tensor(Model& m, const char* name, const float* dev, long long n) {

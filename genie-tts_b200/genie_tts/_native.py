@@ -54,6 +54,8 @@ SIGNATURES = {
     "genie_debug_read_logits": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "genie_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_longlong, C.POINTER(C.c_longlong)]),
     "genie_debug_keep": (C.c_int, [_P, C.c_int]),
+    "genie_debug_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "genie_last_timing": (C.c_int, [_P, _P, C.c_int]),
     "genie_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
 }

@@ -118,6 +118,11 @@ int genie_debug_read_logits(genie_model* m, float* out, int max_floats, int* n_f
 /* intermediate tensors of the last T2S / VITS call by name ("x", "k0", "m_p", "z", ...) */
 int genie_debug_read(genie_model* m, const char* what, float* out, long long max_floats, long long* n_floats);
 int genie_debug_keep(genie_model* m, int enable);
+/* unit self-test of the tcgen05 implicit-GEMM conv kernel against the exact SIMT kernel on random data:
+ * M rows in two ragged segments, ntaps taps with dilation dil; mode 1 = x_hi.w_hi, 2 = (x_hi+x_lo).w_hi,
+ * 3 = 2 + x_hi.w_lo; exact_w = weights rounded to fp16 (the T2S case) */
+int genie_debug_tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err,
+                            float* ref_max);
 /* timing of the last call's stages in milliseconds (CUDA events): prefill, decode, total */
 int genie_last_timing(genie_model* m, float* ms, int n);
 /* use CUDA-graph replay for the decode step (default 1) */
