@@ -5,6 +5,9 @@
 #include <cstring>
 
 using namespace genie;
+namespace genie {
+void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err, float* ref_max);
+}
 
 struct genie_model { Model m; };
 struct genie_prompt { Prompt p; };
@@ -239,9 +242,6 @@ int genie_debug_read(genie_model* h, const char* what, float* out, long long max
     if (out) std::memcpy(out, it->second.data(), std::min<size_t>(it->second.size(), (size_t)max_floats) * sizeof(float));
     return 0;
   });
-}
-namespace genie {
-void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err, float* ref_max);
 }
 int genie_debug_tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err,
                             float* ref_max) {

@@ -83,6 +83,8 @@ struct ConvGemm {
 };
 void launch_conv_gemm(const ConvGemm& p, cudaStream_t s);
 void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s);
+bool skinny_gemm_supported(const ConvGemm& p);
+void launch_skinny_gemm(const ConvGemm& p, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // attention

@@ -10,46 +10,48 @@ inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 // ---- LayerNorm (+residual), one warp per row --------------------------------
 // x may be `nsplit` split-K partial sums `split_stride` floats apart; `lin_bias` is the producing
 // linear layer's bias (deferred from the split-K GEMM epilogue)
+template <int N>   // N = C / 32 values per lane, all in registers
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                  const float* __restrict__ g, const float* __restrict__ b,
-                                 float* __restrict__ y, int rows, int C, int nsplit, long long split_stride,
+                                 float* __restrict__ y, int rows, int nsplit, long long split_stride,
                                  const float* __restrict__ lin_bias) {
+  constexpr int C = N * 32;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + (long long)row * C;
-  const float* rr = res ? res + (long long)row * C : nullptr;
-  float v[32];   // C <= 1024
-  const int n = C >> 5;
+  const float* xr = x + (long long)row * C + lane;
+  float v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = xr[32 * i];
+  for (int sp = 1; sp < nsplit; ++sp) {
+    const float* xs = xr + sp * split_stride;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += xs[32 * i];
+  }
+  if (lin_bias) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += lin_bias[lane + 32 * i];
+  }
+  if (res) {
+    const float* rr = res + (long long)row * C + lane;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += rr[32 * i];
+  }
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (i < n) {
-      float t = xr[lane + 32 * i];
-      for (int sp = 1; sp < nsplit; ++sp) t += xr[sp * split_stride + lane + 32 * i];
-      if (lin_bias) t += lin_bias[lane + 32 * i];
-      if (rr) t += rr[lane + 32 * i];
-      v[i] = t; sum += t;
-    }
-  }
+  for (int i = 0; i < N; ++i) sum += v[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / (float)C;
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i < n) { float d = v[i] - mean; var = fmaf(d, d, var); }
+  for (int i = 0; i < N; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = 1.f / sqrtf(var / (float)C + 1e-5f);
-  float* yr = y + (long long)row * C;
+  float* yr = y + (long long)row * C + lane;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (i < n) {
-      int c = lane + 32 * i;
-      yr[c] = (v[i] - mean) * rstd * g[c] + b[c];
-    }
-  }
+  for (int i = 0; i < N; ++i) yr[32 * i] = (v[i] - mean) * rstd * g[lane + 32 * i] + b[lane + 32 * i];
 }
 
 __device__ __forceinline__ float pe_value(int pos, int c, const float* div_term) {
@@ -292,8 +294,12 @@ __global__ void transpose_kernel(const float* src, int rows, int cols, float* ds
 void launch_layernorm(const float* x, const float* res, const float* g, const float* b, float* y, int rows, int C,
                       cudaStream_t s, int nsplit, long long split_stride, const float* lin_bias) {
   if (rows <= 0) return;
-  GENIE_CHECK(C % 32 == 0 && C <= 1024, "layernorm: bad C");
-  layernorm_kernel<<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, C, nsplit, split_stride, lin_bias);
+  switch (C) {
+    case 512: layernorm_kernel<16><<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, nsplit, split_stride, lin_bias); break;
+    case 192: layernorm_kernel<6><<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, nsplit, split_stride, lin_bias); break;
+    case 128: layernorm_kernel<4><<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, nsplit, split_stride, lin_bias); break;
+    default: GENIE_CHECK(false, "layernorm: unsupported width");
+  }
   GENIE_LAUNCHED("layernorm");
 }
 void launch_text_embed_pe(float* x, const long long* seq, const int* pos, const float* emb, const float* alpha,

@@ -1,6 +1,8 @@
 // Unit self-test of the tcgen05 implicit-GEMM against the exact SIMT path on
 // random data (no model needed).  Exposed through genie_debug_tc_selftest.
 #include "common.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include <random>
 #include <vector>
 
@@ -58,6 +60,23 @@ void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exa
   p.y = y1; p.tc_w = hi; p.tc_wlo = mode >= 3 ? lo : nullptr; p.tc_kpad = kpad; p.tc_split_a = mode >= 2;
   launch_tc_conv_gemm(p, err, s);
   GENIE_CUDA(cudaDeviceSynchronize());
+  if (getenv("GENIE_SELFTEST_TIME")) {
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    ConvGemm ps = p; ps.tc_w = nullptr; ps.y = y0;
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < 10; ++i) launch_conv_gemm(ps, s);
+    cudaEventRecord(e1, s);
+    for (int i = 0; i < 10; ++i) launch_tc_conv_gemm(p, err, s);
+    cudaEventRecord(e2, s);
+    cudaDeviceSynchronize();
+    float t0 = 0, t1 = 0;
+    cudaEventElapsedTime(&t0, e0, e1); cudaEventElapsedTime(&t1, e1, e2);
+    const double fl = 2.0 * rows * (double)K * Cout;
+    fprintf(stderr, "  [time] simt %.1f us (%.1f TF/s)  tc %.1f us (%.1f TF/s)\n", t0 * 100, fl / (t0 * 1e-4) / 1e12,
+            t1 * 100, fl / (t1 * 1e-4) / 1e12);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  }
   std::vector<float> a(hr.size()), c(hr.size());
   int herr = 0;
   GENIE_CUDA(cudaMemcpy(a.data(), y0, a.size() * 4, cudaMemcpyDeviceToHost));

@@ -135,28 +135,53 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int it_k = kb - kb_lo;
     const int s = it_k & 1;
-    if (it_k >= 2) ok = mbar_wait(&bars[s], (uint32_t)(((it_k >> 1) - 1) & 1)) && ok;
     uint8_t* st = sbase + (size_t)s * STAGE_BYTES;
     uint8_t* sA = st;
     uint8_t* sW = st + A_BYTES * SPLIT_A;
-    // ---- A tile: 128 rows x 64 k (fp32 gather -> fp16 hi/lo, swizzled)
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const int idx = tid + it * 128;
-      const int r = idx >> 4, c4 = idx & 15;
+    // ---- global loads of the whole stage first (16 + NT/16 independent 16-byte loads per thread in
+    // flight), then the buffer-free wait, then convert + swizzled stores: the load latency overlaps the
+    // MMAs of the previous stages
+    float4 av[16];
+    // column group of this thread is the same for all 16 A loads: c4 = tid & 15, rows r = (tid>>4) + 8*it
+    {
+      const int c4 = tid & 15;
       const int kk = kb * BK + c4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kk < Ktot && (q0 + r) < nq) {
-        const int tap = kk / p.Cin;
-        const int ci = kk - tap * p.Cin;
-        const int t = q0 + r + p.in_shift0 + tap * p.in_shift_step;
-        if (t >= 0 && t < Tin) {
-          v = *reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + ci);
-          if (pre != 1.f) {
-            v.x = v.x > 0.f ? v.x : v.x * pre; v.y = v.y > 0.f ? v.y : v.y * pre;
-            v.z = v.z > 0.f ? v.z : v.z * pre; v.w = v.w > 0.f ? v.w : v.w * pre;
-          }
-        }
+      const int tap = kk / p.Cin;
+      const int ci = kk - tap * p.Cin;
+      const int tsh = p.in_shift0 + tap * p.in_shift_step;
+      const bool kok = kk < Ktot;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int r = (tid >> 4) + it * 8;
+        const int t = q0 + r + tsh;
+        av[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kok && (q0 + r) < nq && t >= 0 && t < Tin)
+          av[it] = __ldg(reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + ci));
+      }
+    }
+    constexpr int WIT = NT / 16;                   // NT*8 uint4 per tile / 128 threads
+    uint4 wv[WIT], wl[W_LO ? WIT : 1];
+#pragma unroll
+    for (int it = 0; it < WIT; ++it) {
+      const int idx = tid + it * 128;
+      const int n = idx >> 3, c8 = idx & 7;
+      wv[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (W_LO) wl[it] = wv[it];
+      if (n < n_mma && n0 + n < p.Cout) {
+        const long long o = (long long)(n0 + n) * p.tc_kpad + kb * BK + c8 * 8;
+        wv[it] = __ldg(reinterpret_cast<const uint4*>(whi + o));
+        if (W_LO) wl[it] = __ldg(reinterpret_cast<const uint4*>(wlo + o));
+      }
+    }
+    if (it_k >= 2) ok = mbar_wait(&bars[s], (uint32_t)(((it_k >> 1) - 1) & 1)) && ok;
+    // ---- A tile: 128 rows x 64 k (fp32 -> fp16 hi/lo, swizzled)
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int r = (tid >> 4) + it * 8, c4 = tid & 15;
+      float4 v = av[it];
+      if (pre != 1.f) {
+        v.x = v.x > 0.f ? v.x : v.x * pre; v.y = v.y > 0.f ? v.y : v.y * pre;
+        v.z = v.z > 0.f ? v.z : v.z * pre; v.w = v.w > 0.f ? v.w : v.w * pre;
       }
       const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
       const uint32_t off = swz(r, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;
@@ -174,16 +199,14 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
       }
     }
     // ---- W tile: n_mma rows x 64 k (pre-packed fp16, zero padded in K)
-    for (int idx = tid; idx < n_mma * 8; idx += 128) {
+#pragma unroll
+    for (int it = 0; it < WIT; ++it) {
+      const int idx = tid + it * 128;
       const int n = idx >> 3, c8 = idx & 7;
-      uint4 u = make_uint4(0u, 0u, 0u, 0u), ul = u;
-      if (n0 + n < p.Cout) {
-        const long long o = (long long)(n0 + n) * p.tc_kpad + kb * BK + c8 * 8;
-        u = *reinterpret_cast<const uint4*>(whi + o);
-        if (W_LO) ul = *reinterpret_cast<const uint4*>(wlo + o);
+      if (n < n_mma) {
+        *reinterpret_cast<uint4*>(sW + swz(n, c8)) = wv[it];
+        if (W_LO) *reinterpret_cast<uint4*>(sW + W_BYTES + swz(n, c8)) = wl[it];
       }
-      *reinterpret_cast<uint4*>(sW + swz(n, c8)) = u;
-      if (W_LO) *reinterpret_cast<uint4*>(sW + W_BYTES + swz(n, c8)) = ul;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
     __syncthreads();
@@ -209,11 +232,12 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!ok && err_flag) atomicExch(err_flag, 1);
 
-  // ---- epilogue: TMEM lane = output row (warp w owns lanes 32w..32w+31)
-  const int q = q0 + warp * 32 + lane;
-  const int to = q * p.out_mul + p.out_add;
-  const bool row_ok = ok && q < nq && to >= 0 && to < Tout;
-  const long long orow = (long long)out0 + to;
+  // ---- epilogue: TMEM lane = output row (warp w owns lanes 32w..32w+31).  Each 32x32 chunk goes
+  // through a padded per-warp smem tile so that global stores / residual loads are row-contiguous
+  // (one 128-byte line per warp instruction) instead of 32 strided rows.
+  float* tile = reinterpret_cast<float*>(sbase) + warp * (32 * 33);
+  const int row_base = q0 + warp * 32;
+  const float* bias2 = p.bias2 ? p.bias2 + (long long)seg * p.ldb2 : nullptr;
   for (int c0 = 0; c0 < n_mma; c0 += 32) {
     uint32_t v[32];
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
@@ -238,35 +262,42 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
       for (int j = 16; j < 32; ++j) v[j] = 0u;
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row_ok) {
-      const float* bias2 = p.bias2 ? p.bias2 + (long long)seg * p.ldb2 : nullptr;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = n0 + c0 + j;
-        if (n >= p.Cout) break;
-        float o4[4];
+    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    const int n = n0 + c0 + lane;                    // this lane's output column
+    const bool col_ok = n < p.Cout && (c0 + lane) < n_mma;
+    float badd = 0.f;
+    if (col_ok && p.ksplit == 1) {
+      if (p.bias) badd += p.bias[n];
+      if (bias2) badd += bias2[n];
+    }
+    const bool plain = p.ksplit == 1;
+    const bool has_res = plain && p.res != nullptr, has_acc = plain && p.accumulate;
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+      float xv[8], rv[8], cv[8];
+      long long orow[8];
+      bool rok[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = __uint_as_float(v[j + e]);
-          if (n + e < p.Cout && p.ksplit == 1) {
-            if (p.bias) x += p.bias[n + e];
-            if (bias2) x += bias2[n + e];
-            x = apply_act(x, p.act, p.act_slope) * p.out_scale;
-            if (p.res) x += p.res[orow * p.ldr + n + e];
-            if (p.accumulate) x += p.y[orow * p.ldy + n + e];
-          }
-          o4[e] = x;
-        }
-        float* dst = p.y + (long long)ks * p.split_stride + orow * p.ldy + n;
-        if (n + 3 < p.Cout && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-          *reinterpret_cast<float4*>(dst) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        } else {
+      for (int i = 0; i < 8; ++i) {                 // all loads of 8 rows are issued before any store
+        const int q = row_base + r0 + i;
+        const int to = q * p.out_mul + p.out_add;
+        rok[i] = ok && col_ok && q < nq && to >= 0 && to < Tout;
+        orow[i] = (long long)out0 + to;
+        xv[i] = tile[(r0 + i) * 33 + lane];
+        rv[i] = (rok[i] && has_res) ? p.res[orow[i] * p.ldr + n] : 0.f;
+        cv[i] = (rok[i] && has_acc) ? p.y[orow[i] * p.ldy + n] : 0.f;
+      }
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (n + e < p.Cout) dst[e] = o4[e];
-        }
+      for (int i = 0; i < 8; ++i) {
+        if (!rok[i]) continue;
+        float x = xv[i];
+        if (plain) x = apply_act(x + badd, p.act, p.act_slope) * p.out_scale + rv[i] + cv[i];
+        p.y[(long long)ks * p.split_stride + orow[i] * p.ldy + n] = x;
       }
     }
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -32,7 +32,7 @@ void run_conv(Model& m, const Conv& c, const float* x, int ldx, float* y, int ld
   p.pre_slope = o.pre_slope; p.act = o.act; p.act_slope = o.act_slope; p.accumulate = o.accumulate;
   p.in_off = sg.off; p.out_off = sg.off; p.B = sg.B; p.M = sg.maxT; p.M_out = sg.maxT;
   if (!sg.off) { p.B = 1; p.M = sg.rows; p.M_out = sg.rows; }
-  if (m.use_tc && c.tc.hi && sg.rows >= m.tc_min_rows && o.cin0 == 0 && cin == c.Cin) {
+  if (m.use_tc && c.tc.hi && sg.off != nullptr && o.cin0 == 0 && cin == c.Cin) {
     p.tc_w = c.tc.hi + (long long)o.co0 * c.tc.kpad; p.tc_kpad = c.tc.kpad;
     p.tc_wlo = m.tc_vits >= 3 ? c.tc.lo + (long long)o.co0 * c.tc.kpad : nullptr;
     p.tc_split_a = m.tc_vits >= 2;
@@ -55,7 +55,7 @@ void run_convt(Model& m, const ConvT& c, const float* x, float* y, const Seg& in
     // t_out = q*s + r - pad < T_in*s  =>  q <= T_in - 1 + floor((s - 1 + pad - r) / s)
     p.in_off = in.off; p.out_off = out.off; p.B = in.B; p.M = in.maxT; p.M_out = out.maxT;
     p.q_extra = (c.stride - 1 + c.pad - r) / c.stride;
-    if (m.use_tc && r < 10 && c.tc[r].hi && in.rows >= m.tc_min_rows) {
+    if (m.use_tc && r < 10 && c.tc[r].hi) {
       p.tc_w = c.tc[r].hi; p.tc_kpad = c.tc[r].kpad;
       p.tc_wlo = m.tc_vits >= 3 ? c.tc[r].lo : nullptr;
       p.tc_split_a = m.tc_vits >= 2;

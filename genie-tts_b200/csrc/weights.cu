@@ -321,7 +321,11 @@ void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, in
   ConvGemm p;
   p.x = x; p.ldx = ldx; p.w = L.w; p.w_f16 = L.w_f16; p.w_co_stride = L.K; p.w_tap_stride = 0;
   p.bias = L.b; p.y = y; p.ldy = ldy; p.Cin = L.K; p.Cout = L.N; p.M = M; p.M_out = M; p.act = act;
-  p.res = res; p.ldr = ldr;
+  p.res = res; p.ldr = ldr; p.ksplit = ksplit; p.split_stride = split_stride;
+  if (skinny_gemm_supported(p)) {          // decode-sized batch: batch-composition-independent exact path
+    launch_skinny_gemm(p, m.stream);
+    return;
+  }
   if (m.use_tc && L.tc.hi && M >= m.tc_min_rows) {
     // fp16-exact weights: (x_hi + x_lo) . w keeps the fp32 graphs' token parity
     p.tc_w = L.tc.hi; p.tc_wlo = L.tc.lo; p.tc_kpad = L.tc.kpad; p.tc_split_a = 1;

@@ -1,0 +1,22 @@
+"""Small profiling target: one T2S call (+ optional vocoder) at batch B for a few decode steps."""
+import os, sys, numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "genie-tts_b200")]
+from conftest import fixture_dir
+from genie_tts.engine import B200Model, SamplingParams
+from synth import make_prompt_inputs, make_text_inputs
+B = int(sys.argv[1]); steps = int(sys.argv[2]); vits = len(sys.argv) > 3 and sys.argv[3] == "vits"
+m = B200Model(fixture_dir("v2", 0))
+m.set_option("use_graph", int(os.environ.get("USE_GRAPH", "1")))
+pr = make_prompt_inputs(seed=1, Lr=60, Ts=264, n_audio=169600)
+prompt = m.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"])
+rng = np.random.default_rng(0)
+txs = [make_text_inputs(seed=200 + i, Lt=int(rng.integers(40, 61))) for i in range(B)]
+sp = SamplingParams(seed=3, max_steps=steps, fixed_steps=steps)
+for it in range(2):
+    ys, idx = m.t2s_generate([prompt] * B, [t["text_seq"] for t in txs], None, sp)
+    print("t2s", m.last_timing())
+    if vits:
+        sems = [y[-steps:] % 1024 for y in ys]
+        a = m.vits_decode([prompt] * B, [t["text_seq"] for t in txs], sems)
+        print("vits", m.last_timing())

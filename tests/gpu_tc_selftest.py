@@ -13,7 +13,7 @@ for (M, Cin, Cout, nt, dil) in cases:
     for mode, exact in ((1, 0), (2, 1), (3, 0)):
         e, r = C.c_float(0), C.c_float(0)
         rc = L.genie_debug_tc_selftest(M, Cin, Cout, nt, dil, mode, exact, C.byref(e), C.byref(r))
-        tol = {1: 2e-2, 2: 2e-5, 3: 2e-5}[mode]
+        tol = {1: 2e-2, 2: 6e-5, 3: 6e-5}[mode]
         flag = "" if (rc == 0 and e.value < tol) else "  <-- FAIL " + (L.genie_last_error() or b"").decode()
         bad += bool(flag)
         print(f"M={M} Cin={Cin} Cout={Cout} taps={nt} dil={dil} mode={mode} exact_w={exact}: err {e.value:.3e} (ref max {r.value:.2f}){flag}")
