@@ -261,6 +261,7 @@ int genie_set_option(genie_model* h, const char* key, int value) {
   if (std::strcmp(key, "use_graph") == 0) { h->m.use_graph = value; return 0; }
   if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
+  if (std::strcmp(key, "skinny_max_rows") == 0) { h->m.skinny_max_rows = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_min_rows") == 0) { h->m.tc_min_rows = value; h->m.step_graph_flags = -1; return 0; }
   g_err = std::string("unknown option ") + key;
   return 1;

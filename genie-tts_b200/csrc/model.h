@@ -117,7 +117,7 @@ struct Model {
   int use_graph = 1;
   // tcgen05 path: 0 = exact SIMT everywhere; T2S always runs x_hi+x_lo against fp16-exact weights;
   // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo
-  int use_tc = 1, tc_vits = 1, tc_min_rows = 9;
+  int use_tc = 1, tc_vits = 1, tc_min_rows = 9, skinny_max_rows = 8;
   int* tc_err = nullptr;
   // debug
   bool record_logits = false, keep = false;

@@ -48,18 +48,21 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
     const T2SLayer& L = m.layers[l];
     // tcgen05 path for a small batch: 64-wide N tiles and split-K spread each GEMM over more SMs; the
     // split-K partials, the linear bias and the residual are summed inside the following LayerNorm
-    const bool tc = B <= 128;   // skinny weight-streaming GEMMs with split-K (skinny_gemm.cu)
+    const bool tc = B <= 128;
+    // B <= skinny_max_rows: weight-streaming SIMT GEMV (skinny_gemm.cu); else tcgen05 with narrow N tiles
+    const bool sk = !m.use_tc || B <= m.skinny_max_rows;
+    const int nt_w = sk ? 0 : 32, nt_s = sk ? 0 : 64, ks_out = sk ? 2 : 4;
     const long long ps = (long long)B * D;
-    run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B, ACT_NONE, nullptr, 0, tc ? 64 : 0);
+    run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B, ACT_NONE, nullptr, 0, tc ? nt_w : 0);
     launch_kv_scatter(w.qkv, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap, nullptr, w.kv_len,
                       nullptr, B, w.active, s);
     launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
                                 w.active, B, w.cap, scale, /*t_add=*/1, s);
     if (tc) {
-      run_linear(m, L.out, w.att, D, w.part, D, B, ACT_NONE, nullptr, 0, 64, 2, ps);
-      launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 2, ps, L.out.b);
-      run_linear(m, L.ff1, w.h1, D, w.ff, 4 * D, B, ACT_RELU, nullptr, 0, 64);
-      run_linear(m, L.ff2, w.ff, 4 * D, w.part, D, B, ACT_NONE, nullptr, 0, 64, 8, ps);
+      run_linear(m, L.out, w.att, D, w.part, D, B, ACT_NONE, nullptr, 0, nt_s, ks_out, ps);
+      launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, ks_out, ps, L.out.b);
+      run_linear(m, L.ff1, w.h1, D, w.ff, 4 * D, B, ACT_RELU, nullptr, 0, nt_w);
+      run_linear(m, L.ff2, w.ff, 4 * D, w.part, D, B, ACT_NONE, nullptr, 0, nt_s, 8, ps);
       launch_layernorm(w.part, w.h1, L.ln2_g, L.ln2_b, w.h, B, D, s, 8, ps, L.ff2.b);
     } else {
       run_linear(m, L.out, w.att, D, w.tmp, D, B, ACT_NONE, w.h, D);

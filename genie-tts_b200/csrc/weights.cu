@@ -322,7 +322,7 @@ void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, in
   p.x = x; p.ldx = ldx; p.w = L.w; p.w_f16 = L.w_f16; p.w_co_stride = L.K; p.w_tap_stride = 0;
   p.bias = L.b; p.y = y; p.ldy = ldy; p.Cin = L.K; p.Cout = L.N; p.M = M; p.M_out = M; p.act = act;
   p.res = res; p.ldr = ldr; p.ksplit = ksplit; p.split_stride = split_stride;
-  if (skinny_gemm_supported(p)) {          // decode-sized batch: batch-composition-independent exact path
+  if (M <= (m.use_tc ? m.skinny_max_rows : 128) && skinny_gemm_supported(p)) {   // small decode batch: exact weight-streaming path
     launch_skinny_gemm(p, m.stream);
     return;
   }
