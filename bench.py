@@ -256,9 +256,11 @@ def main():
     t0 = time.perf_counter()
     audio_s = 0.0
     last_t = None
+    N.lib().genie_profiler_range(1)     # no-op unless run under `ncu --profile-from-start off`
     for _ in range(args.steps):
         a, last_t = step_device()
         audio_s += a
+    N.lib().genie_profiler_range(0)
     barrier()
     dt = time.perf_counter() - t0
     launches = N.lib().genie_launch_count() - launches0
@@ -275,6 +277,16 @@ def main():
         d2h = nb + B * y_ld * 8
     barrier()
     dt_e = time.perf_counter() - t1
+
+    # ---- batch-1 first-audio latency (BASELINE.json metric part 3): one ~20-char sentence, host buffers,
+    # text front end excluded (untimed in the reference comparison too), 90-token budget
+    lat = []
+    for i in range(12):
+        torch.cuda.synchronize()
+        tl0 = time.perf_counter()
+        genie.tts_batch(model, [prompt], [seqs[i % B]], None, sampling=sp)
+        lat.append(1000 * (time.perf_counter() - tl0))
+    first_audio_ms = float(np.median(lat[2:]))
 
     tt = torch.tensor([dt, dt_e], dtype=torch.float64, device=dev)
     aa = torch.tensor([audio_s, e_audio], dtype=torch.float64, device=dev)
@@ -305,8 +317,9 @@ def main():
             "t2s_tokens_per_s": world * B * TOKENS * args.steps / (np.sum(stage_ms["decode"]) * 1e-3) / 1.0
             if stage_ms["decode"] else None,
             "stage_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+            "first_audio_ms_p50_batch1": first_audio_ms,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (HiFi-GAN generator convs, fp32 SIMT)",
+            "roofline": {"bound": "tensor", "kernel": "tc_conv_gemm_kernel (tcgen05 implicit-GEMM, HiFi-GAN generator convs)",
                          "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "peak_source": which, "launches_per_step": n_gen,
                          "avg_launch_ms": gen_ms / n_gen, "traffic": None},

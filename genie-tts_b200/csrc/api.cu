@@ -3,6 +3,7 @@
 #include "../../include/genie_b200.h"
 #include "model.h"
 #include <cstring>
+#include <cuda_profiler_api.h>
 
 using namespace genie;
 namespace genie {
@@ -57,6 +58,9 @@ int genie_model_create(int device, genie_model** out) {
     genie_model* h = new genie_model();
     h->m.device = device;
     GENIE_CUDA(cudaStreamCreateWithFlags(&h->m.stream, cudaStreamNonBlocking));
+    GENIE_CUDA(cudaStreamCreateWithFlags(&h->m.stream2, cudaStreamNonBlocking));
+    GENIE_CUDA(cudaEventCreateWithFlags(&h->m.ev_fork, cudaEventDisableTiming));
+    GENIE_CUDA(cudaEventCreateWithFlags(&h->m.ev_join, cudaEventDisableTiming));
     *out = h;
     return 0;
   });
@@ -251,6 +255,10 @@ int genie_debug_tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mo
     return 0;
   });
 }
+int genie_profiler_range(int on) {   // cudaProfilerStart/Stop: `ncu --profile-from-start off` captures only this range
+  cudaError_t e = on ? cudaProfilerStart() : cudaProfilerStop();
+  return e == cudaSuccess ? 0 : 1;
+}
 int genie_last_timing(genie_model* h, float* ms, int n) {
   if (!h || !ms) return 1;
   for (int i = 0; i < n && i < 8; ++i) ms[i] = h->m.timing[i];
@@ -261,6 +269,7 @@ int genie_set_option(genie_model* h, const char* key, int value) {
   if (std::strcmp(key, "use_graph") == 0) { h->m.use_graph = value; return 0; }
   if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
+  if (std::strcmp(key, "decode_split_min") == 0) { h->m.decode_split_min = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "skinny_max_rows") == 0) { h->m.skinny_max_rows = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_min_rows") == 0) { h->m.tc_min_rows = value; h->m.step_graph_flags = -1; return 0; }
   g_err = std::string("unknown option ") + key;

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) attention_kernel(Attn p) {
 __global__ void __launch_bounds__(128) decode_attention_kernel(
     const float* __restrict__ q, float* __restrict__ o, const float* __restrict__ kv_base,
     long long utt_stride, long long layer_off, long long v_off, const int* __restrict__ kv_len,
-    const int* __restrict__ active, int cap, float scale, int t_add) {
+    const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
   const int h = blockIdx.x, b = blockIdx.y;
   if (active && !active[b]) return;
   const int T = kv_len[b] + t_add;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
   const float* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
   const float* V = K + v_off;
 
-  float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * 512 + h * 32 + sub * 4);
+  float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + h * 32 + sub * 4);
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
 
   float m = -CUDART_INF_F, l = 0.f;
@@ -232,10 +232,10 @@ void launch_attention(const Attn& p, cudaStream_t s) {
 
 void launch_decode_attention_raw(const float* q, float* o, const float* kv_base, long long utt_stride,
                                  long long layer_off, long long v_off, const int* kv_len, const int* active,
-                                 int B, int cap, float scale, int t_add, cudaStream_t s) {
+                                 int B, int cap, float scale, int t_add, int ldq, cudaStream_t s) {
   if (B <= 0) return;
   decode_attention_kernel<<<dim3(16, B), 128, 0, s>>>(q, o, kv_base, utt_stride, layer_off, v_off, kv_len,
-                                                      active, cap, scale, t_add);
+                                                      active, cap, scale, t_add, ldq);
   GENIE_LAUNCHED("decode_attention");
 }
 

@@ -23,7 +23,18 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   float v[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = xr[32 * i];
-  for (int sp = 1; sp < nsplit; ++sp) {
+  // split-K partials: two slices per pass so that 2N loads are in flight before the adds
+  int sp = 1;
+  for (; sp + 1 < nsplit; sp += 2) {
+    const float* xs = xr + sp * split_stride;
+    const float* xt = xs + split_stride;
+    float a[N], c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { a[i] = xs[32 * i]; c[i] = xt[32 * i]; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += a[i] + c[i];
+  }
+  for (; sp < nsplit; ++sp) {
     const float* xs = xr + sp * split_stride;
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] += xs[32 * i];

@@ -6,7 +6,7 @@ namespace genie {
 
 void launch_decode_attention_raw(const float* q, float* o, const float* kv_base, long long utt_stride,
                                  long long layer_off, long long v_off, const int* kv_len, const int* active,
-                                 int B, int cap, float scale, int t_add, cudaStream_t s);
+                                 int B, int cap, float scale, int t_add, int ldq, cudaStream_t s);
 
 // y[r,:] = LN(x[r,:] (+ res[r,:])) * g + b   (eps 1e-5), C multiple of 32, C <= 1024
 // x may be nsplit split-K partials (split_stride apart) with the producer's bias deferred to here
@@ -29,6 +29,20 @@ void launch_decode_embed(float* out, const int* hist, int hist_ld, const int* hi
 void launch_kv_scatter(const float* qkv, int ld, float* kv_base, long long utt_stride, long long layer_off,
                        long long v_off, int cap, const int* row_off, const int* dst_pos0, const int* row2utt,
                        int rows, const int* active, cudaStream_t s);
+
+// decode-step single-shot tcgen05 GEMM (tc_small_gemm.cu): raw split-K partials of
+// act_in(sum_s x_s + a_bias) . W^T for rows <= 128, K multiple of 256
+struct SmallGemm {
+  const float* x = nullptr; int ldx = 0; int a_nsplit = 1; long long a_stride = 0;
+  const float* a_bias = nullptr; int a_relu = 0;
+  const __half* w = nullptr; int ldw = 0;
+  int N = 0, K = 0, M = 0;
+  float* y = nullptr; int ldy = 0; long long split_stride = 0;
+};
+void launch_tc_small_gemm(const SmallGemm& p, int nt, int* err_flag, cudaStream_t s);
+void launch_qkv_finish(const float* part, int nsplit, long long split_stride, const float* bias, float* q,
+                       float* kv_base, long long utt_stride, long long layer_off, long long v_off, int cap,
+                       const int* kv_len, const int* active, int B, cudaStream_t s);
 
 struct SamplerArgs {
   const float* logits;     // [B, ld]

@@ -75,6 +75,9 @@ struct Workspace {
 struct Model {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;     // second branch of the decode-step graph
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int decode_split_min = 1 << 30;     // measured: halves are latency-bound like the whole batch, no gain
   bool finalized = false, v2pp = false;
   std::unordered_map<std::string, RawTensor> raw[4];
   std::vector<void*> owned;           // device allocations owned by the model

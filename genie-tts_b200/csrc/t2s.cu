@@ -34,9 +34,9 @@ __global__ void hist_to_i64_kernel(const int* hist, int hist_ld, const int* hist
 }
 
 struct StepBufs {
-  float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part;
+  float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part, *part2;
   int *hist, *hist_len, *kv_len, *active, *stop_step;
-  float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld;
+  float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld; long long part_stride;
 };
 
 // one decode step for every active utterance (stage#[12-1821])
@@ -46,18 +46,47 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   const float scale = 1.0f / std::sqrt(32.0f);
   for (int l = 0; l < NL; ++l) {
     const T2SLayer& L = m.layers[l];
-    // tcgen05 path for a small batch: 64-wide N tiles and split-K spread each GEMM over more SMs; the
-    // split-K partials, the linear bias and the residual are summed inside the following LayerNorm
+    const long long ps = w.part_stride;   // rows of the WHOLE batch
+    const bool small_tc = m.use_tc && B > m.skinny_max_rows && B <= 128;
+    if (small_tc) {
+      // single-shot tcgen05 GEMMs (tc_small_gemm.cu): every output is a split-K partial; bias, residual,
+      // activation and the KV append are applied by the consumer kernels
+      auto gemm = [&](const Linear& Lw, const float* x, int ldx, int a_ns, const float* a_bias, int a_relu, int nt) {
+        SmallGemm g;
+        g.x = x; g.ldx = ldx; g.a_nsplit = a_ns; g.a_stride = ps * (ldx / D); g.a_bias = a_bias; g.a_relu = a_relu;
+        g.w = reinterpret_cast<const __half*>(Lw.w); g.ldw = Lw.K; g.N = Lw.N; g.K = Lw.K; g.M = B;
+        g.y = w.part; g.ldy = Lw.N; g.split_stride = ps * (Lw.N / D);
+        launch_tc_small_gemm(g, nt, m.tc_err, s);
+      };
+      gemm(L.qkv, w.h, D, 1, nullptr, 0, 32);                                   // 2 partials [B,1536]
+      launch_qkv_finish(w.part, 2, ps * 3, L.qkv.b, w.qkv, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap,
+                        w.kv_len, w.active, B, s);
+      launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
+                                  w.active, B, w.cap, scale, /*t_add=*/1, /*ldq=*/D, s);
+      gemm(L.out, w.att, D, 1, nullptr, 0, 32);                                 // 2 partials [B,512]
+      launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 2, ps, L.out.b);
+      gemm(L.ff1, w.h1, D, 1, nullptr, 0, 32);                                  // 2 partials [B,2048]
+      // FFN2 reads relu(sum FFN1 partials + bias) as its A operand: partials live in w.part, so its own
+      // output partials go to w.part2
+      {
+        SmallGemm g;
+        g.x = w.part; g.ldx = 4 * D; g.a_nsplit = 2; g.a_stride = ps * 4; g.a_bias = L.ff1.b; g.a_relu = 1;
+        g.w = reinterpret_cast<const __half*>(L.ff2.w); g.ldw = L.ff2.K; g.N = D; g.K = 4 * D; g.M = B;
+        g.y = w.part2; g.ldy = D; g.split_stride = ps;
+        launch_tc_small_gemm(g, 32, m.tc_err, s);                               // 8 partials [B,512]
+      }
+      launch_layernorm(w.part2, w.h1, L.ln2_g, L.ln2_b, w.h, B, D, s, 8, ps, L.ff2.b);
+      continue;
+    }
+    const bool sk = true;   // B <= skinny_max_rows (or tcgen05 disabled): weight-streaming SIMT GEMV path
     const bool tc = B <= 128;
-    // B <= skinny_max_rows: weight-streaming SIMT GEMV (skinny_gemm.cu); else tcgen05 with narrow N tiles
-    const bool sk = !m.use_tc || B <= m.skinny_max_rows;
-    const int nt_w = sk ? 0 : 32, nt_s = sk ? 0 : 64, ks_out = sk ? 2 : 4;
-    const long long ps = (long long)B * D;
+    const int nt_w = 0, nt_s = 0, ks_out = 2;
+    (void)sk;
     run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B, ACT_NONE, nullptr, 0, tc ? nt_w : 0);
     launch_kv_scatter(w.qkv, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap, nullptr, w.kv_len,
                       nullptr, B, w.active, s);
     launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
-                                w.active, B, w.cap, scale, /*t_add=*/1, s);
+                                w.active, B, w.cap, scale, /*t_add=*/1, /*ldq=*/3 * D, s);
     if (tc) {
       run_linear(m, L.out, w.att, D, w.part, D, B, ACT_NONE, nullptr, 0, nt_s, ks_out, ps);
       launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, ks_out, ps, L.out.b);
@@ -276,6 +305,8 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
   w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
   w.part = ws.get<float>("t2s.step.part", (size_t)8 * B * D);
+  w.part2 = ws.get<float>("t2s.step.part2", (size_t)8 * B * D);
+  w.part_stride = (long long)B * D;
   w.logits = LOGITS; w.hist = HIST; w.hist_len = d_histlen; w.kv_len = d_kvlen; w.active = d_active;
   w.stop_step = d_stop; w.kv = KV; w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off;
   w.cap = bt.cap; w.hist_ld = bt.hist_ld;
@@ -296,7 +327,29 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       unsigned long long launches_before = g_launches;
       GENIE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
-        decode_step(m, w, B, cfg);
+        if (B >= m.decode_split_min && m.stream2) {
+          // two independent halves of the batch as parallel graph branches: every decode kernel is
+          // latency-bound on a fraction of the SMs, so the halves overlap (one half's KV-bound
+          // attention runs under the other half's GEMMs)
+          const int b1 = B / 2;
+          GENIE_CUDA(cudaEventRecord(m.ev_fork, s));
+          GENIE_CUDA(cudaStreamWaitEvent(m.stream2, m.ev_fork, 0));
+          decode_step(m, w, b1, cfg);
+          StepBufs w2 = w;
+          w2.h += (size_t)b1 * D; w2.qkv += (size_t)b1 * 3 * D; w2.att += (size_t)b1 * D; w2.tmp += (size_t)b1 * D;
+          w2.h1 += (size_t)b1 * D; w2.ff += (size_t)b1 * 4 * D; w2.logits += (size_t)b1 * V;
+          w2.part += (size_t)b1 * D; w2.part2 += (size_t)b1 * D; w2.hist += (size_t)b1 * w.hist_ld; w2.hist_len += b1; w2.kv_len += b1;
+          w2.active += b1; w2.stop_step += b1; w2.kv += (size_t)b1 * w.utt_stride;
+          w2.part_stride = w.part_stride;
+          cudaStream_t keep = m.stream;
+          m.stream = m.stream2;
+          try { decode_step(m, w2, B - b1, cfg); } catch (...) { m.stream = keep; throw; }
+          m.stream = keep;
+          GENIE_CUDA(cudaEventRecord(m.ev_join, m.stream2));
+          GENIE_CUDA(cudaStreamWaitEvent(s, m.ev_join, 0));
+        } else {
+          decode_step(m, w, B, cfg);
+        }
       } catch (...) {
         cudaStreamEndCapture(s, &g);
         if (g) cudaGraphDestroy(g);

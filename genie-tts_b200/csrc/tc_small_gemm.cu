@@ -1,0 +1,252 @@
+// Single-shot tcgen05 GEMM for the decode step of a batch (8 < rows <= 128):
+//   P[ks][rows, N-tile] = act_in(sum_s X_s + a_bias)[rows, K-slice ks] . W[N-tile, K-slice ks]^T
+// One CTA owns a 256-wide K slice and an NT-wide N tile.  The whole slice of both operands is
+// brought into shared memory at once (every global load of the CTA is in flight before the first
+// store), one barrier, 32 back-to-back MMAs (x_hi and x_lo against the fp16-exact weights), one
+// commit: the latency chain is launch -> loads -> MMA -> read-out instead of 8 dependent k-blocks.
+// Outputs are raw split-K partials; the consumers sum them and apply bias / residual / activation:
+// LayerNorm (elementwise.cu), qkv_finish (below) or this kernel's own A-operand loader (FFN2 reads
+// relu(sum FFN1 partials + bias)).
+#include "kernels.cuh"
+
+namespace genie {
+namespace {
+
+constexpr int KS = 256;                       // K slice per CTA
+constexpr int NKB = KS / 64;                  // 4 swizzle-128B k-blocks
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ uint32_t swz(int r, int c8) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256) tc_small_gemm_kernel(SmallGemm p, int* err_flag) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * NT, ks = blockIdx.y, k0 = ks * KS;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sA = smem_raw + (base - smem_u32(smem_raw));     // [hi|lo][NKB][128 x 128 B]
+  uint8_t* sAlo = sA + NKB * 16384;
+  uint8_t* sW = sAlo + NKB * 16384;                          // [NKB][NT x 128 B]
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(NT < 32 ? 32 : NT)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // ---- weights: NT rows x 256 k (fp16 as stored), all loads first
+  constexpr int WIT = NT * 32 / 256;            // uint4 per thread
+  uint4 wv[WIT];
+#pragma unroll
+  for (int it = 0; it < WIT; ++it) {
+    const int idx = tid + it * 256;
+    const int n = idx >> 5, c = idx & 31;       // c: 8-half chunk within the 256-wide slice
+    wv[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (n0 + n < p.N) wv[it] = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)(n0 + n) * p.ldw + k0 + c * 8));
+  }
+  // ---- activations: 128 rows x 256 k fp32 (sum of a_nsplit partials + bias, optional relu) -> fp16 hi/lo
+  const int c4 = tid & 15;                      // float4 column within a 64-wide k-block
+  float4 badd[NKB];
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb)
+    badd[kb] = p.a_bias ? __ldg(reinterpret_cast<const float4*>(p.a_bias + k0 + kb * 64 + c4 * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    float4 av[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = (tid >> 4) + it * 16;
+      av[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < p.M) {
+        const float* src = p.x + (long long)r * p.ldx + k0 + kb * 64 + c4 * 4;
+        av[it] = __ldg(reinterpret_cast<const float4*>(src));
+        for (int sp = 1; sp < p.a_nsplit; ++sp) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src + sp * p.a_stride));
+          av[it].x += t.x; av[it].y += t.y; av[it].z += t.z; av[it].w += t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = (tid >> 4) + it * 16;
+      float4 v = av[it];
+      if (r < p.M) {
+        v.x += badd[kb].x; v.y += badd[kb].y; v.z += badd[kb].z; v.w += badd[kb].w;
+        if (p.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      }
+      const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y);
+      const __half2 l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+      const uint32_t off = (uint32_t)kb * 16384u + swz(r, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+      *reinterpret_cast<uint2*>(sA + off) = pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&l01); pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(sAlo + off) = pk;
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < WIT; ++it) {
+    const int idx = tid + it * 256;
+    const int n = idx >> 5, c = idx & 31;
+    *reinterpret_cast<uint4*>(sW + (c >> 3) * (NT * 128) + swz(n, c & 7)) = wv[it];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t aA = smem_u32(sA), aL = smem_u32(sAlo), aW = smem_u32(sW);
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t db = umma_desc(aW + kb * (NT * 128) + j * 32);
+        umma_f16(tmem, umma_desc(aA + kb * 16384 + j * 32), db, idesc, (uint32_t)((kb | j) != 0));
+        umma_f16(tmem, umma_desc(aL + kb * 16384 + j * 32), db, idesc, 1u);
+      }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(&bar)) : "memory");
+  }
+  // ---- wait for the accumulator (bounded: a wedged pipeline must not hang the GPU)
+  bool ok = false;
+  for (uint32_t i = 0; i < (1u << 22) && !ok; ++i) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    ok = done != 0;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!ok && err_flag) atomicExch(err_flag, 1);
+
+  // ---- read-out: warps 0..3 own TMEM lanes 32w..32w+31 (= output rows); transposed through smem so
+  // that each warp instruction stores one row's 32 consecutive floats
+  if (warp < 4) {
+    float* tile = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // operand buffers are free now
+    float* yb = p.y + (long long)ks * p.split_stride;
+#pragma unroll
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      if (ok && n < p.N) {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int row = warp * 32 + r;
+          if (row < p.M) yb[(long long)row * p.ldy + n] = tile[r * 33 + lane];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem), "r"((uint32_t)(NT < 32 ? 32 : NT)));
+  }
+}
+
+// q[b,:] = sum partials + bias ; K/V rows -> head-major cache at position kv_len[b]
+__global__ void qkv_finish_kernel(const float* __restrict__ part, int nsplit, long long split_stride,
+                                  const float* __restrict__ bias, float* __restrict__ q,
+                                  float* __restrict__ kv_base, long long utt_stride, long long layer_off,
+                                  long long v_off, int cap, const int* __restrict__ kv_len,
+                                  const int* __restrict__ active, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // float4 index over B x 1536 / 4
+  if (i >= B * 384) return;
+  const int b = i / 384, c = (i % 384) * 4;
+  if (active && !active[b]) return;
+  const float* src = part + (long long)b * 1536 + c;
+  float4 v = *reinterpret_cast<const float4*>(src);
+  for (int sp = 1; sp < nsplit; ++sp) {
+    const float4 t = *reinterpret_cast<const float4*>(src + sp * split_stride);
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  }
+  const float4 bb = *reinterpret_cast<const float4*>(bias + c);
+  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+  if (c < 512) {
+    *reinterpret_cast<float4*>(q + (long long)b * 512 + c) = v;
+  } else {
+    const int isv = c >= 1024, col = c - (isv ? 1024 : 512);
+    const int h = col >> 5, e = col & 31;
+    float* dst = kv_base + (long long)b * utt_stride + layer_off + (isv ? v_off : 0) +
+                 ((long long)h * cap + kv_len[b]) * 32 + e;
+    *reinterpret_cast<float4*>(dst) = v;
+  }
+}
+
+template <int NT>
+void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
+  constexpr size_t smem = 2 * NKB * 16384 + (size_t)NKB * NT * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    GENIE_CUDA(cudaFuncSetAttribute(tc_small_gemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  tc_small_gemm_kernel<NT><<<dim3((p.N + NT - 1) / NT, p.K / KS), 256, smem, s>>>(p, err_flag);
+  GENIE_LAUNCHED("tc_small_gemm");
+}
+
+}  // namespace
+
+void launch_tc_small_gemm(const SmallGemm& p, int nt, int* err_flag, cudaStream_t s) {
+  GENIE_CHECK(p.M >= 1 && p.M <= 128 && p.K % KS == 0 && p.ldx % 4 == 0 && p.ldw % 8 == 0, "tc_small_gemm: bad shape");
+  if (nt == 64) launch_nt<64>(p, err_flag, s); else launch_nt<32>(p, err_flag, s);
+}
+
+void launch_qkv_finish(const float* part, int nsplit, long long split_stride, const float* bias, float* q,
+                       float* kv_base, long long utt_stride, long long layer_off, long long v_off, int cap,
+                       const int* kv_len, const int* active, int B, cudaStream_t s) {
+  if (B <= 0) return;
+  qkv_finish_kernel<<<(B * 384 + 255) / 256, 256, 0, s>>>(part, nsplit, split_stride, bias, q, kv_base, utt_stride,
+                                                        layer_off, v_off, cap, kv_len, active, B);
+  GENIE_LAUNCHED("qkv_finish");
+}
+
+}  // namespace genie

@@ -15,6 +15,9 @@ int g_sync_debug = []() { const char* e = getenv("GENIE_SYNC_DEBUG"); return (e 
 Model::~Model() {
   if (step_graph) cudaGraphExecDestroy(step_graph);
   for (void* p : owned) cudaFree(p);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  if (stream2) cudaStreamDestroy(stream2);
   if (stream) cudaStreamDestroy(stream);
 }
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "genie_debug_keep": (C.c_int, [_P, C.c_int]),
     "genie_debug_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "genie_profiler_range": (C.c_int, [C.c_int]),
     "genie_last_timing": (C.c_int, [_P, _P, C.c_int]),
     "genie_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
 }

@@ -123,6 +123,8 @@ int genie_debug_keep(genie_model* m, int enable);
  * 3 = 2 + x_hi.w_lo; exact_w = weights rounded to fp16 (the T2S case) */
 int genie_debug_tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exact_w, float* max_err,
                             float* ref_max);
+/* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture one bench step */
+int genie_profiler_range(int on);
 /* timing of the last call's stages in milliseconds (CUDA events): prefill, decode, total */
 int genie_last_timing(genie_model* m, float* ms, int n);
 /* use CUDA-graph replay for the decode step (default 1) */

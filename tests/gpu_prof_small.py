@@ -13,10 +13,14 @@ prompt = m.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref
 rng = np.random.default_rng(0)
 txs = [make_text_inputs(seed=200 + i, Lt=int(rng.integers(40, 61))) for i in range(B)]
 sp = SamplingParams(seed=3, max_steps=steps, fixed_steps=steps)
+from genie_tts import _native as N
 for it in range(2):
+    if it == 1:
+        N.lib().genie_profiler_range(1)
     ys, idx = m.t2s_generate([prompt] * B, [t["text_seq"] for t in txs], None, sp)
     print("t2s", m.last_timing())
     if vits:
         sems = [y[-steps:] % 1024 for y in ys]
         a = m.vits_decode([prompt] * B, [t["text_seq"] for t in txs], sems)
         print("vits", m.last_timing())
+N.lib().genie_profiler_range(0)

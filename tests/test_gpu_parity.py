@@ -102,10 +102,21 @@ def test_batch_ragged_matches_single_and_oracle(v2):
     B = 10
     txs = [make_text_inputs(seed=200 + i, Lt=9 + 3 * (i % 5), bert=(i % 3 == 0)) for i in range(B)]
     pid = [i % 4 for i in range(B)]
+    m.record_logits(True)
     ys, idx = m.t2s_generate([prompts[p] for p in pid], [t["text_seq"] for t in txs], [t["text_bert"] for t in txs], sp)
+    lg_batch = m.read_logits().reshape(-1, B, 1025)
     for b in (0, 3, 7, 9):
         y1, i1 = m.t2s_generate([prompts[pid[b]]], [txs[b]["text_seq"]], [txs[b]["text_bert"]], sp)
+        lg1 = m.read_logits().reshape(-1, 1, 1025)
+        # logits, not only tokens: random-init attention is near-uniform, so token equality alone is blind to
+        # per-utterance indexing mistakes in the decode path
+        n = min(len(lg1), len(lg_batch))
+        assert np.abs(lg1[:n, 0] - lg_batch[:n, b]).max() < 3e-4
         assert np.array_equal(y1[0], ys[b]) and i1[0] == idx[b]
+    m.record_logits(False)
+    ys_g, idx_g = m.t2s_generate([prompts[p] for p in pid], [t["text_seq"] for t in txs], [t["text_bert"] for t in txs], sp)
+    assert all(np.array_equal(a, b_) for a, b_ in zip(ys, ys_g)) and idx == idx_g      # graph replay == eager
+    for b in (0, 3, 7, 9):
         r = P.t2s_generate(pm, prs[pid[b]]["ref_seq"], prs[pid[b]]["ref_bert"], txs[b]["text_seq"],
                            txs[b]["text_bert"], prs[pid[b]]["ssl_content"], max_steps=steps)
         assert np.array_equal(ys[b], r.y_full[0])
@@ -124,6 +135,46 @@ def test_batch_ragged_matches_single_and_oracle(v2):
         assert snr_db(ref, auds[b]) >= WAVE_SNR_DB
     for p in prompts:
         p.close()
+
+
+def test_v2pp_english_paragraph_shape(v2pp):
+    """Config-3 shape (V2ProPlus, long target text, longer KV) and config-4 shape (non-zero BERT rows):
+    batch of 4 ragged utterances, one checked end to end against the oracle."""
+    from genie_tts.engine import SamplingParams
+    from oracle import gsv_port as P
+    m, pm = v2pp
+    steps = 24
+    pr = make_prompt_inputs(seed=71, Lr=80, Ts=400, n_audio=128000, bert=True, v2pp=True)
+    prompt = _prompt(m, pr)
+    txs = [make_text_inputs(seed=80 + i, Lt=100 + 13 * i, bert=(i % 2 == 0)) for i in range(4)]
+    ys, idx = m.t2s_generate([prompt] * 4, [t["text_seq"] for t in txs], [t["text_bert"] for t in txs],
+                             SamplingParams(greedy=True, max_steps=steps))
+    b = 2
+    r = P.t2s_generate(pm, pr["ref_seq"], pr["ref_bert"], txs[b]["text_seq"], txs[b]["text_bert"], pr["ssl_content"],
+                       max_steps=steps)
+    assert np.array_equal(ys[b], r.y_full[0]) and idx[b] == r.idx
+    sems = [y[-steps:] % 1024 for y in ys]
+    zps = [make_zp_noise(90 + i, steps) for i in range(4)]
+    auds = m.vits_decode([prompt] * 4, [t["text_seq"] for t in txs], sems, zps)
+    ge, gea = P.prompt_encoder_v2pp(pm, pr["ref_audio"], pr["sv_emb"])
+    ref = P.vits_decode(pm, txs[b]["text_seq"], sems[b], ge, gea, zp_noise=torch.as_tensor(zps[b]))
+    assert np.abs(auds[b] - ref).max() <= WAVE_ABS_TOL
+    assert snr_db(ref, auds[b]) >= WAVE_SNR_DB
+    prompt.close()
+
+
+def test_tc_selftest_shapes():
+    """tcgen05 implicit-GEMM (incl. halo-staged multi-tap path) vs the exact SIMT kernel on random data."""
+    import ctypes as C
+    from genie_tts import _native as N
+    L = N.lib()
+    for (M, Cin, Cout, nt, dil) in [(300, 64, 64, 1, 1), (1000, 256, 256, 3, 3), (777, 192, 384, 5, 1),
+                                    (2000, 32, 32, 11, 5), (2000, 16, 16, 7, 3), (640, 24, 24, 11, 1),
+                                    (333, 192, 768, 3, 1), (500, 128, 128, 7, 5), (260, 2048, 512, 1, 1)]:
+        for mode, exact, tol in ((1, 0, 2e-2), (2, 1, 6e-5), (3, 0, 6e-5)):
+            e, r = C.c_float(0), C.c_float(0)
+            N.check(L.genie_debug_tc_selftest(M, Cin, Cout, nt, dil, mode, exact, C.byref(e), C.byref(r)))
+            assert e.value < tol, (M, Cin, Cout, nt, dil, mode, e.value)
 
 
 def test_natural_stop_and_loop_quirks(v2):
