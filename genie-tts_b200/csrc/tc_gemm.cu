@@ -17,15 +17,12 @@
 // Validated against the exact SIMT path (conv_gemm.cu) by genie_debug_tc_selftest and by the
 // end-to-end parity tests.
 #include "common.cuh"
-#include <cstdlib>
 
 namespace genie {
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-// halo staging measured slower than per-tap gathers on B200 (the k-loop is not load-bound): opt-in only
-const bool g_tc_no_halo = [] { const char* e = getenv("GENIE_TC_HALO"); return !(e && e[0] == '1'); }();
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -82,24 +79,8 @@ __device__ __forceinline__ uint32_t swz(int r, int c8) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
 }
 
-// HALO: multi-tap convolutions stage the fp16 input rows [q0 + min_shift, q0 + 127 + max_shift] in shared
-// memory ONCE; every k-block's A tile is then assembled smem->smem (tap shift = row offset), so the
-// activations are read from L2/HBM once per CTA instead of once per tap.
-__host__ __device__ inline int halo_rows(const ConvGemm& p) {
-  const int a = p.in_shift0, b = p.in_shift0 + (p.ntaps - 1) * p.in_shift_step;
-  return 128 + (a > b ? a - b : b - a);
-}
-__host__ __device__ inline int halo_lo(const ConvGemm& p) {
-  const int a = p.in_shift0, b = p.in_shift0 + (p.ntaps - 1) * p.in_shift_step;
-  return a < b ? a : b;
-}
-__host__ __device__ inline unsigned halo_bytes(const ConvGemm& p) {
-  return ((unsigned)(halo_rows(p) * p.Cin * 2) + 1023u) & ~1023u;
-}
-
-template <int NT, int SPLIT_A, int W_LO, bool HALO>
+template <int NT, int SPLIT_A, int W_LO>
 __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
-  static_assert(!HALO || SPLIT_A == 1, "halo staging is single-pass fp16");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
@@ -121,8 +102,6 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   constexpr uint32_t STAGE_BYTES = A_BYTES * SPLIT_A + W_BYTES * (1 + W_LO);
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* sraw = sbase;                             // HALO: [R][Cin] fp16 rows, then the stage ring
-  if (HALO) sbase += halo_bytes(p);
 
   int n_mma = p.Cout - n0;                          // columns this CTA really needs
   if (n_mma > NT) n_mma = NT;
@@ -152,41 +131,6 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   const __half* __restrict__ wlo = p.tc_wlo;
   bool ok = true;
 
-  if (HALO) {
-    const int R = halo_rows(p), lo = halo_lo(p), cq = p.Cin >> 2;
-    const int total = R * cq;
-    for (int b0 = 0; b0 < total; b0 += 128 * 8) {
-      float4 v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = b0 + j * 128 + tid;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < total) {
-          const int rr = idx / cq, c = idx - rr * cq;
-          const int t = q0 + lo + rr;
-          if (t >= 0 && t < Tin) v[j] = __ldg(reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + c * 4));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = b0 + j * 128 + tid;
-        if (idx < total) {
-          float4 w4 = v[j];
-          if (pre != 1.f) {
-            w4.x = w4.x > 0.f ? w4.x : w4.x * pre; w4.y = w4.y > 0.f ? w4.y : w4.y * pre;
-            w4.z = w4.z > 0.f ? w4.z : w4.z * pre; w4.w = w4.w > 0.f ? w4.w : w4.w * pre;
-          }
-          const __half2 h01 = __floats2half2_rn(w4.x, w4.y), h23 = __floats2half2_rn(w4.z, w4.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&h01);
-          pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-          *reinterpret_cast<uint2*>(sraw + (size_t)idx * 8) = pk;      // row-major [R][Cin] halves
-        }
-      }
-    }
-    __syncthreads();
-  }
-
   const int kb_lo = (int)((long long)KB * ks / p.ksplit), kb_hi = (int)((long long)KB * (ks + 1) / p.ksplit);
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
     const int it_k = kb - kb_lo;
@@ -197,9 +141,9 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
     // ---- global loads of the whole stage first (16 + NT/16 independent 16-byte loads per thread in
     // flight), then the buffer-free wait, then convert + swizzled stores: the load latency overlaps the
     // MMAs of the previous stages
-    float4 av[HALO ? 1 : 16];
+    float4 av[16];
     // column group of this thread is the same for all 16 A loads: c4 = tid & 15, rows r = (tid>>4) + 8*it
-    if (!HALO) {
+    {
       const int c4 = tid & 15;
       const int kk = kb * BK + c4 * 4;
       const int tap = kk / p.Cin;
@@ -230,25 +174,9 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
       }
     }
     if (it_k >= 2) ok = mbar_wait(&bars[s], (uint32_t)(((it_k >> 1) - 1) & 1)) && ok;
-    if (HALO) {
-      // ---- A tile from the staged rows: chunk c8 (8 halves) of k-block kb belongs to one tap
-      const int c8 = tid & 7;
-      const int kk = kb * BK + c8 * 8;
-      const int tap = kk / p.Cin;
-      const int ci = kk - tap * p.Cin;
-      const int roff = p.in_shift0 + tap * p.in_shift_step - halo_lo(p);
-      const bool kok = kk < Ktot;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = (tid >> 3) + it * 16;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (kok) u = *reinterpret_cast<const uint4*>(sraw + ((size_t)(r + roff) * p.Cin + ci) * 2);
-        *reinterpret_cast<uint4*>(sA + swz(r, c8)) = u;
-      }
-    }
     // ---- A tile: 128 rows x 64 k (fp32 -> fp16 hi/lo, swizzled)
 #pragma unroll
-    for (int it = 0; it < (HALO ? 0 : 16); ++it) {
+    for (int it = 0; it < 16; ++it) {
       const int r = (tid >> 4) + it * 8, c4 = tid & 15;
       float4 v = av[it];
       if (pre != 1.f) {
@@ -310,12 +238,8 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   float* tile = reinterpret_cast<float*>(sbase) + warp * (32 * 33);
   const int row_base = q0 + warp * 32;
   const float* bias2 = p.bias2 ? p.bias2 + (long long)seg * p.ldb2 : nullptr;
-  const bool plain = p.ksplit == 1;
-  const bool has_res = plain && p.res != nullptr, has_acc = plain && p.accumulate;
   for (int c0 = 0; c0 < n_mma; c0 += 32) {
     uint32_t v[32];
-    const int n = n0 + c0 + lane;                    // this lane's output column
-    const bool col_ok = n < p.Cout && (c0 + lane) < n_mma;
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
     if (n_mma - c0 >= 32) {
       asm volatile(
@@ -341,31 +265,35 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
 #pragma unroll
     for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
     __syncwarp();
+    const int n = n0 + c0 + lane;                    // this lane's output column
+    const bool col_ok = n < p.Cout && (c0 + lane) < n_mma;
     float badd = 0.f;
-    if (col_ok && plain) {
+    if (col_ok && p.ksplit == 1) {
       if (p.bias) badd += p.bias[n];
       if (bias2) badd += bias2[n];
     }
+    const bool plain = p.ksplit == 1;
+    const bool has_res = plain && p.res != nullptr, has_acc = plain && p.accumulate;
 #pragma unroll 1
     for (int r0 = 0; r0 < 32; r0 += 8) {
-      float xv[8], rv[8];
+      float xv[8], rv[8], cv[8];
       long long orow[8];
       bool rok[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {                 // loads of 8 rows are issued before any store
+      for (int i = 0; i < 8; ++i) {                 // all loads of 8 rows are issued before any store
         const int q = row_base + r0 + i;
         const int to = q * p.out_mul + p.out_add;
         rok[i] = ok && col_ok && q < nq && to >= 0 && to < Tout;
         orow[i] = (long long)out0 + to;
         xv[i] = tile[(r0 + i) * 33 + lane];
         rv[i] = (rok[i] && has_res) ? p.res[orow[i] * p.ldr + n] : 0.f;
-        if (rok[i] && has_acc) rv[i] += p.y[orow[i] * p.ldy + n];
+        cv[i] = (rok[i] && has_acc) ? p.y[orow[i] * p.ldy + n] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (!rok[i]) continue;
         float x = xv[i];
-        if (plain) x = apply_act(x + badd, p.act, p.act_slope) * p.out_scale + rv[i];
+        if (plain) x = apply_act(x + badd, p.act, p.act_slope) * p.out_scale + rv[i] + cv[i];
         p.y[(long long)ks * p.split_stride + orow[i] * p.ldy + n] = x;
       }
     }
@@ -382,26 +310,15 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
 template <int NT, int SPLIT_A, int W_LO>
 void launch_tc(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   constexpr size_t smem = 2 * ((size_t)BM * 128 * SPLIT_A + (size_t)NT * 128 * (1 + W_LO)) + 1024;
-  constexpr size_t smem_max = 226 * 1024;   // 227 KB opt-in limit minus the static barriers
   static bool configured = false;
   if (!configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_conv_gemm_kernel<NT, SPLIT_A, W_LO, false>,
+    GENIE_CUDA(cudaFuncSetAttribute(tc_conv_gemm_kernel<NT, SPLIT_A, W_LO>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (SPLIT_A == 1)
-      GENIE_CUDA(cudaFuncSetAttribute(tc_conv_gemm_kernel<NT, 1, W_LO, true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     configured = true;
   }
   const int nq = p.M + p.q_extra;
   dim3 grid((nq + BM - 1) / BM, ((p.Cout + NT - 1) / NT) * p.ksplit, p.B);
-  // halo staging pays when several taps re-read the same rows and the staged rows fit next to the ring
-  const bool halo = SPLIT_A == 1 && p.ntaps > 1 && p.Cin % 8 == 0 && p.ksplit == 1 && !g_tc_no_halo &&
-                    smem + halo_bytes(p) <= smem_max;
-  if (halo) {
-    tc_conv_gemm_kernel<NT, 1, W_LO, true><<<grid, 128, smem + halo_bytes(p), s>>>(p, err_flag);
-  } else {
-    tc_conv_gemm_kernel<NT, SPLIT_A, W_LO, false><<<grid, 128, smem, s>>>(p, err_flag);
-  }
+  tc_conv_gemm_kernel<NT, SPLIT_A, W_LO><<<grid, 128, smem, s>>>(p, err_flag);
   GENIE_LAUNCHED("tc_conv_gemm");
 }
 
