@@ -71,33 +71,40 @@ __global__ void __launch_bounds__(256) tc_small_gemm_kernel(SmallGemm p, int* er
   }
   // ---- activations: 128 rows x 256 k fp32 (sum of a_nsplit partials + bias, optional relu) -> fp16 hi/lo
   const int c4 = tid & 15;                      // float4 column within a 64-wide k-block
-  float4 badd[NKB];
-#pragma unroll
-  for (int kb = 0; kb < NKB; ++kb)
-    badd[kb] = p.a_bias ? __ldg(reinterpret_cast<const float4*>(p.a_bias + k0 + kb * 64 + c4 * 4))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+  // compact loops on purpose: this kernel runs once per CTA, so straight-line code size (cold
+  // instruction fetch) matters more than unrolling (ncu source view, profiles/)
+#pragma unroll 1
   for (int kb = 0; kb < NKB; ++kb) {
     float4 av[8];
+    const float* colp = p.x + k0 + kb * 64 + c4 * 4;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = (tid >> 4) + it * 16;
       av[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < p.M) {
-        const float* src = p.x + (long long)r * p.ldx + k0 + kb * 64 + c4 * 4;
-        av[it] = __ldg(reinterpret_cast<const float4*>(src));
-        for (int sp = 1; sp < p.a_nsplit; ++sp) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(src + sp * p.a_stride));
-          av[it].x += t.x; av[it].y += t.y; av[it].z += t.z; av[it].w += t.w;
-        }
+      if (r < p.M) av[it] = __ldg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx));
+    }
+#pragma unroll 1
+    for (int sp = 1; sp < p.a_nsplit; ++sp) {
+      float4 tv[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = (tid >> 4) + it * 16;
+        tv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < p.M) tv[it] = __ldg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx + sp * p.a_stride));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        av[it].x += tv[it].x; av[it].y += tv[it].y; av[it].z += tv[it].z; av[it].w += tv[it].w;
       }
     }
+    const float4 bb = p.a_bias ? __ldg(reinterpret_cast<const float4*>(p.a_bias + k0 + kb * 64 + c4 * 4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = (tid >> 4) + it * 16;
       float4 v = av[it];
       if (r < p.M) {
-        v.x += badd[kb].x; v.y += badd[kb].y; v.z += badd[kb].z; v.w += badd[kb].w;
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
         if (p.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
       }
       const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(256) tc_small_gemm_kernel(SmallGemm p, int* er
   if (warp < 4) {
     float* tile = reinterpret_cast<float*>(sA) + warp * (32 * 33);    // operand buffers are free now
     float* yb = p.y + (long long)ks * p.split_stride;
-#pragma unroll
+#pragma unroll 1
     for (int c0 = 0; c0 < NT; c0 += 32) {
       uint32_t v[32];
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
