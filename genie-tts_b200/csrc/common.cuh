@@ -83,6 +83,8 @@ struct ConvGemm {
 };
 void launch_conv_gemm(const ConvGemm& p, cudaStream_t s);
 void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s);
+// k-tap convs with the activation halo staged once per CTA (tc_halo_conv.cu); false => not applicable
+bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s);
 bool skinny_gemm_supported(const ConvGemm& p);
 void launch_skinny_gemm(const ConvGemm& p, cudaStream_t s);
 

@@ -17,6 +17,7 @@
 // Validated against the exact SIMT path (conv_gemm.cu) by genie_debug_tc_selftest and by the
 // end-to-end parity tests.
 #include "common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace genie {
 namespace {
@@ -64,26 +65,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
 
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  switch (act) {
-    case ACT_RELU: return v > 0.f ? v : 0.f;
-    case ACT_LRELU: return v > 0.f ? v : v * slope;
-    case ACT_MISH: { float sp = v > 20.f ? v : log1pf(expf(v)); return v * tanhf(sp); }
-    case ACT_TANH: return tanhf(v);
-    default: return v;
-  }
-}
-
 // byte offset of element (row r, 8-half chunk c8) inside a K-major SW128 tile
 __device__ __forceinline__ uint32_t swz(int r, int c8) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
 }
 
+constexpr int NTHR = 256;                           // 8 warps: loaders for the k-loop, 2 x 4 TMEM-quarter epilogue warps
+
 template <int NT, int SPLIT_A, int W_LO>
-__global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
+constexpr size_t tc_smem_bytes() { return 2 * ((size_t)BM * 128 * SPLIT_A + (size_t)NT * 128 * (1 + W_LO)) + 1024; }
+// two CTAs per SM whenever the stage ring allows it: the k-loop of one overlaps the epilogue of the other
+template <int NT, int SPLIT_A, int W_LO>
+constexpr int tc_min_blocks() { return tc_smem_bytes<NT, SPLIT_A, W_LO>() <= 113 * 1024 ? 2 : 1; }
+
+template <int NT, int SPLIT_A, int W_LO>
+__global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int s_to[BM];                          // epilogue: output row of accumulator row (-1 = skip)
+  __shared__ __align__(16) float s_bias[NT];
 
   const int seg = blockIdx.z;
   int in0 = 0, Tin = p.M, out0 = 0, Tout = p.M_out;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   constexpr uint32_t A_BYTES = BM * 128;            // 16 KB
   constexpr uint32_t W_BYTES = NT * 128;
   constexpr uint32_t STAGE_BYTES = A_BYTES * SPLIT_A + W_BYTES * (1 + W_LO);
+  static_assert(2 * STAGE_BYTES >= (NTHR / 32) * tc_epi::TILE_FLOATS * 4, "epilogue tiles alias the stage ring");
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
 
@@ -117,6 +119,23 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // epilogue tables (row offsets, combined bias) are independent of the k-loop: fill them up front
+  const bool plain = p.ksplit == 1;
+  if (tid < BM) {
+    const int q = q0 + tid;
+    const int to = q * p.out_mul + p.out_add;
+    const bool rok = q < nq && to >= 0 && to < Tout;
+    s_to[tid] = rok ? to : -1;
+  }
+  for (int j = tid; j < NT; j += NTHR) {
+    float bsum = 0.f;
+    const int n = n0 + j;
+    if (plain && n < p.Cout) {
+      if (p.bias) bsum += p.bias[n];
+      if (p.bias2) bsum += p.bias2[(long long)seg * p.ldb2 + n];
+    }
+    s_bias[j] = bsum;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -126,10 +145,18 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   const int Ktot = p.ntaps * p.Cin;
   const int KB = p.tc_kpad / BK;
   const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
-  const float pre = p.pre_slope;
+  const float pre = p.pre_slope;                    // 0 <= pre <= 1: lrelu(v) == max(v, v * pre)
   const __half* __restrict__ whi = p.tc_w;
   const __half* __restrict__ wlo = p.tc_wlo;
   bool ok = true;
+
+  // loader geometry: A tile = 128 rows x 16 float4; thread -> column group c4, rows ar0 + 16 * it
+  const int c4 = tid & 15, ar0 = tid >> 4;
+  const uint32_t a_off0 = swz(ar0, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;   // rows step by 16 -> +2048 bytes
+  constexpr int AIT = BM * 16 / NTHR;               // 8
+  constexpr int WIT = (NT * 8 + NTHR - 1) / NTHR;   // uint4 per thread per W tile
+  const int wn0 = tid >> 3, wc8 = tid & 7;          // W tile: rows wn0 + 32 * it, 16-byte chunk wc8
+  const uint32_t w_off0 = swz(wn0, wc8);            // rows step by 32 -> +4096 bytes
 
   const int kb_lo = (int)((long long)KB * ks / p.ksplit), kb_hi = (int)((long long)KB * (ks + 1) / p.ksplit);
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
@@ -138,53 +165,49 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
     uint8_t* st = sbase + (size_t)s * STAGE_BYTES;
     uint8_t* sA = st;
     uint8_t* sW = st + A_BYTES * SPLIT_A;
-    // ---- global loads of the whole stage first (16 + NT/16 independent 16-byte loads per thread in
-    // flight), then the buffer-free wait, then convert + swizzled stores: the load latency overlaps the
-    // MMAs of the previous stages
-    float4 av[16];
-    // column group of this thread is the same for all 16 A loads: c4 = tid & 15, rows r = (tid>>4) + 8*it
+    // ---- all global loads of the stage first (independent 16-byte loads in flight), then the
+    // buffer-free wait, then convert + swizzled stores; the other resident CTA covers the latency
+    float4 av[AIT];
     {
-      const int c4 = tid & 15;
       const int kk = kb * BK + c4 * 4;
       const int tap = kk / p.Cin;
       const int ci = kk - tap * p.Cin;
-      const int tsh = p.in_shift0 + tap * p.in_shift_step;
+      const int t0 = q0 + ar0 + p.in_shift0 + tap * p.in_shift_step;
       const bool kok = kk < Ktot;
+      const float* __restrict__ xp = xg + (long long)t0 * p.ldx + ci;
+      const long long rstep = 16ll * p.ldx;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int r = (tid >> 4) + it * 8;
-        const int t = q0 + r + tsh;
+      for (int it = 0; it < AIT; ++it) {
+        const int t = t0 + it * 16;
         av[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kok && (q0 + r) < nq && t >= 0 && t < Tin)
-          av[it] = __ldg(reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + ci));
+        if (kok && (q0 + ar0 + it * 16) < nq && (unsigned)t < (unsigned)Tin)
+          av[it] = __ldg(reinterpret_cast<const float4*>(xp + it * rstep));
       }
     }
-    constexpr int WIT = NT / 16;                   // NT*8 uint4 per tile / 128 threads
     uint4 wv[WIT], wl[W_LO ? WIT : 1];
+    {
+      const __half* __restrict__ wp = whi + (long long)(n0 + wn0) * p.tc_kpad + kb * BK + wc8 * 8;
+      const long long wdelta = wlo - whi;
 #pragma unroll
-    for (int it = 0; it < WIT; ++it) {
-      const int idx = tid + it * 128;
-      const int n = idx >> 3, c8 = idx & 7;
-      wv[it] = make_uint4(0u, 0u, 0u, 0u);
-      if (W_LO) wl[it] = wv[it];
-      if (n < n_mma && n0 + n < p.Cout) {
-        const long long o = (long long)(n0 + n) * p.tc_kpad + kb * BK + c8 * 8;
-        wv[it] = __ldg(reinterpret_cast<const uint4*>(whi + o));
-        if (W_LO) wl[it] = __ldg(reinterpret_cast<const uint4*>(wlo + o));
+      for (int it = 0; it < WIT; ++it) {
+        const int n = wn0 + it * 32;
+        wv[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (W_LO) wl[it] = wv[it];
+        if (n < n_mma && n0 + n < p.Cout) {
+          wv[it] = __ldg(reinterpret_cast<const uint4*>(wp + (long long)it * 32 * p.tc_kpad));
+          if (W_LO) wl[it] = __ldg(reinterpret_cast<const uint4*>(wp + (long long)it * 32 * p.tc_kpad + wdelta));
+        }
       }
     }
     if (it_k >= 2) ok = mbar_wait(&bars[s], (uint32_t)(((it_k >> 1) - 1) & 1)) && ok;
     // ---- A tile: 128 rows x 64 k (fp32 -> fp16 hi/lo, swizzled)
 #pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int r = (tid >> 4) + it * 8, c4 = tid & 15;
+    for (int it = 0; it < AIT; ++it) {
       float4 v = av[it];
-      if (pre != 1.f) {
-        v.x = v.x > 0.f ? v.x : v.x * pre; v.y = v.y > 0.f ? v.y : v.y * pre;
-        v.z = v.z > 0.f ? v.z : v.z * pre; v.w = v.w > 0.f ? v.w : v.w * pre;
-      }
+      v.x = fmaxf(v.x, v.x * pre); v.y = fmaxf(v.y, v.y * pre);
+      v.z = fmaxf(v.z, v.z * pre); v.w = fmaxf(v.w, v.w * pre);
       const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-      const uint32_t off = swz(r, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;
+      const uint32_t off = a_off0 + (uint32_t)it * 2048u;
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&h01);
       pk.y = *reinterpret_cast<const uint32_t*>(&h23);
@@ -201,11 +224,9 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
     // ---- W tile: n_mma rows x 64 k (pre-packed fp16, zero padded in K)
 #pragma unroll
     for (int it = 0; it < WIT; ++it) {
-      const int idx = tid + it * 128;
-      const int n = idx >> 3, c8 = idx & 7;
-      if (n < n_mma) {
-        *reinterpret_cast<uint4*>(sW + swz(n, c8)) = wv[it];
-        if (W_LO) *reinterpret_cast<uint4*>(sW + W_BYTES + swz(n, c8)) = wl[it];
+      if (wn0 + it * 32 < n_mma) {
+        *reinterpret_cast<uint4*>(sW + w_off0 + (uint32_t)it * 4096u) = wv[it];
+        if (W_LO) *reinterpret_cast<uint4*>(sW + W_BYTES + w_off0 + (uint32_t)it * 4096u) = wl[it];
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
@@ -232,72 +253,28 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (!ok && err_flag) atomicExch(err_flag, 1);
 
-  // ---- epilogue: TMEM lane = output row (warp w owns lanes 32w..32w+31).  Each 32x32 chunk goes
-  // through a padded per-warp smem tile so that global stores / residual loads are row-contiguous
-  // (one 128-byte line per warp instruction) instead of 32 strided rows.
-  float* tile = reinterpret_cast<float*>(sbase) + warp * (32 * 33);
-  const int row_base = q0 + warp * 32;
-  const float* bias2 = p.bias2 ? p.bias2 + (long long)seg * p.ldb2 : nullptr;
-  for (int c0 = 0; c0 < n_mma; c0 += 32) {
-    uint32_t v[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    if (n_mma - c0 >= 32) {
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-    } else {   // 16-column tail (n_mma is a multiple of 16)
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr));
-#pragma unroll
-      for (int j = 16; j < 32; ++j) v[j] = 0u;
+  // ---- epilogue: TMEM lane = output row.  Warp w reads lane quarter (w & 3) and the 32-column chunks
+  // c0 = 32 * (w >> 2) + 64 * i.  Kept lean on purpose (it touches NT/2 outputs per thread): row offsets and
+  // the combined bias come from the shared tables; each 32x32 chunk is transposed through a padded
+  // per-warp tile so that global stores / residual loads are one 128-byte line per warp instruction.
+  tc_epi::Args ea;
+  ea.y = p.y + (long long)ks * p.split_stride;
+  ea.res = plain ? p.res : nullptr; ea.acc = plain && p.accumulate ? p.y : nullptr;
+  ea.ldy = p.ldy; ea.ldr = p.ldr;
+  ea.act = plain ? p.act : (int)ACT_NONE; ea.slope = p.act == ACT_RELU ? 0.f : p.act_slope;
+  ea.oscale = plain ? p.out_scale : 1.f;
+  ea.Cout = p.Cout;
+  ea.vec = tc_epi::vec_ok(ea.y, p.ldy, ea.res, p.ldr, p.Cout);
+  float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
+  const int rq = (warp & 3) * 32;                               // first row of this warp's lane quarter
+  if (ok) {
+    for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
+      uint32_t v[32];
+      const bool full = n_mma - c0 >= 32;
+      tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)c0, full, v);
+      if (full) tc_epi::store_chunk<32>(v, tile, s_bias + c0, s_to + rq, out0, n0 + c0, ea, lane);
+      else tc_epi::store_chunk<16>(v, tile, s_bias + c0, s_to + rq, out0, n0 + c0, ea, lane);
     }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
-    __syncwarp();
-    const int n = n0 + c0 + lane;                    // this lane's output column
-    const bool col_ok = n < p.Cout && (c0 + lane) < n_mma;
-    float badd = 0.f;
-    if (col_ok && p.ksplit == 1) {
-      if (p.bias) badd += p.bias[n];
-      if (bias2) badd += bias2[n];
-    }
-    const bool plain = p.ksplit == 1;
-    const bool has_res = plain && p.res != nullptr, has_acc = plain && p.accumulate;
-#pragma unroll 1
-    for (int r0 = 0; r0 < 32; r0 += 8) {
-      float xv[8], rv[8], cv[8];
-      long long orow[8];
-      bool rok[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {                 // all loads of 8 rows are issued before any store
-        const int q = row_base + r0 + i;
-        const int to = q * p.out_mul + p.out_add;
-        rok[i] = ok && col_ok && q < nq && to >= 0 && to < Tout;
-        orow[i] = (long long)out0 + to;
-        xv[i] = tile[(r0 + i) * 33 + lane];
-        rv[i] = (rok[i] && has_res) ? p.res[orow[i] * p.ldr + n] : 0.f;
-        cv[i] = (rok[i] && has_acc) ? p.y[orow[i] * p.ldy + n] : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (!rok[i]) continue;
-        float x = xv[i];
-        if (plain) x = apply_act(x + badd, p.act, p.act_slope) * p.out_scale + rv[i] + cv[i];
-        p.y[(long long)ks * p.split_stride + orow[i] * p.ldy + n] = x;
-      }
-    }
-    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -309,7 +286,7 @@ __global__ void __launch_bounds__(128) tc_conv_gemm_kernel(ConvGemm p, int* err_
 
 template <int NT, int SPLIT_A, int W_LO>
 void launch_tc(const ConvGemm& p, int* err_flag, cudaStream_t s) {
-  constexpr size_t smem = 2 * ((size_t)BM * 128 * SPLIT_A + (size_t)NT * 128 * (1 + W_LO)) + 1024;
+  constexpr size_t smem = tc_smem_bytes<NT, SPLIT_A, W_LO>();
   static bool configured = false;
   if (!configured) {
     GENIE_CUDA(cudaFuncSetAttribute(tc_conv_gemm_kernel<NT, SPLIT_A, W_LO>,
@@ -318,18 +295,22 @@ void launch_tc(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   }
   const int nq = p.M + p.q_extra;
   dim3 grid((nq + BM - 1) / BM, ((p.Cout + NT - 1) / NT) * p.ksplit, p.B);
-  tc_conv_gemm_kernel<NT, SPLIT_A, W_LO><<<grid, 128, smem, s>>>(p, err_flag);
+  tc_conv_gemm_kernel<NT, SPLIT_A, W_LO><<<grid, NTHR, smem, s>>>(p, err_flag);
   GENIE_LAUNCHED("tc_conv_gemm");
 }
 
 template <int SPLIT_A, int W_LO>
 void dispatch_nt(const ConvGemm& p, int* err_flag, cudaStream_t s) {
-  // smallest tile that covers Cout in one CTA column; wide layers use 256 (or 128 when that tiles exactly)
+  // smallest tile that covers Cout in one CTA column; wide layers take the widest tile whose stage ring
+  // still leaves room for two CTAs per SM (256 for single-pass fp16, 128 for the hi/lo split forms)
+  constexpr bool wide_ok = tc_min_blocks<256, SPLIT_A, W_LO>() == 2;
+  constexpr bool mid_ok = tc_min_blocks<128, SPLIT_A, W_LO>() == 2;
   if (p.tc_nt == 32 || (p.tc_nt == 0 && p.Cout <= 32)) launch_tc<32, SPLIT_A, W_LO>(p, err_flag, s);
   else if (p.tc_nt == 64 || (p.tc_nt == 0 && p.Cout <= 64)) launch_tc<64, SPLIT_A, W_LO>(p, err_flag, s);
   else if (p.tc_nt == 128) launch_tc<128, SPLIT_A, W_LO>(p, err_flag, s);
   else if (p.tc_nt == 256) launch_tc<256, SPLIT_A, W_LO>(p, err_flag, s);
-  else if (p.Cout <= 128 || (p.Cout % 256 != 0 && p.Cout % 128 == 0 && p.Cout > 256))
+  else if (!mid_ok) launch_tc<64, SPLIT_A, W_LO>(p, err_flag, s);
+  else if (!wide_ok || p.Cout <= 128 || (p.Cout % 256 != 0 && p.Cout % 128 == 0 && p.Cout > 256))
     launch_tc<128, SPLIT_A, W_LO>(p, err_flag, s);
   else launch_tc<256, SPLIT_A, W_LO>(p, err_flag, s);
 }
@@ -342,6 +323,7 @@ void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   GENIE_CHECK(p.ksplit >= 1 && p.ksplit <= p.tc_kpad / BK, "tc_conv_gemm: bad ksplit");
   const int nq = p.M + p.q_extra;
   if (nq <= 0 || p.B <= 0) return;
+  if (try_launch_tc_halo_conv(p, err_flag, s)) return;
   const bool wlo = p.tc_wlo != nullptr;
   if (p.tc_split_a) {
     if (wlo) dispatch_nt<2, 1>(p, err_flag, s); else dispatch_nt<2, 0>(p, err_flag, s);

@@ -1,0 +1,335 @@
+// tcgen05 k-tap convolution with the activation tile staged ONCE per CTA (sm_100a).
+//
+// tc_gemm.cu rebuilds the A operand for every tap (an im2col gather: load, convert, swizzled
+// store), which is what bounds the HiFi-GAN resblock convs (k = 3/7/11, dilation 1/3/5): every
+// stage of the generator costs the same ~300 us per tap whatever its width.  Here the CTA loads
+// the rows [q0 + lo, q0 + MT*128 + hi) of the fp32 channels-last input once, applies the
+// pre-activation, rounds to fp16 and stores them as K-major swizzled rows (one 64-channel slab
+// per 128-byte row; 32 / 16 channel layers use the 64B / 32B swizzle modes).  Tap m is then just
+// a shifted view: the A descriptor of MMA (tap, slab, k16 step) starts `shift(m)` rows into the
+// slab.  The k-loop therefore only streams weights: cp.async (16 B, zero register traffic) from
+// the packed fp16 [Cout][K] matrix into a 4-slot ring of swizzled [NT x 64] tiles, MMAs issued
+// two slots behind the loads, slot reuse gated by tcgen05.commit -> mbarrier.
+//
+// MT accumulators of 128 rows each live side by side in TMEM, so narrow layers (NT = 16/32)
+// amortise the halo (up to 50 rows) and the per-CTA setup over 512 output rows.
+//
+// Epilogue as in tc_gemm.cu: tcgen05.ld -> bias/activation in registers -> per-warp padded
+// transpose -> coalesced row stores with the residual / accumulate adds.
+#include "common.cuh"
+#include "tc_epilogue.cuh"
+
+#include <cstdlib>
+
+namespace genie {
+namespace {
+
+constexpr int NTHR = 256;
+constexpr int NSLOT = 4;                            // weight ring slots (loads run 2 iterations ahead)
+constexpr int AHEAD = 2;
+constexpr size_t EPI_BYTES = (NTHR / 32) * tc_epi::TILE_FLOATS * 4;
+
+struct HaloGeom {
+  int lo = 0;                 // smallest tap shift: halo row rr holds input row q0 + lo + rr
+  int R = 0;                  // rows staged per CTA
+  int slabs = 1;              // 64-channel slabs (1 for Cin <= 64)
+  uint32_t slab_bytes = 0;
+  int U = 1, NU = 1, NI = 1;  // units (tap, slab) per ring slot / total / ring iterations
+  uint32_t slot_bytes = 0;
+  int flags = 0;              // debug: 1 force wide layers onto this path, 2 skip halo load, 4 skip MMAs, 8 skip epilogue stores, 16 skip weight loads
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {   // bounded: false on timeout
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+
+template <int NT, int MT, int ROWB>
+__global__ void __launch_bounds__(NTHR, 2) tc_halo_conv_kernel(ConvGemm p, HaloGeom g, int* err_flag) {
+  constexpr int KS = ROWB / 2;                      // channels per shared-memory row
+  constexpr int CH = ROWB / 16;                     // 16-byte chunks per row
+  constexpr uint32_t SWMASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;     // Swizzle<3|2|1, 4, 3>
+  constexpr uint64_t LAYOUT = ROWB == 128 ? 2 : ROWB == 64 ? 4 : 6;        // SWIZZLE_128B / 64B / 32B
+  constexpr uint32_t SBO = 8 * ROWB;                // 8-row group pitch
+  constexpr uint32_t UNIT_BYTES = NT * ROWB;        // one (tap, slab) weight tile
+  constexpr uint32_t TCOLS = MT * NT < 32 ? 32 : MT * NT;
+  constexpr int ROWS = MT * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NSLOT];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_to[ROWS];                        // output row of accumulator row (or -1)
+  __shared__ __align__(16) float s_bias[NT < 32 ? 32 : NT];
+
+  const int seg = blockIdx.z;
+  int in0 = 0, Tin = p.M, out0 = 0, Tout = p.M_out;
+  if (p.in_off) { in0 = p.in_off[seg]; Tin = p.in_off[seg + 1] - in0; }
+  if (p.out_off) { out0 = p.out_off[seg]; Tout = p.out_off[seg + 1] - out0; }
+  const int nq = Tin + p.q_extra;
+  const int q0 = blockIdx.x * ROWS;
+  if (q0 >= nq) return;
+  const int n0 = (int)blockIdx.y * NT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base;
+  const uint32_t sW = base + (uint32_t)g.slabs * g.slab_bytes;
+
+  int n_mma = p.Cout - n0;
+  if (n_mma > NT) n_mma = NT;
+  n_mma = (n_mma + 15) & ~15;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"(TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int r = tid; r < ROWS; r += NTHR) {
+    const int q = q0 + r;
+    const int to = q * p.out_mul + p.out_add;
+    s_to[r] = (q < nq && to >= 0 && to < Tout) ? to : -1;
+  }
+  for (int j = tid; j < NT; j += NTHR) {
+    float bsum = 0.f;
+    const int n = n0 + j;
+    if (n < p.Cout) {
+      if (p.bias) bsum += p.bias[n];
+      if (p.bias2) bsum += p.bias2[(long long)seg * p.ldb2 + n];
+    }
+    s_bias[j] = bsum;
+  }
+
+  const __half* __restrict__ whi = p.tc_w;
+  // ---- weight ring: iteration `it` = units [it*U, it*U + nu) into slot it % NSLOT
+  auto load_w = [&](int it) {
+    if (g.flags & 16) return;
+    const int u0 = it * g.U;
+    const int nu = min(g.U, g.NU - u0);
+    const uint32_t dst = sW + (uint32_t)(it % NSLOT) * g.slot_bytes;
+    const int total = nu * (NT * CH);
+    for (int idx = tid; idx < total; idx += NTHR) {
+      const int c = idx % CH, n = (idx / CH) % NT, ul = idx / (CH * NT);
+      if (n >= n_mma) continue;
+      const int u = u0 + ul;
+      const int tap = u / g.slabs, sl = u - tap * g.slabs;
+      const bool valid = n0 + n < p.Cout;
+      const __half* src = whi + (long long)(n0 + n) * p.tc_kpad + tap * p.Cin + sl * 64 + c * 8;
+      const uint32_t off = (uint32_t)(n * ROWB + c * 16);
+      cp_async16(dst + (uint32_t)ul * UNIT_BYTES + (off ^ (((off >> 7) & SWMASK) << 4)), valid ? src : whi,
+                 valid ? 16 : 0);
+    }
+  };
+#pragma unroll
+  for (int it = 0; it < AHEAD; ++it) {
+    if (it < g.NI) load_w(it);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // ---- activation halo tile: each input element is loaded, activated, rounded and stored once
+  if (!(g.flags & 2)) {
+    const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
+    const float pre = p.pre_slope;                  // 0 <= pre <= 1: lrelu(v) == max(v, v * pre)
+    const int cq = p.Cin >> 2;                      // float4 per row
+    const int totalA = g.R * cq;
+    const int tbase = q0 + g.lo;
+    for (int i0 = 0; i0 < totalA; i0 += NTHR * 8) {
+      float4 v[8];
+      uint32_t so[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = i0 + k * NTHR + tid;
+        const int rr = idx / cq, f = idx - rr * cq;
+        const int t = tbase + rr;
+        const int c = f * 4;
+        const uint32_t off = (uint32_t)(rr * ROWB + (c & 63) * 2);
+        so[k] = idx < totalA ? (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & SWMASK) << 4)) : 0xffffffffu;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < totalA && (unsigned)t < (unsigned)Tin)
+          v[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + c));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (so[k] == 0xffffffffu) continue;
+        float4 a = v[k];
+        a.x = fmaxf(a.x, a.x * pre); a.y = fmaxf(a.y, a.y * pre);
+        a.z = fmaxf(a.z, a.z * pre); a.w = fmaxf(a.w, a.w * pre);
+        const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(sbase + so[k]) = pk;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t desc_hi = ((uint64_t)(SBO >> 4) << 32) | ((uint64_t)1 << 46) | (LAYOUT << 61) | ((uint64_t)1 << 16);
+  bool ok = true;
+
+  for (int it = 0; it < g.NI; ++it) {
+    const int nx = it + AHEAD;                      // prefetch two iterations ahead
+    if (nx < g.NI) {
+      if (nx >= NSLOT) ok = mbar_wait(&bars[nx % NSLOT], (uint32_t)((nx / NSLOT - 1) & 1)) && ok;
+      load_w(nx);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic / cp.async writes -> tensor-core reads
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int u0 = it * g.U;
+      const int nu = min(g.U, g.NU - u0);
+      const uint32_t wslot = sW + (uint32_t)(it % NSLOT) * g.slot_bytes;
+      for (int ul = 0; ul < ((g.flags & 4) ? 0 : nu); ++ul) {
+        const int u = u0 + ul;
+        const int tap = u / g.slabs, sl = u - tap * g.slabs;
+        const int shift = p.in_shift0 + tap * p.in_shift_step - g.lo;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int j = 0; j < KS / 16; ++j) {
+            const uint32_t aaddr = sA + (uint32_t)sl * g.slab_bytes + (uint32_t)(mt * 128 + shift) * ROWB + j * 32;
+            const uint32_t waddr = wslot + (uint32_t)ul * UNIT_BYTES + j * 32;
+            const uint64_t da = desc_hi | (uint64_t)((aaddr & 0x3FFFFu) >> 4);
+            const uint64_t db = desc_hi | (uint64_t)((waddr & 0x3FFFFu) >> 4);
+            umma_f16(tmem + (uint32_t)(mt * NT), da, db, idesc, (uint32_t)((u | j) != 0));
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                   ::"r"(smem_u32(&bars[it % NSLOT])) : "memory");
+    }
+  }
+  {
+    const int last = g.NI - 1;
+    ok = mbar_wait(&bars[last % NSLOT], (uint32_t)((last / NSLOT) & 1)) && ok;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!ok && err_flag) atomicExch(err_flag, 1);
+  __syncthreads();                                  // every warp is past its waits: the tile region can be reused
+
+  // ---- epilogue: chunk = (accumulator mt, 32 columns); warp w takes lane quarter (w & 3) of the chunks
+  // with index parity (w >> 2)
+  tc_epi::Args ea;
+  ea.y = p.y; ea.res = p.res; ea.acc = p.accumulate ? p.y : nullptr;
+  ea.ldy = p.ldy; ea.ldr = p.ldr;
+  ea.act = p.act; ea.slope = p.act == ACT_RELU ? 0.f : p.act_slope; ea.oscale = p.out_scale;
+  ea.Cout = p.Cout;
+  ea.vec = tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout);
+  float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
+  const int rq = (warp & 3) * 32;
+  const int ncc = (n_mma + 31) >> 5;                // column chunks per accumulator
+  if (ok && !(g.flags & 8)) {
+    for (int chunk = warp >> 2; chunk < MT * ncc; chunk += 2) {
+      const int mt = chunk / ncc, c0 = (chunk - mt * ncc) * 32;
+      if (q0 + mt * 128 >= nq) break;
+      uint32_t v[32];
+      const bool full = n_mma - c0 >= 32;
+      tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)(mt * NT + c0), full, v);
+      if (full) tc_epi::store_chunk<32>(v, tile, s_bias + c0, s_to + mt * 128 + rq, out0, n0 + c0, ea, lane);
+      else tc_epi::store_chunk<16>(v, tile, s_bias + c0, s_to + mt * 128 + rq, out0, n0 + c0, ea, lane);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS));
+  }
+}
+
+template <int NT, int MT, int ROWB>
+bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
+  HaloGeom g;
+  const int s_first = p.in_shift0, s_last = p.in_shift0 + (p.ntaps - 1) * p.in_shift_step;
+  g.lo = s_first < s_last ? s_first : s_last;
+  const int hi = s_first < s_last ? s_last : s_first;
+  g.R = MT * 128 + (hi - g.lo);
+  g.slabs = p.Cin > 64 ? p.Cin / 64 : 1;
+  g.slab_bytes = (uint32_t)(((size_t)g.R * ROWB + 1023) / 1024 * 1024);
+  g.NU = p.ntaps * g.slabs;
+  g.U = 16384 / (NT * ROWB);
+  if (g.U < 1) g.U = 1;
+  if (g.U > g.NU) g.U = g.NU;
+  g.NI = (g.NU + g.U - 1) / g.U;
+  g.slot_bytes = (uint32_t)g.U * NT * ROWB;
+  g.flags = flags;
+  const int nslots = g.NI < NSLOT ? g.NI : NSLOT;
+  size_t smem = (size_t)g.slabs * g.slab_bytes + (size_t)nslots * g.slot_bytes;
+  if (smem < EPI_BYTES) smem = EPI_BYTES;
+  smem += 1024;
+  if (smem > 200 * 1024) return false;
+  static size_t configured = 0;
+  if (smem > configured) {
+    GENIE_CUDA(cudaFuncSetAttribute(tc_halo_conv_kernel<NT, MT, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    configured = smem;
+  }
+  const int nq = p.M + p.q_extra;
+  dim3 grid((nq + MT * 128 - 1) / (MT * 128), (p.Cout + NT - 1) / NT, p.B);
+  tc_halo_conv_kernel<NT, MT, ROWB><<<grid, NTHR, smem, s>>>(p, g, err_flag);
+  GENIE_LAUNCHED("tc_halo_conv");
+  return true;
+}
+
+// GENIE_TC_HALO: -1 disables the path, > 0 = debug flags (HaloGeom::flags); default 0 = on
+int halo_mode() {
+  static int mode = [] {
+    const char* e = getenv("GENIE_TC_HALO");
+    return e ? atoi(e) : 0;
+  }();
+  return mode;
+}
+
+}  // namespace
+
+// k-tap convs whose activation halo fits in shared memory; false => caller uses tc_conv_gemm
+bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
+  const int mode = halo_mode();
+  if (mode < 0) return false;
+  if (p.ntaps < 2 || p.tc_wlo != nullptr || p.tc_split_a || p.ksplit != 1 || p.tc_nt != 0) return false;
+  if (p.pre_slope < 0.f || p.pre_slope > 1.f) return false;
+  if (p.act != ACT_NONE && p.act != ACT_RELU && p.act != ACT_LRELU) return false;
+  if (p.ldx % 4 != 0) return false;
+  if (p.M + p.q_extra <= 0 || p.B <= 0) return true;
+  if (p.Cin == 16 && p.Cout <= 16) return launch_halo<16, 4, 32>(p, mode, err_flag, s);
+  if (p.Cin == 32 && p.Cout <= 32) return launch_halo<32, 4, 64>(p, mode, err_flag, s);
+  // wider layers: the per-tap gather of tc_gemm.cu at two CTAs per SM is faster than one halo CTA per SM
+  // (measured: C=256 k=11 586 vs 1269 us, C=128 k=7 1067 vs 1194 us) unless forced for testing
+  if (p.Cin % 64 != 0 || (p.Cin > 64 && !(mode & 1))) return false;
+  if (p.Cout <= 64) return launch_halo<64, 2, 128>(p, mode, err_flag, s);
+  return launch_halo<128, 1, 128>(p, mode, err_flag, s);
+}
+
+}  // namespace genie
