@@ -14,6 +14,7 @@ namespace {
 
 constexpr int KS = 256;                       // K slice per CTA
 constexpr int NKB = KS / 64;                  // 4 swizzle-128B k-blocks
+constexpr int NTHR = 512;                     // 16 warps: the whole A slice of the CTA is one batch of loads
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -37,7 +38,7 @@ __device__ __forceinline__ uint32_t swz(int r, int c8) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(256) tc_small_gemm_kernel(SmallGemm p, int* err_flag) {
+__global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* err_flag) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -60,49 +61,54 @@ __global__ void __launch_bounds__(256) tc_small_gemm_kernel(SmallGemm p, int* er
   }
 
   // ---- weights: NT rows x 256 k (fp16 as stored), all loads first
-  constexpr int WIT = NT * 32 / 256;            // uint4 per thread
+  constexpr int WIT = (NT * 32 + NTHR - 1) / NTHR;          // uint4 per thread
   uint4 wv[WIT];
 #pragma unroll
   for (int it = 0; it < WIT; ++it) {
-    const int idx = tid + it * 256;
+    const int idx = tid + it * NTHR;
     const int n = idx >> 5, c = idx & 31;       // c: 8-half chunk within the 256-wide slice
     wv[it] = make_uint4(0u, 0u, 0u, 0u);
-    if (n0 + n < p.N) wv[it] = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)(n0 + n) * p.ldw + k0 + c * 8));
+    if (n < NT && n0 + n < p.N) wv[it] = __ldg(reinterpret_cast<const uint4*>(p.w + (long long)(n0 + n) * p.ldw + k0 + c * 8));
   }
-  // ---- activations: 128 rows x 256 k fp32 (sum of a_nsplit partials + bias, optional relu) -> fp16 hi/lo
+  // ---- activations: 128 rows x 256 k fp32 (sum of a_nsplit partials + bias, optional relu) -> fp16 hi/lo.
+  // The kernel is one dependent chain (launch -> loads -> MMA -> read-out), so the whole slice of a
+  // partial is in flight at once: 16 float4 per thread (row r0 + 32*i, k-block kb, i = j >> 2, kb = j & 3)
+  // = one L2 round trip per partial instead of one per k-block.
   const int c4 = tid & 15;                      // float4 column within a 64-wide k-block
-  // compact loops on purpose: this kernel runs once per CTA, so straight-line code size (cold
-  // instruction fetch) matters more than unrolling (ncu source view, profiles/)
-#pragma unroll 1
-  for (int kb = 0; kb < NKB; ++kb) {
-    float4 av[8];
-    const float* colp = p.x + k0 + kb * 64 + c4 * 4;
+  const int r0 = tid >> 4;                      // 0..31
+  float4 av[16];
+  {
+    const float* colp = p.x + k0 + c4 * 4;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = (tid >> 4) + it * 16;
-      av[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < p.M) av[it] = __ldg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx));
+    for (int j = 0; j < 16; ++j) {
+      const int r = r0 + (j >> 2) * 32;
+      av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < p.M) av[j] = __ldg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx + (j & 3) * 64));
     }
 #pragma unroll 1
     for (int sp = 1; sp < p.a_nsplit; ++sp) {
-      float4 tv[8];
+      const float* cs = colp + sp * p.a_stride;
+      float4 tv[16];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = (tid >> 4) + it * 16;
-        tv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < p.M) tv[it] = __ldg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx + sp * p.a_stride));
+      for (int j = 0; j < 16; ++j) {
+        const int r = r0 + (j >> 2) * 32;
+        tv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < p.M) tv[j] = __ldg(reinterpret_cast<const float4*>(cs + (long long)r * p.ldx + (j & 3) * 64));
       }
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        av[it].x += tv[it].x; av[it].y += tv[it].y; av[it].z += tv[it].z; av[it].w += tv[it].w;
-      }
+      for (int j = 0; j < 16; ++j) { av[j].x += tv[j].x; av[j].y += tv[j].y; av[j].z += tv[j].z; av[j].w += tv[j].w; }
     }
+  }
+  // compact loop on purpose: this kernel runs once per CTA, so straight-line code size (cold
+  // instruction fetch) matters more than unrolling (ncu source view, profiles/)
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
     const float4 bb = p.a_bias ? __ldg(reinterpret_cast<const float4*>(p.a_bias + k0 + kb * 64 + c4 * 4))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = (tid >> 4) + it * 16;
-      float4 v = av[it];
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i * 32;
+      float4 v = av[i * 4 + kb];
       if (r < p.M) {
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
         if (p.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -121,9 +127,9 @@ __global__ void __launch_bounds__(256) tc_small_gemm_kernel(SmallGemm p, int* er
   }
 #pragma unroll
   for (int it = 0; it < WIT; ++it) {
-    const int idx = tid + it * 256;
+    const int idx = tid + it * NTHR;
     const int n = idx >> 5, c = idx & 31;
-    *reinterpret_cast<uint4*>(sW + (c >> 3) * (NT * 128) + swz(n, c & 7)) = wv[it];
+    if (n < NT) *reinterpret_cast<uint4*>(sW + (c >> 3) * (NT * 128) + swz(n, c & 7)) = wv[it];
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,7 +242,7 @@ void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
     GENIE_CUDA(cudaFuncSetAttribute(tc_small_gemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  tc_small_gemm_kernel<NT><<<dim3((p.N + NT - 1) / NT, p.K / KS), 256, smem, s>>>(p, err_flag);
+  tc_small_gemm_kernel<NT><<<dim3((p.N + NT - 1) / NT, p.K / KS), NTHR, smem, s>>>(p, err_flag);
   GENIE_LAUNCHED("tc_small_gemm");
 }
 
