@@ -153,45 +153,98 @@ __global__ void __launch_bounds__(128) attention_kernel(Attn p) {
 // Decode attention: grid (H=16, B); 128 threads.  8 lanes x float4 cover one
 // 32-float key row, so each warp-load touches 4 keys = 512 contiguous bytes.
 // ---------------------------------------------------------------------------
+// FUSED: q / k_new / v_new are still split-K partials of the QKV GEMM ([nsplit][B][1536], bias deferred):
+// the CTA finishes its own 3 x 32 columns, appends k_new / v_new to the cache at position kv_len[b] and
+// attends over the kv_len[b] cached tokens plus the new one (replaces qkv_finish + t_add = 1).
+// Four tokens per thread group are loaded per round (8 independent 16-byte loads per thread in flight):
+// the per-CTA chain is ceil(T / 64) HBM round trips instead of ceil(T / 16).
+template <bool FUSED>
 __global__ void __launch_bounds__(128) decode_attention_kernel(
-    const float* __restrict__ q, float* __restrict__ o, const float* __restrict__ kv_base,
-    long long utt_stride, long long layer_off, long long v_off, const int* __restrict__ kv_len,
-    const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
+    const float* __restrict__ q, int nsplit, long long split_stride, const float* __restrict__ bias,
+    float* __restrict__ o, float* __restrict__ kv_base, long long utt_stride, long long layer_off, long long v_off,
+    const int* __restrict__ kv_len, const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
   const int h = blockIdx.x, b = blockIdx.y;
   if (active && !active[b]) return;
-  const int T = kv_len[b] + t_add;
+  const int T = kv_len[b] + (FUSED ? 0 : t_add);           // cached tokens to stream
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;
-  const float* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
-  const float* V = K + v_off;
+  float* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
+  float* V = K + v_off;
 
-  float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + h * 32 + sub * 4);
+  float4 q4, kn = make_float4(0.f, 0.f, 0.f, 0.f), vn = kn;
+  if (FUSED) {
+    const float* pq = q + (long long)b * ldq + h * 32 + sub * 4;
+    q4 = *reinterpret_cast<const float4*>(bias + h * 32 + sub * 4);
+    kn = *reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 4);
+    vn = *reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 4);
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float4 a = *reinterpret_cast<const float4*>(pq + sp * split_stride);
+      const float4 c = *reinterpret_cast<const float4*>(pq + sp * split_stride + 512);
+      const float4 d = *reinterpret_cast<const float4*>(pq + sp * split_stride + 1024);
+      q4.x += a.x; q4.y += a.y; q4.z += a.z; q4.w += a.w;
+      kn.x += c.x; kn.y += c.y; kn.z += c.z; kn.w += c.w;
+      vn.x += d.x; vn.y += d.y; vn.z += d.z; vn.w += d.w;
+    }
+    if (warp == 0 && grp == 0 && T < cap) {
+      *reinterpret_cast<float4*>(K + (long long)T * 32 + sub * 4) = kn;
+      *reinterpret_cast<float4*>(V + (long long)T * 32 + sub * 4) = vn;
+    }
+  } else {
+    q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + h * 32 + sub * 4);
+  }
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
 
   float m = -CUDART_INF_F, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int iters = (T + 15) / 16;
+  const int iters = (T + 63) / 64;
   for (int it = 0; it < iters; ++it) {
-    const int j = it * 16 + warp * 4 + grp;
-    const bool ok = j < T;
-    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = k4;
-    if (ok) {
-      k4 = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
-      v4 = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+    const int j0 = it * 64 + warp * 4 + grp;
+    float4 k4[4], v4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 16;
+      k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); v4[u] = k4[u];
+      if (j < T) {
+        k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
+        v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+      }
     }
-    float s = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (ok) {
-      float m_new = fmaxf(m, s);
-      float c = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
-      float pj = expf(s - m_new);
-      l = l * c + pj;
-      acc.x = acc.x * c + pj * v4.x; acc.y = acc.y * c + pj * v4.y;
-      acc.z = acc.z * c + pj * v4.z; acc.w = acc.w * c + pj * v4.w;
+    float sc[4];
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float t = q4.x * k4[u].x + q4.y * k4[u].y + q4.z * k4[u].z + q4.w * k4[u].w;
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      sc[u] = (j0 + u * 16 < T) ? t : -CUDART_INF_F;
+      m_new = fmaxf(m_new, sc[u]);
+    }
+    if (m_new != -CUDART_INF_F) {
+      const float c = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+      l *= c; acc.x *= c; acc.y *= c; acc.z *= c; acc.w *= c;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pj = (sc[u] == -CUDART_INF_F) ? 0.f : expf(sc[u] - m_new);
+        l += pj;
+        acc.x = fmaf(pj, v4[u].x, acc.x); acc.y = fmaf(pj, v4[u].y, acc.y);
+        acc.z = fmaf(pj, v4[u].z, acc.z); acc.w = fmaf(pj, v4[u].w, acc.w);
+      }
       m = m_new;
     }
+  }
+  if (FUSED && warp == 0 && grp == 0) {                      // the token of this step
+    float t = q4.x * kn.x + q4.y * kn.y + q4.z * kn.z + q4.w * kn.w;
+    t += __shfl_xor_sync(0x000000ffu, t, 1);
+    t += __shfl_xor_sync(0x000000ffu, t, 2);
+    t += __shfl_xor_sync(0x000000ffu, t, 4);
+    const float m_new = fmaxf(m, t);
+    const float c = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+    const float pj = expf(t - m_new);
+    l = l * c + pj;
+    acc.x = acc.x * c + pj * vn.x; acc.y = acc.y * c + pj * vn.y;
+    acc.z = acc.z * c + pj * vn.z; acc.w = acc.w * c + pj * vn.w;
+    m = m_new;
   }
   __shared__ float sm_m[16], sm_l[16], sm_acc[16][32];
   const int g = warp * 4 + grp;
@@ -234,8 +287,17 @@ void launch_decode_attention_raw(const float* q, float* o, const float* kv_base,
                                  long long layer_off, long long v_off, const int* kv_len, const int* active,
                                  int B, int cap, float scale, int t_add, int ldq, cudaStream_t s) {
   if (B <= 0) return;
-  decode_attention_kernel<<<dim3(16, B), 128, 0, s>>>(q, o, kv_base, utt_stride, layer_off, v_off, kv_len,
-                                                      active, cap, scale, t_add, ldq);
+  decode_attention_kernel<false><<<dim3(16, B), 128, 0, s>>>(q, 1, 0, nullptr, o, const_cast<float*>(kv_base), utt_stride,
+                                                             layer_off, v_off, kv_len, active, cap, scale, t_add, ldq);
+  GENIE_LAUNCHED("decode_attention");
+}
+
+void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
+                                   float* kv_base, long long utt_stride, long long layer_off, long long v_off,
+                                   const int* kv_len, const int* active, int B, int cap, float scale, cudaStream_t s) {
+  if (B <= 0) return;
+  decode_attention_kernel<true><<<dim3(16, B), 128, 0, s>>>(part, nsplit, split_stride, bias, o, kv_base, utt_stride,
+                                                            layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
   GENIE_LAUNCHED("decode_attention");
 }
 

@@ -65,6 +65,53 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   for (int i = 0; i < N; ++i) yr[32 * i] = (v[i] - mean) * rstd * g[lane + 32 * i] + b[lane + 32 * i];
 }
 
+// Decode-step LayerNorm (few rows, C = 512): one 128-thread CTA per row, one float4 per thread.  Every
+// load of the row (up to 8 split-K partials, residual, deferred bias, gamma, beta) is issued before the
+// first add, so the kernel is one L2 round trip + two block reductions instead of a chain of
+// partial-pair round trips per warp (8.8 -> ~3 us for the 8-partial FFN2 output at 100 rows).
+__global__ void __launch_bounds__(128) layernorm_row512_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                               const float* __restrict__ g, const float* __restrict__ b,
+                                                               float* __restrict__ y, int nsplit, long long split_stride,
+                                                               const float* __restrict__ lin_bias) {
+  constexpr int C = 512;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* xr = x + (long long)row * C + tid * 4;
+  float4 part[8];
+#pragma unroll
+  for (int sp = 0; sp < 8; ++sp) {
+    part[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sp < nsplit) part[sp] = *reinterpret_cast<const float4*>(xr + sp * split_stride);
+  }
+  float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), lb = rr;
+  if (res) rr = *reinterpret_cast<const float4*>(res + (long long)row * C + tid * 4);
+  if (lin_bias) lb = __ldg(reinterpret_cast<const float4*>(lin_bias + tid * 4));
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g + tid * 4));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(b + tid * 4));
+  float4 v = part[0];
+#pragma unroll
+  for (int sp = 1; sp < 8; ++sp) { v.x += part[sp].x; v.y += part[sp].y; v.z += part[sp].z; v.w += part[sp].w; }
+  v.x += lb.x + rr.x; v.y += lb.y + rr.y; v.z += lb.z + rr.z; v.w += lb.w + rr.w;
+
+  __shared__ float red[2][4];
+  float sum = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((tid & 31) == 0) red[0][tid >> 5] = sum;
+  __syncthreads();
+  const float mean = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / (float)C;
+  const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+  float var = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  if ((tid & 31) == 0) red[1][tid >> 5] = var;
+  __syncthreads();
+  const float rstd = 1.f / sqrtf(((red[1][0] + red[1][1]) + (red[1][2] + red[1][3])) / (float)C + 1e-5f);
+  float4 o4;
+  o4.x = dx * rstd * gg.x + bb.x; o4.y = dy * rstd * gg.y + bb.y;
+  o4.z = dz * rstd * gg.z + bb.z; o4.w = dw * rstd * gg.w + bb.w;
+  *reinterpret_cast<float4*>(y + (long long)row * C + tid * 4) = o4;
+}
+
 __device__ __forceinline__ float pe_value(int pos, int c, const float* div_term) {
   // interleaved sin/cos (t2s_encoder#[71-79]): even c -> sin(pos*div[c/2]), odd -> cos
   float ang = (float)pos * div_term[c >> 1];
@@ -305,6 +352,11 @@ __global__ void transpose_kernel(const float* src, int rows, int cols, float* ds
 void launch_layernorm(const float* x, const float* res, const float* g, const float* b, float* y, int rows, int C,
                       cudaStream_t s, int nsplit, long long split_stride, const float* lin_bias) {
   if (rows <= 0) return;
+  if (C == 512 && rows <= 512 && nsplit <= 8 && (split_stride & 3) == 0) {
+    layernorm_row512_kernel<<<rows, 128, 0, s>>>(x, res, g, b, y, nsplit, split_stride, lin_bias);
+    GENIE_LAUNCHED("layernorm");
+    return;
+  }
   switch (C) {
     case 512: layernorm_kernel<16><<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, nsplit, split_stride, lin_bias); break;
     case 192: layernorm_kernel<6><<<nblk(rows, 8), 256, 0, s>>>(x, res, g, b, y, rows, nsplit, split_stride, lin_bias); break;

@@ -8,6 +8,11 @@ void launch_decode_attention_raw(const float* q, float* o, const float* kv_base,
                                  long long layer_off, long long v_off, const int* kv_len, const int* active,
                                  int B, int cap, float scale, int t_add, int ldq, cudaStream_t s);
 
+// QKV split-K partials [nsplit][B][1536] (+ bias) -> q, append k/v at kv_len[b], attend over kv_len[b] + 1 tokens
+void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
+                                   float* kv_base, long long utt_stride, long long layer_off, long long v_off,
+                                   const int* kv_len, const int* active, int B, int cap, float scale, cudaStream_t s);
+
 // y[r,:] = LN(x[r,:] (+ res[r,:])) * g + b   (eps 1e-5), C multiple of 32, C <= 1024
 // x may be nsplit split-K partials (split_stride apart) with the producer's bias deferred to here
 void launch_layernorm(const float* x, const float* res, const float* g, const float* b, float* y,

@@ -59,10 +59,8 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
         launch_tc_small_gemm(g, nt, m.tc_err, s);
       };
       gemm(L.qkv, w.h, D, 1, nullptr, 0, 32);                                   // 2 partials [B,1536]
-      launch_qkv_finish(w.part, 2, ps * 3, L.qkv.b, w.qkv, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap,
-                        w.kv_len, w.active, B, s);
-      launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
-                                  w.active, B, w.cap, scale, /*t_add=*/1, /*ldq=*/D, s);
+      launch_decode_attention_fused(w.part, 2, ps * 3, L.qkv.b, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off,
+                                    w.kv_len, w.active, B, w.cap, scale, s);
       gemm(L.out, w.att, D, 1, nullptr, 0, 32);                                 // 2 partials [B,512]
       launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 2, ps, L.out.b);
       gemm(L.ff1, w.h1, D, 1, nullptr, 0, 32);                                  // 2 partials [B,2048]
