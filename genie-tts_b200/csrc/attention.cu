@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
     float* __restrict__ o, float* __restrict__ kv_base, long long utt_stride, long long layer_off, long long v_off,
     const int* __restrict__ kv_len, const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
   const int h = blockIdx.x, b = blockIdx.y;
+  if (FUSED) { pdl_trigger(); pdl_wait(); }
   if (active && !active[b]) return;
   const int T = kv_len[b] + (FUSED ? 0 : t_add);           // cached tokens to stream
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -178,9 +179,9 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
     kn = *reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 4);
     vn = *reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 4);
     for (int sp = 0; sp < nsplit; ++sp) {
-      const float4 a = *reinterpret_cast<const float4*>(pq + sp * split_stride);
-      const float4 c = *reinterpret_cast<const float4*>(pq + sp * split_stride + 512);
-      const float4 d = *reinterpret_cast<const float4*>(pq + sp * split_stride + 1024);
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride));          // producer data:
+      const float4 c = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 512));    // via L2, see
+      const float4 d = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 1024));   // common.cuh (PDL)
       q4.x += a.x; q4.y += a.y; q4.z += a.z; q4.w += a.w;
       kn.x += c.x; kn.y += c.y; kn.z += c.z; kn.w += c.w;
       vn.x += d.x; vn.y += d.y; vn.z += d.z; vn.w += d.w;
@@ -296,8 +297,8 @@ void launch_decode_attention_fused(const float* part, int nsplit, long long spli
                                    float* kv_base, long long utt_stride, long long layer_off, long long v_off,
                                    const int* kv_len, const int* active, int B, int cap, float scale, cudaStream_t s) {
   if (B <= 0) return;
-  decode_attention_kernel<true><<<dim3(16, B), 128, 0, s>>>(part, nsplit, split_stride, bias, o, kv_base, utt_stride,
-                                                            layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
+  launch_pdl(decode_attention_kernel<true>, dim3(16, B), dim3(128), 0, s, part, nsplit, split_stride, bias, o, kv_base,
+             utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
   GENIE_LAUNCHED("decode_attention");
 }
 

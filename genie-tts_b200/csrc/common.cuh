@@ -44,6 +44,29 @@ inline void check_launch(const char* what) {
 extern unsigned long long g_launches;
 #define GENIE_LAUNCHED(name) do { ++::genie::g_launches; ::genie::check_launch(name); } while (0)
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch (decode step chain).  A kernel launched through launch_pdl may start while
+// its predecessor in the stream is still running (once every CTA of the predecessor has executed
+// pdl_trigger or exited); it must call pdl_wait() before it reads anything an earlier kernel wrote or
+// writes anything an earlier kernel reads.  Everything before pdl_wait (TMEM allocation, barrier init,
+// loads of constant weights) overlaps the predecessor's tail.  Both are no-ops in a normal launch.
+// ---------------------------------------------------------------------------
+extern int g_pdl;          // GENIE_PDL=0 disables
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  GENIE_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_MISH = 3, ACT_TANH = 4 };
 
 // ---------------------------------------------------------------------------

@@ -75,18 +75,21 @@ __global__ void __launch_bounds__(128) layernorm_row512_kernel(const float* __re
                                                                const float* __restrict__ lin_bias) {
   constexpr int C = 512;
   const int row = blockIdx.x, tid = threadIdx.x;
+  pdl_trigger();
   const float* xr = x + (long long)row * C + tid * 4;
+  float4 lb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lin_bias) lb = __ldg(reinterpret_cast<const float4*>(lin_bias + tid * 4));
+  const float4 gg = __ldg(reinterpret_cast<const float4*>(g + tid * 4));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(b + tid * 4));
+  pdl_wait();
   float4 part[8];
 #pragma unroll
   for (int sp = 0; sp < 8; ++sp) {
     part[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (sp < nsplit) part[sp] = *reinterpret_cast<const float4*>(xr + sp * split_stride);
+    if (sp < nsplit) part[sp] = __ldcg(reinterpret_cast<const float4*>(xr + sp * split_stride));
   }
-  float4 rr = make_float4(0.f, 0.f, 0.f, 0.f), lb = rr;
-  if (res) rr = *reinterpret_cast<const float4*>(res + (long long)row * C + tid * 4);
-  if (lin_bias) lb = __ldg(reinterpret_cast<const float4*>(lin_bias + tid * 4));
-  const float4 gg = __ldg(reinterpret_cast<const float4*>(g + tid * 4));
-  const float4 bb = __ldg(reinterpret_cast<const float4*>(b + tid * 4));
+  float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (res) rr = __ldcg(reinterpret_cast<const float4*>(res + (long long)row * C + tid * 4));
   float4 v = part[0];
 #pragma unroll
   for (int sp = 1; sp < 8; ++sp) { v.x += part[sp].x; v.y += part[sp].y; v.z += part[sp].z; v.w += part[sp].w; }
@@ -353,7 +356,7 @@ void launch_layernorm(const float* x, const float* res, const float* g, const fl
                       cudaStream_t s, int nsplit, long long split_stride, const float* lin_bias) {
   if (rows <= 0) return;
   if (C == 512 && rows <= 512 && nsplit <= 8 && (split_stride & 3) == 0) {
-    layernorm_row512_kernel<<<rows, 128, 0, s>>>(x, res, g, b, y, nsplit, split_stride, lin_bias);
+    launch_pdl(layernorm_row512_kernel, dim3(rows), dim3(128), 0, s, x, res, g, b, y, nsplit, split_stride, lin_bias);
     GENIE_LAUNCHED("layernorm");
     return;
   }

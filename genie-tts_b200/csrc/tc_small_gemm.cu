@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
+  pdl_trigger();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * NT, ks = blockIdx.y, k0 = ks * KS;
 
@@ -76,6 +77,9 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
   // = one L2 round trip per partial instead of one per k-block.
   const int c4 = tid & 15;                      // float4 column within a 64-wide k-block
   const int r0 = tid >> 4;                      // 0..31
+  // weights above are constant; activations come from the predecessor, which may still have been running when
+  // this CTA started: they are read after the wait and through L2 (never the non-coherent path)
+  pdl_wait();
   float4 av[16];
   {
     const float* colp = p.x + k0 + c4 * 4;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
     for (int j = 0; j < 16; ++j) {
       const int r = r0 + (j >> 2) * 32;
       av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < p.M) av[j] = __ldg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx + (j & 3) * 64));
+      if (r < p.M) av[j] = __ldcg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx + (j & 3) * 64));
     }
 #pragma unroll 1
     for (int sp = 1; sp < p.a_nsplit; ++sp) {
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
       for (int j = 0; j < 16; ++j) {
         const int r = r0 + (j >> 2) * 32;
         tv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < p.M) tv[j] = __ldg(reinterpret_cast<const float4*>(cs + (long long)r * p.ldx + (j & 3) * 64));
+        if (r < p.M) tv[j] = __ldcg(reinterpret_cast<const float4*>(cs + (long long)r * p.ldx + (j & 3) * 64));
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) { av[j].x += tv[j].x; av[j].y += tv[j].y; av[j].z += tv[j].z; av[j].w += tv[j].w; }
@@ -242,7 +246,7 @@ void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
     GENIE_CUDA(cudaFuncSetAttribute(tc_small_gemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  tc_small_gemm_kernel<NT><<<dim3((p.N + NT - 1) / NT, p.K / KS), NTHR, smem, s>>>(p, err_flag);
+  launch_pdl(tc_small_gemm_kernel<NT>, dim3((p.N + NT - 1) / NT, p.K / KS), dim3(NTHR), smem, s, p, err_flag);
   GENIE_LAUNCHED("tc_small_gemm");
 }
 
