@@ -164,20 +164,39 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
     float* __restrict__ o, float* __restrict__ kv_base, long long utt_stride, long long layer_off, long long v_off,
     const int* __restrict__ kv_len, const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
   const int h = blockIdx.x, b = blockIdx.y;
-  if (FUSED) { pdl_trigger(); pdl_wait(); }
+  if (FUSED) pdl_trigger();
+  // kv_len / active are written by the sampler, the cache rows < kv_len by earlier steps: all complete before
+  // this step's first kernel started, so they may be read ahead of pdl_wait (only the QKV partials may not)
   if (active && !active[b]) return;
   const int T = kv_len[b] + (FUSED ? 0 : t_add);           // cached tokens to stream
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;
   float* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
   float* V = K + v_off;
+  const int jt = warp * 4 + grp;                            // this thread group's token within a 16-token slab
+
+  auto load_batch = [&](int it, float4 (&k4)[4], float4 (&v4)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = it * 64 + u * 16 + jt;
+      k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); v4[u] = k4[u];
+      if (j < T) {
+        k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
+        v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+      }
+    }
+  };
+  const int iters = (T + 63) / 64;
+  float4 k4[4], v4[4], kx[4], vx[4];
+  load_batch(0, k4, v4);                                    // in flight across the wait below
 
   float4 q4, kn = make_float4(0.f, 0.f, 0.f, 0.f), vn = kn;
   if (FUSED) {
     const float* pq = q + (long long)b * ldq + h * 32 + sub * 4;
-    q4 = *reinterpret_cast<const float4*>(bias + h * 32 + sub * 4);
-    kn = *reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 4);
-    vn = *reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 4);
+    q4 = __ldg(reinterpret_cast<const float4*>(bias + h * 32 + sub * 4));
+    kn = __ldg(reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 4));
+    vn = __ldg(reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 4));
+    pdl_wait();
     for (int sp = 0; sp < nsplit; ++sp) {
       const float4 a = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride));          // producer data:
       const float4 c = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 512));    // via L2, see
@@ -197,19 +216,9 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
 
   float m = -CUDART_INF_F, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int iters = (T + 63) / 64;
   for (int it = 0; it < iters; ++it) {
-    const int j0 = it * 64 + warp * 4 + grp;
-    float4 k4[4], v4[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * 16;
-      k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); v4[u] = k4[u];
-      if (j < T) {
-        k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
-        v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
-      }
-    }
+    if (it + 1 < iters) load_batch(it + 1, kx, vx);         // next round in flight while this one is reduced
+    const int j0 = it * 64 + jt;
     float sc[4];
     float m_new = m;
 #pragma unroll
@@ -233,6 +242,8 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
       }
       m = m_new;
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { k4[u] = kx[u]; v4[u] = vx[u]; }
   }
   if (FUSED && warp == 0 && grp == 0) {                      // the token of this step
     float t = q4.x * kn.x + q4.y * kn.y + q4.z * kn.z + q4.w * kn.w;
