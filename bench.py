@@ -38,6 +38,10 @@ TOKENS = 90
 WORKLOAD = "GPT-SoVITS V2, 100 sentences x ~20 chars (Lr=60, Lt~U{40..60}, 132 prompt tokens, 90-token budget), 1 B200"
 # algorithmic work (measured on the reference graphs)
 GEN_GFLOP_PER_AUDIO_S = 8.26 + 16.52 + 8.26 + 4.13 + 2.06 + 1.36   # HiFi-GAN stages 0-4 + ups
+# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attention launch from the committed
+# `ncu --set full` capture (profiles/); None until that capture exists for the current kernel
+ATT_DRAM_BYTES_NCU = 104438016   # profiles/r01_v5_ncu_full_decode_attention.txt: 100.88 MB read + 3.56 MB written at
+                                 # kv_len ~ 245 per utterance (algorithmic 100.4 MB for that launch)
 
 
 def peaks():
@@ -296,16 +300,34 @@ def main():
     dt, dt_e = tt.tolist()
     audio_s, e_audio = aa.tolist()
 
+    # ---- dominant kernel, timed live: decode_attention sits inside the step's CUDA graph, so the library
+    # replays it on the final KV cache (24 layers back to back, 2.8 GB >> L2) between CUDA events on its stream
+    model.set_option("time_attention", 20)
+    model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev)
+    t_att = model.last_timing()
+    model.set_option("time_attention", 0)
+
     if rank == 0:
         hbm_peak, tf_peak, which = peaks()
-        gen_ms = float(np.mean(stage_ms["generator"]))
+        sm = {k: float(np.mean(v)) for k, v in stage_ms.items()}
         audio_per_step = audio_s / args.steps / world
-        gen_flops = GEN_GFLOP_PER_AUDIO_S * 1e9 * audio_per_step
+        step_ms = 1000 * dt / args.steps
+        # (1) decode attention (HBM): algorithmic bytes = K and V rows of every cached token of one layer, fp32
+        att_us, att_mb = t_att["decode_attention_us"], t_att["decode_attention_kv_mb"]
+        att_gbs = att_mb * 1e6 / (att_us * 1e-6) / 1e9 if att_us > 0 else 0.0
+        att_share = att_us * 1e-3 * 24 * TOKENS / step_ms
+        # (2) generator convs (tensor): BASELINE.md's 40.59 GFLOP per audio-second over the generator stage
         n_gen = max(1, last_t["generator_launches"])
-        achieved = gen_flops / (gen_ms * 1e-3) / 1e12
+        gen_tf = GEN_GFLOP_PER_AUDIO_S * 1e9 * audio_per_step / (sm["generator"] * 1e-3) / 1e12
+        # (3) whole decode step (HBM): fp16 weights + fp32 KV read + KV append per step
+        kv_mb_step = att_mb * 24
+        dec_gbs = (152.364 + kv_mb_step) * 1e6 / (sm["decode"] / TOKENS * 1e-3) / 1e9
+        # (4) prefill (tensor): 150.99 MFLOP per position + 24*4*S^2*512 attention
+        S = np.asarray([60 + len(q) + 132 for q in seqs], dtype=np.float64)
+        pre_tf = float((S * 150.99e6 + 24 * 4 * S * S * 512).sum()) / (sm["prefill"] * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sentences_per_gpu": B, "tokens_per_sentence": TOKENS,
                        "sampling": "top_k=15 T=1.0 rep=1.35 Philox", "l2": "working set (KV cache, vocoder "
@@ -316,13 +338,29 @@ def main():
             "gpu_launches": int(launches),
             "t2s_tokens_per_s": world * B * TOKENS * args.steps / (np.sum(stage_ms["decode"]) * 1e-3) / 1.0
             if stage_ms["decode"] else None,
-            "stage_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+            "stage_ms": sm,
             "first_audio_ms_p50_batch1": first_audio_ms,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "tc_conv_gemm_kernel (tcgen05 implicit-GEMM, HiFi-GAN generator convs)",
-                         "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                         "peak_source": which, "launches_per_step": n_gen,
-                         "avg_launch_ms": gen_ms / n_gen, "traffic": None},
+            "roofline": {"bound": "hbm", "kernel": "decode_attention_kernel<fused> (one query per utterance x head over "
+                         "the fp32 KV cache; largest single kernel of the step)",
+                         "achieved": att_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": att_gbs / hbm_peak,
+                         "peak_source": which, "bytes_per_launch": att_mb * 1e6, "avg_launch_us": att_us,
+                         "launches_per_step": 24 * TOKENS, "share_of_step": att_share,
+                         "timing": "replayed alone after the timed steps, 20 x 24 layers back to back, CUDA events "
+                                   "on the launching stream (inside the step it is a CUDA-graph node)",
+                         "traffic": ATT_DRAM_BYTES_NCU,
+                         "traffic_note": "ncu --set full capture of one launch at kv_len~245 (algorithmic 100.4 MB there; "
+                                         "the replay above runs at the final kv_len)"},
+            "rooflines": [
+                {"stage": "sovits generator convs (tc_conv_gemm / tc_halo_conv, tcgen05)", "bound": "tensor",
+                 "achieved": gen_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gen_tf / tf_peak,
+                 "launches_per_step": n_gen, "avg_launch_ms": sm["generator"] / n_gen,
+                 "share_of_step": sm["generator"] / step_ms},
+                {"stage": "t2s decode step (all kernels, CUDA graph)", "bound": "hbm", "achieved": dec_gbs,
+                 "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "share_of_step": sm["decode"] / step_ms},
+                {"stage": "t2s prefill (tc_conv_gemm split-fp16 + attention)", "bound": "tensor", "achieved": pre_tf,
+                 "peak": tf_peak, "unit": "TFLOP/s", "frac": pre_tf / tf_peak, "share_of_step": sm["prefill"] / step_ms},
+            ],
         }
         if not args.no_cpu_baseline:
             obj, kind = load_cpu_reference(model_dir)

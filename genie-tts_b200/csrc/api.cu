@@ -261,12 +261,13 @@ int genie_profiler_range(int on) {   // cudaProfilerStart/Stop: `ncu --profile-f
 }
 int genie_last_timing(genie_model* h, float* ms, int n) {
   if (!h || !ms) return 1;
-  for (int i = 0; i < n && i < 8; ++i) ms[i] = h->m.timing[i];
+  for (int i = 0; i < n && i < 12; ++i) ms[i] = h->m.timing[i];
   return 0;
 }
 int genie_set_option(genie_model* h, const char* key, int value) {
   if (!h || !key) return 1;
   if (std::strcmp(key, "use_graph") == 0) { h->m.use_graph = value; return 0; }
+  if (std::strcmp(key, "time_attention") == 0) { h->m.time_attention = value; return 0; }
   if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
   if (std::strcmp(key, "decode_split_min") == 0) { h->m.decode_split_min = value; h->m.step_graph_flags = -1; return 0; }

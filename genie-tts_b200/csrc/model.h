@@ -126,7 +126,8 @@ struct Model {
   bool record_logits = false, keep = false;
   std::vector<float> logits_host;
   std::map<std::string, std::vector<float>> kept;
-  float timing[8] = {0};
+  float timing[12] = {0};      // [8] decode-attention us / launch, [9] its KV MB / launch (time_attention option)
+  int time_attention = 0;      // > 0: after t2s_generate replay the fused decode attention this many times per layer
 
   ~Model();
 };
