@@ -332,9 +332,12 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
   float4 q4, kn = make_float4(0.f, 0.f, 0.f, 0.f), vn = kn;
   if (FUSED) {
     const float* pq = q + (long long)b * ldq + h * 32 + sub * 4;
-    q4 = __ldg(reinterpret_cast<const float4*>(bias + h * 32 + sub * 4));
-    kn = __ldg(reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 4));
-    vn = __ldg(reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 4));
+    q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) {                                              // null: the producer already added it
+      q4 = __ldg(reinterpret_cast<const float4*>(bias + h * 32 + sub * 4));
+      kn = __ldg(reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 4));
+      vn = __ldg(reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 4));
+    }
     pdl_wait();
     for (int sp = 0; sp < nsplit; ++sp) {
       const float4 a = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride));          // producer data:

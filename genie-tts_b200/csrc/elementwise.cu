@@ -141,6 +141,7 @@ __global__ void audio_embed_pe_kernel(float* out, const int* tok, const int* pos
 __global__ void decode_embed_kernel(float* out, const int* hist, int hist_ld, const int* hist_len,
                                     const int* active, const float* emb, const float* alpha,
                                     const float* div_term, int prompt_len_is_in_hist) {
+  pdl_trigger();   // launched normally (full barrier after the sampler); lets the QKV GEMM start its weight loads
   const int b = blockIdx.x, c = threadIdx.x;   // 512 threads
   if (active && !active[b]) return;
   const int n = hist_len[b];

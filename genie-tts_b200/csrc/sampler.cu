@@ -45,6 +45,8 @@ __device__ float block_sum(float x, float* sh) {
 }
 
 __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
+  pdl_trigger();
+  pdl_wait();      // logits come from the predecessor GEMM
   __shared__ float raw[V];
   __shared__ float lg[V];
   __shared__ unsigned char taken[V];
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
 void launch_sampler(const SamplerArgs& a, cudaStream_t s) {
   if (a.B <= 0) return;
   GENIE_CHECK(a.top_k >= 1 && a.top_k <= V, "sampler: bad top_k");
-  sampler_kernel<<<a.B, 256, 0, s>>>(a);
+  launch_pdl(sampler_kernel, dim3(a.B), dim3(256), 0, s, a);
   GENIE_LAUNCHED("sampler");
 }
 

@@ -13,9 +13,10 @@ constexpr int CHUNK = 256;     // K elements per pass: 32 lanes x 8 halves (one 
 
 template <int CPW, int NCHUNK>
 __global__ void __launch_bounds__(256) skinny_gemm_kernel(ConvGemm p, int M) {
+  pdl_trigger();                               // the weight loads below overlap the predecessor's tail (PDL)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_base = (blockIdx.x * 8 + warp) * CPW;
-  if (n_base >= p.Cout) return;
+  const bool live = n_base < p.Cout;           // dead warps still take part in the barriers below
   const int ks = blockIdx.y;
   const int k0 = ks * (NCHUNK * CHUNK);
   const __half* __restrict__ W = reinterpret_cast<const __half*>(p.w);
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(ConvGemm p, int M) {
 #pragma unroll
     for (int ch = 0; ch < NCHUNK; ++ch) {
       uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (n < p.Cout)
+      if (live && n < p.Cout)
         u = __ldg(reinterpret_cast<const uint4*>(W + (long long)n * p.w_co_stride + k0 + ch * CHUNK + lane * 8));
       const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -38,19 +39,29 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(ConvGemm p, int M) {
       }
     }
   }
+  pdl_wait();                                  // activations / residual: predecessor data, read through L2
   float* __restrict__ ybase = p.y + (long long)ks * p.split_stride;
-  const float* __restrict__ xb = p.x + k0 + lane * 8;
-  constexpr int RB = 4;                        // rows in flight: their loads are issued before any math
+  constexpr int RB = 4;                        // rows per round
+  constexpr int KL = NCHUNK * CHUNK;           // K elements of this CTA's slice
+  // the rows of a round are staged once per CTA in shared memory (every warp needs all of them; reading them
+  // per warp through L2 cost 8x the weight traffic), 16-byte loads through L2 because they are producer data
+  __shared__ __align__(16) float xs[RB][KL];
   for (int m0 = 0; m0 < M; m0 += RB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < RB * (KL / 4); i += 256) {
+      const int r = i / (KL / 4), c4 = i - r * (KL / 4);
+      const int m = (m0 + r < M) ? m0 + r : M - 1;       // clamp: tail rows are recomputed, not stored
+      *reinterpret_cast<float4*>(&xs[r][c4 * 4]) =
+          __ldcg(reinterpret_cast<const float4*>(p.x + (long long)m * p.ldx + k0 + c4 * 4));
+    }
+    __syncthreads();
     float4 xa[RB][NCHUNK], xc[RB][NCHUNK];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const int m = (m0 + r < M) ? m0 + r : M - 1;       // clamp: tail rows are recomputed, not stored
-      const float* xr = xb + (long long)m * p.ldx;
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch) {
-        xa[r][ch] = __ldg(reinterpret_cast<const float4*>(xr + ch * CHUNK));
-        xc[r][ch] = __ldg(reinterpret_cast<const float4*>(xr + ch * CHUNK + 4));
+        xa[r][ch] = *reinterpret_cast<const float4*>(&xs[r][ch * CHUNK + lane * 8]);
+        xc[r][ch] = *reinterpret_cast<const float4*>(&xs[r][ch * CHUNK + lane * 8 + 4]);
       }
     }
     float acc[RB][CPW];
@@ -78,7 +89,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(ConvGemm p, int M) {
         acc[r][c] = v;
       }
     // lane (r*CPW + c) stores element (row m0+r, column n_base+c)
-    if (lane < RB * CPW) {
+    if (live && lane < RB * CPW) {
       const int r = lane / CPW, c = lane % CPW;
       float v = 0.f;
 #pragma unroll
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(ConvGemm p, int M) {
         if (p.ksplit == 1) {
           if (p.bias) v += p.bias[n];
           if (p.act == ACT_RELU) v = v > 0.f ? v : 0.f;
-          if (p.res) v += p.res[(long long)m * p.ldr + n];
+          if (p.res) v += __ldcg(p.res + (long long)m * p.ldr + n);
         }
         ybase[(long long)m * p.ldy + n] = v;
       }
@@ -120,11 +131,11 @@ void launch_skinny_gemm(const ConvGemm& p, cudaStream_t s) {
   const int cpw = wide ? 4 : 1;
   dim3 grid((p.Cout + 8 * cpw - 1) / (8 * cpw), p.ksplit);
   if (wide) {
-    if (kl == 512) skinny_gemm_kernel<4, 2><<<grid, 256, 0, s>>>(p, p.M);
-    else skinny_gemm_kernel<4, 1><<<grid, 256, 0, s>>>(p, p.M);
+    if (kl == 512) launch_pdl(skinny_gemm_kernel<4, 2>, grid, dim3(256), 0, s, p, p.M);
+    else launch_pdl(skinny_gemm_kernel<4, 1>, grid, dim3(256), 0, s, p, p.M);
   } else {
-    if (kl == 512) skinny_gemm_kernel<1, 2><<<grid, 256, 0, s>>>(p, p.M);
-    else skinny_gemm_kernel<1, 1><<<grid, 256, 0, s>>>(p, p.M);
+    if (kl == 512) launch_pdl(skinny_gemm_kernel<1, 2>, grid, dim3(256), 0, s, p, p.M);
+    else launch_pdl(skinny_gemm_kernel<1, 1>, grid, dim3(256), 0, s, p, p.M);
   }
   GENIE_LAUNCHED("skinny_gemm");
 }

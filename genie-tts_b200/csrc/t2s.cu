@@ -42,6 +42,8 @@ struct StepBufs {
 // one decode step for every active utterance (stage#[12-1821])
 void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   cudaStream_t s = m.stream;
+  struct PdlScope { int prev; explicit PdlScope(int on) : prev(g_pdl_now) { g_pdl_now = on; } ~PdlScope() { g_pdl_now = prev; } };
+  const PdlScope pdl_scope(B > m.skinny_max_rows ? 1 : 0);
   launch_decode_embed(w.h, w.hist, w.hist_ld, w.hist_len, w.active, m.audio_emb, m.audio_alpha, m.div_term, B, s);
   const float scale = 1.0f / std::sqrt(32.0f);
   for (int l = 0; l < NL; ++l) {
@@ -81,10 +83,9 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
     const int nt_w = 0, nt_s = 0, ks_out = 2;
     (void)sk;
     run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B, ACT_NONE, nullptr, 0, tc ? nt_w : 0);
-    launch_kv_scatter(w.qkv, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.cap, nullptr, w.kv_len,
-                      nullptr, B, w.active, s);
-    launch_decode_attention_raw(w.qkv, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len,
-                                w.active, B, w.cap, scale, /*t_add=*/1, /*ldq=*/3 * D, s);
+    // q / k_new / v_new straight from the finished QKV rows: cache append + attention in one kernel
+    launch_decode_attention_fused(w.qkv, 1, 0, nullptr, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off,
+                                  w.kv_len, w.active, B, w.cap, scale, s);
     if (tc) {
       run_linear(m, L.out, w.att, D, w.part, D, B, ACT_NONE, nullptr, 0, nt_s, ks_out, ps);
       launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, ks_out, ps, L.out.b);

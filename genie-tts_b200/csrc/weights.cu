@@ -11,6 +11,7 @@ namespace genie {
 
 unsigned long long g_launches = 0;
 int g_sync_debug = []() { const char* e = getenv("GENIE_SYNC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+int g_pdl_now = 1;
 int g_pdl = []() { const char* e = getenv("GENIE_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 
 Model::~Model() {
