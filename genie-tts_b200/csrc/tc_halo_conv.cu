@@ -67,7 +67,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 
 template <int NT, int MT, int ROWB>
-__global__ void __launch_bounds__(NTHR, 2) tc_halo_conv_kernel(ConvGemm p, HaloGeom g, int* err_flag) {
+__global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_halo_conv_kernel(ConvGemm p, HaloGeom g, int* err_flag) {
   constexpr int KS = ROWB / 2;                      // channels per shared-memory row
   constexpr int CH = ROWB / 16;                     // 16-byte chunks per row
   constexpr uint32_t SWMASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;     // Swizzle<3|2|1, 4, 3>
@@ -279,7 +279,7 @@ bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   g.slabs = p.Cin > 64 ? p.Cin / 64 : 1;
   g.slab_bytes = (uint32_t)(((size_t)g.R * ROWB + 1023) / 1024 * 1024);
   g.NU = p.ntaps * g.slabs;
-  g.U = 16384 / (NT * ROWB);
+  g.U = (NT <= 64 ? 8192 : 16384) / (NT * ROWB);   // ring slot: 8 KB where that buys a third / fourth CTA per SM
   if (g.U < 1) g.U = 1;
   if (g.U > g.NU) g.U = g.NU;
   g.NI = (g.NU + g.U - 1) / g.U;
