@@ -125,9 +125,16 @@ int genie_debug_tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mo
                             float* ref_max);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture one bench step */
 int genie_profiler_range(int on);
-/* timing of the last call's stages in milliseconds (CUDA events): prefill, decode, total */
+/* stage timing of the last calls (CUDA events on the library's stream), up to 12 floats:
+ * [0] prefill ms, [1] decode ms, [2] t2s total ms, [3] decode steps, [4] vits ms, [5] generator ms,
+ * [6] generator launches, [7] latent rows, [8] decode-attention us per launch and [9] its KV MB per launch
+ * (only after a genie_t2s_generate with option time_attention > 0) */
 int genie_last_timing(genie_model* m, float* ms, int n);
-/* use CUDA-graph replay for the decode step (default 1) */
+/* options: use_graph (CUDA-graph replay of the decode step, default 1), use_tc / tc_vits (tensor-core paths),
+ * skinny_max_rows, tc_min_rows, decode_split_min (path selection, debugging),
+ * time_attention (n > 0: after the next t2s_generate replay the decode attention n x 24 times between events).
+ * Environment: GENIE_TC_HALO=-1 disables the halo conv kernel, GENIE_PDL=0 programmatic dependent launch,
+ * GENIE_SYNC_DEBUG=1 synchronises after every launch and names the failing kernel. */
 int genie_set_option(genie_model* m, const char* key, int value);
 
 #ifdef __cplusplus
