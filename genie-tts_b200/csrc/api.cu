@@ -268,6 +268,7 @@ int genie_set_option(genie_model* h, const char* key, int value) {
   if (!h || !key) return 1;
   if (std::strcmp(key, "use_graph") == 0) { h->m.use_graph = value; return 0; }
   if (std::strcmp(key, "time_attention") == 0) { h->m.time_attention = value; return 0; }
+  if (std::strcmp(key, "persistent_step") == 0) { h->m.persistent_step = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
   if (std::strcmp(key, "decode_split_min") == 0) { h->m.decode_split_min = value; h->m.step_graph_flags = -1; return 0; }

@@ -49,6 +49,30 @@ void launch_qkv_finish(const float* part, int nsplit, long long split_stride, co
                        float* kv_base, long long utt_stride, long long layer_off, long long v_off, int cap,
                        const int* kv_len, const int* active, int B, cudaStream_t s);
 
+// ---- persistent decode step for batch <= 8 (t2s_persistent.cu)
+struct StepLayerPtrs {
+  const __half *wqkv, *wout, *wff1, *wff2;
+  const float *bqkv, *bout, *bff1, *bff2, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+struct PersistentStep {
+  const StepLayerPtrs* layers = nullptr; int n_layers = 24;      // device array
+  const __half* wpredict = nullptr; const float* bpredict = nullptr; int vocab = 1025;
+  float* h = nullptr;          // [B,512] in: embedded rows of this step; then the running layer input (residual)
+  float* qkv = nullptr;        // [B,1536]
+  float* part = nullptr;       // [B,16,nch,36] attention partials
+  float* lnin = nullptr;       // [B,512] out-proj + residual (input of LN1)
+  float* lnin2 = nullptr;      // [B,512] FFN2 + residual (input of LN2)
+  float* h1 = nullptr;         // [B,512] LN1 output
+  float* ff = nullptr;         // [B,2048]
+  float* logits = nullptr; int ld_logits = 1025;
+  float* kv = nullptr; long long utt_stride = 0, layer_stride = 0, v_off = 0; int cap = 0;
+  const int* kv_len = nullptr; const int* active = nullptr;
+  unsigned* sync = nullptr;    // [0] barrier counter (zeroed per launch), [1] barrier-timeout flag
+  int B = 1, nch = 1; float scale = 1.f;
+};
+int persistent_step_chunks(int B, int grid);
+void launch_t2s_step_persistent(const PersistentStep& a, int grid, cudaStream_t s);
+
 struct SamplerArgs {
   const float* logits;     // [B, ld]
   int ld;

@@ -122,6 +122,8 @@ struct Model {
   // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo
   int use_tc = 1, tc_vits = 1, tc_min_rows = 9, skinny_max_rows = 8;
   int* tc_err = nullptr;
+  // persistent decode step (batch <= skinny_max_rows): per-layer pointer table, barrier words, grid size
+  void* step_layers_dev = nullptr; unsigned* step_sync = nullptr; int num_sms = 0; int persistent_step = 1;
   // debug
   bool record_logits = false, keep = false;
   std::vector<float> logits_host;

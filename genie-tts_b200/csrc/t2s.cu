@@ -34,10 +34,32 @@ __global__ void hist_to_i64_kernel(const int* hist, int hist_ld, const int* hist
 }
 
 struct StepBufs {
-  float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part, *part2;
+  float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part, *part2, *ppart;
   int *hist, *hist_len, *kv_len, *active, *stop_step;
   float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld; long long part_stride;
 };
+
+// pointer table / barrier words of the persistent step (allocated outside any stream capture)
+void ensure_persistent_step(Model& m) {
+  if (!m.step_layers_dev) {
+    std::vector<StepLayerPtrs> hl(NL);
+    for (int l = 0; l < NL; ++l) {
+      const T2SLayer& L = m.layers[l];
+      hl[l] = StepLayerPtrs{reinterpret_cast<const __half*>(L.qkv.w), reinterpret_cast<const __half*>(L.out.w),
+                            reinterpret_cast<const __half*>(L.ff1.w), reinterpret_cast<const __half*>(L.ff2.w),
+                            L.qkv.b, L.out.b, L.ff1.b, L.ff2.b, L.ln1_g, L.ln1_b, L.ln2_g, L.ln2_b};
+    }
+    StepLayerPtrs* d = nullptr;
+    GENIE_CUDA(cudaMalloc(&d, sizeof(StepLayerPtrs) * NL));
+    GENIE_CUDA(cudaMemcpy(d, hl.data(), sizeof(StepLayerPtrs) * NL, cudaMemcpyHostToDevice));
+    m.owned.push_back(d);
+    m.step_layers_dev = d;
+    GENIE_CUDA(cudaMalloc(&m.step_sync, 2 * sizeof(unsigned)));
+    GENIE_CUDA(cudaMemset(m.step_sync, 0, 2 * sizeof(unsigned)));
+    m.owned.push_back(m.step_sync);
+    GENIE_CUDA(cudaDeviceGetAttribute(&m.num_sms, cudaDevAttrMultiProcessorCount, m.device));
+  }
+}
 
 // one decode step for every active utterance (stage#[12-1821])
 void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
@@ -46,7 +68,21 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   const PdlScope pdl_scope(B > m.skinny_max_rows ? 1 : 0);
   launch_decode_embed(w.h, w.hist, w.hist_ld, w.hist_len, w.active, m.audio_emb, m.audio_alpha, m.div_term, B, s);
   const float scale = 1.0f / std::sqrt(32.0f);
-  for (int l = 0; l < NL; ++l) {
+  const bool persistent = m.persistent_step && B <= 8 && B <= m.skinny_max_rows && m.layers[0].qkv.w_f16 &&
+                          m.predict.w_f16 && w.ppart != nullptr && m.step_layers_dev != nullptr;
+  if (persistent) {
+    // batch <= 8: all 24 layers + logits in one resident kernel (t2s_persistent.cu)
+    PersistentStep a;
+    a.layers = reinterpret_cast<const StepLayerPtrs*>(m.step_layers_dev); a.n_layers = NL;
+    a.wpredict = reinterpret_cast<const __half*>(m.predict.w); a.bpredict = m.predict.b; a.vocab = V;
+    a.h = w.h; a.qkv = w.qkv; a.part = w.ppart; a.lnin = w.tmp; a.lnin2 = w.part2; a.h1 = w.h1; a.ff = w.ff;
+    a.logits = w.logits; a.ld_logits = V;
+    a.kv = w.kv; a.utt_stride = w.utt_stride; a.layer_stride = w.layer_stride; a.v_off = w.v_off; a.cap = w.cap;
+    a.kv_len = w.kv_len; a.active = w.active; a.sync = m.step_sync;
+    a.B = B; a.nch = persistent_step_chunks(B, m.num_sms); a.scale = scale;
+    launch_t2s_step_persistent(a, m.num_sms, s);
+  }
+  for (int l = 0; l < (persistent ? 0 : NL); ++l) {
     const T2SLayer& L = m.layers[l];
     const long long ps = w.part_stride;   // rows of the WHOLE batch
     const bool small_tc = m.use_tc && B > m.skinny_max_rows && B <= 128;
@@ -100,7 +136,7 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
       launch_layernorm(w.tmp, nullptr, L.ln2_g, L.ln2_b, w.h, B, D, s);
     }
   }
-  run_linear(m, m.predict, w.h, D, w.logits, V, B);
+  if (!persistent) run_linear(m, m.predict, w.h, D, w.logits, V, B);
   SamplerArgs a{};
   a.logits = w.logits; a.ld = V; a.hist = w.hist; a.hist_ld = w.hist_ld; a.hist_len = w.hist_len;
   a.kv_len = w.kv_len; a.active = w.active; a.stop_step = w.stop_step; a.B = B;
@@ -305,11 +341,13 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
   w.part = ws.get<float>("t2s.step.part", (size_t)8 * B * D);
   w.part2 = ws.get<float>("t2s.step.part2", (size_t)8 * B * D);
+  w.ppart = ws.get<float>("t2s.step.ppart", (size_t)B * 16 * 8 * 36);
   w.part_stride = (long long)B * D;
   w.logits = LOGITS; w.hist = HIST; w.hist_len = d_histlen; w.kv_len = d_kvlen; w.active = d_active;
   w.stop_step = d_stop; w.kv = KV; w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off;
   w.cap = bt.cap; w.hist_ld = bt.hist_ld;
 
+  if (m.persistent_step && B <= 8) ensure_persistent_step(m);
   // the graph bakes pointers and scalar args; re-capture when any of them changes
   const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (m.use_tc ? 4 : 0) | (cfg.top_k << 4) |
                     (m.tc_min_rows << 16);
@@ -400,6 +438,14 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   }
   GENIE_CUDA(cudaStreamSynchronize(s));
   check_tc_error(m);
+  if (m.step_sync) {
+    unsigned flag[2] = {0, 0};
+    GENIE_CUDA(cudaMemcpy(flag, m.step_sync, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag[1]) {
+      cudaMemset(m.step_sync, 0, sizeof(flag));
+      GENIE_CHECK(false, "persistent decode step: device-wide barrier timed out");
+    }
+  }
   for (int b = 0; b < B; ++b) {
     // reference loop variable at exit: index of the step whose stop flag fired, else last index
     int idx;

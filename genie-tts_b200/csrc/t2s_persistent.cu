@@ -1,0 +1,347 @@
+// Persistent decode step for small batches (rows <= 8): stage_decoder#[12-1821] of ALL 24 layers + logits in
+// ONE kernel launch.
+//
+// At batch 1 a decode step is 152 MB of fp16 weights and ~170 dependent kernels; each kernel boundary costs
+// ~3.8 us however small the kernel, so the step was launch-latency bound (0.64 ms per token).  Here one CTA
+// per SM stays resident for the whole step and the phases of a layer are separated by a device-wide barrier
+// (one atomic arrive + acquire spin, bounded) instead of kernel boundaries:
+//
+//   P1  x = LN2(prev layer) (recomputed by every CTA, 512 floats per row)  ->  QKV GEMV        | barrier
+//   P2  attention partials per (utterance, head, key chunk), cache append of the new k / v      | barrier
+//   P3  combine partials (every CTA)  ->  out-proj GEMV + bias + residual                       | barrier
+//   P4  LN1 (every CTA)               ->  FFN1 GEMV + bias + ReLU                               | barrier
+//   P5  FFN2 GEMV + bias + residual                                                             | barrier
+//
+// GEMV = weight streaming: each warp owns output columns, 16-byte fp16 weight loads (all chunks of up to two
+// columns in flight), fp32 FMA against the activation rows held in shared memory, warp-shuffle reduction.
+// Everything another CTA wrote is read through L2 (ld.global.cg); weights and old cache rows through the
+// read-only path.
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace genie {
+namespace {
+
+constexpr int D = 512, FF = 2048, NH = 16, PART_LD = 36;   // partial: [0] m, [1] l, [4..35] acc
+constexpr int NTHR = 256, NWARP = NTHR / 32;
+
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, unsigned G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += G;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    for (unsigned spins = 0;; ++spins) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if (spins > (1u << 22)) { atomicExch(ctr + 1, 1u); break; }   // never hang the GPU: flag and fall through
+    }
+  }
+  __syncthreads();
+}
+
+// y[r, n] = epi(n, r, sum_k W[n, k] * xs[r, k]) for the columns owned by this warp
+template <int BR, typename Epi>
+__device__ __forceinline__ void gemv(const __half* __restrict__ W, int K, int N, const float* xs, int gwarp,
+                                     int nwarps, int lane, Epi epi) {
+  for (int n0 = gwarp; n0 < N; n0 += 2 * nwarps) {
+    const int n1 = n0 + nwarps;
+    const bool two = n1 < N;
+    float acc0[BR], acc1[BR];
+#pragma unroll
+    for (int r = 0; r < BR; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+    const __half* w0 = W + (long long)n0 * K + lane * 8;
+    const __half* w1 = W + (long long)(two ? n1 : n0) * K + lane * 8;
+    for (int kb = 0; kb < K; kb += 1024) {
+      uint4 u0[4], u1[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int kk = kb + c * 256;
+        if (kk < K) {
+          u0[c] = __ldg(reinterpret_cast<const uint4*>(w0 + kk));
+          u1[c] = __ldg(reinterpret_cast<const uint4*>(w1 + kk));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int kk = kb + c * 256;
+        if (kk < K) {
+          const __half2* h0 = reinterpret_cast<const __half2*>(&u0[c]);
+          const __half2* h1 = reinterpret_cast<const __half2*>(&u1[c]);
+          float wa[8], wb[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 fa = __half22float2(h0[e]), fb = __half22float2(h1[e]);
+            wa[2 * e] = fa.x; wa[2 * e + 1] = fa.y; wb[2 * e] = fb.x; wb[2 * e + 1] = fb.y;
+          }
+#pragma unroll
+          for (int r = 0; r < BR; ++r) {
+            const float4 xa = *reinterpret_cast<const float4*>(xs + r * K + kk + lane * 8);
+            const float4 xb = *reinterpret_cast<const float4*>(xs + r * K + kk + lane * 8 + 4);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              acc0[r] = fmaf(wa[e], xv[e], acc0[r]);
+              acc1[r] = fmaf(wb[e], xv[e], acc1[r]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
+        acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < BR; ++r) {
+      if (lane == r) {
+        epi(n0, r, acc0[r]);
+        if (two) epi(n1, r, acc1[r]);
+      }
+    }
+  }
+}
+
+// xs[r, :] = LN(src[r, :]) * g + b for r < B (one warp per row), zero rows above; optional copy to global
+template <int BR>
+__device__ __forceinline__ void layernorm_rows(float* xs, const float* src, const float* __restrict__ g,
+                                               const float* __restrict__ b, float* gout, int B, int warp, int lane) {
+  for (int r = warp; r < BR; r += NWARP) {
+    float v[16];
+    if (r < B) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldcg(src + (long long)r * D + lane + 32 * i);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sum += v[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / (float)D;
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+      const float rstd = 1.f / sqrtf(var / (float)D + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+        if (gout) gout[(long long)r * D + c] = v[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xs[r * D + lane + 32 * i] = v[i];
+  }
+}
+
+template <int BR>
+__device__ __forceinline__ void load_rows(float* xs, const float* src, int K, int B) {
+  for (int i = threadIdx.x; i < BR * (K / 4); i += NTHR) {
+    const int r = i / (K / 4), c4 = i - r * (K / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < B) v = __ldcg(reinterpret_cast<const float4*>(src + (long long)r * K + c4 * 4));
+    *reinterpret_cast<float4*>(xs + r * K + c4 * 4) = v;
+  }
+}
+
+// one (utterance, head, key chunk): partial softmax statistics over the chunk's keys -> part[36]
+__device__ __forceinline__ void attention_chunk(const PersistentStep& a, int layer, int b, int h, int c, float* sred) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = tid >> 3, sub = tid & 7;                  // 32 groups of 8 lanes, one key per group per pass
+  const int T = a.kv_len[b];                                // cached tokens; the new token is key index T
+  const int total = T + 1;
+  const int cs = (total + a.nch - 1) / a.nch;
+  const int lo = c * cs, hi = min(lo + cs, total);
+  float* K = a.kv + (long long)b * a.utt_stride + (long long)layer * a.layer_stride + (long long)h * a.cap * 32;
+  float* V = K + a.v_off;
+  const float* qrow = a.qkv + (long long)b * 3 * D + h * 32 + sub * 4;
+  float4 q4 = __ldcg(reinterpret_cast<const float4*>(qrow));
+  q4.x *= a.scale; q4.y *= a.scale; q4.z *= a.scale; q4.w *= a.scale;
+
+  float m = -CUDART_INF_F, l = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = lo; j0 < hi; j0 += 64) {                    // two keys per group in flight
+    float4 k4[2], v4[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u * 32 + grp;
+      ok[u] = j < hi;
+      k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); v4[u] = k4[u];
+      if (ok[u]) {
+        if (j < T) {
+          k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
+          v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+        } else {                                            // this step's token: from the QKV rows, and into the cache
+          k4[u] = __ldcg(reinterpret_cast<const float4*>(qrow + D));
+          v4[u] = __ldcg(reinterpret_cast<const float4*>(qrow + 2 * D));
+          if (T < a.cap) {
+            *reinterpret_cast<float4*>(K + (long long)T * 32 + sub * 4) = k4[u];
+            *reinterpret_cast<float4*>(V + (long long)T * 32 + sub * 4) = v4[u];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float s = q4.x * k4[u].x + q4.y * k4[u].y + q4.z * k4[u].z + q4.w * k4[u].w;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (ok[u]) {
+        const float m_new = fmaxf(m, s);
+        const float corr = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+        const float pj = expf(s - m_new);
+        l = l * corr + pj;
+        acc.x = acc.x * corr + pj * v4[u].x; acc.y = acc.y * corr + pj * v4[u].y;
+        acc.z = acc.z * corr + pj * v4[u].z; acc.w = acc.w * corr + pj * v4[u].w;
+        m = m_new;
+      }
+    }
+  }
+  // combine the 32 groups: sred = [32] m | [32] l | [32][32] acc
+  float* sm_m = sred; float* sm_l = sred + 32; float* sm_acc = sred + 64;
+  __syncthreads();
+  if (sub == 0) { sm_m[grp] = m; sm_l[grp] = l; }
+  sm_acc[grp * 32 + sub * 4 + 0] = acc.x; sm_acc[grp * 32 + sub * 4 + 1] = acc.y;
+  sm_acc[grp * 32 + sub * 4 + 2] = acc.z; sm_acc[grp * 32 + sub * 4 + 3] = acc.w;
+  __syncthreads();
+  if (warp == 0) {
+    float M = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) M = fmaxf(M, sm_m[i]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float wgt = (sm_m[i] == -CUDART_INF_F) ? 0.f : expf(sm_m[i] - M);
+      num = fmaf(sm_acc[i * 32 + lane], wgt, num);
+      den = fmaf(sm_l[i], wgt, den);
+    }
+    float* p = a.part + ((long long)(b * NH + h) * a.nch + c) * PART_LD;
+    if (lane == 0) { p[0] = M; p[1] = den; }
+    p[4 + lane] = num;
+  }
+}
+
+template <int BR>
+__global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(PersistentStep a) {
+  extern __shared__ __align__(16) float xs[];               // [BR][2048] activation rows
+  __shared__ float sred[64 + 32 * 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x;
+  const int gwarp = blockIdx.x * NWARP + warp, nwarps = G * NWARP;
+  const int B = a.B;
+  unsigned target = 0;
+
+  for (int l = 0; l < a.n_layers; ++l) {
+    const StepLayerPtrs L = a.layers[l];
+    // ---- P1: layer input rows (embedding for layer 0, LN2 of the previous layer otherwise) -> QKV
+    if (l == 0) {
+      load_rows<BR>(xs, a.h, D, B);
+    } else {
+      const StepLayerPtrs P = a.layers[l - 1];
+      layernorm_rows<BR>(xs, a.lnin2, P.ln2g, P.ln2b, blockIdx.x == 0 ? a.h : nullptr, B, warp, lane);
+    }
+    __syncthreads();
+    gemv<BR>(L.wqkv, D, 3 * D, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
+      if (r < B) a.qkv[(long long)r * 3 * D + n] = v + __ldg(L.bqkv + n);
+    });
+    grid_sync(a.sync, target, G);
+    // ---- P2: attention partials (+ cache append)
+    for (int item = blockIdx.x; item < B * NH * a.nch; item += G) {
+      const int c = item % a.nch, bh = item / a.nch;
+      const int h = bh % NH, b = bh / NH;
+      if (a.active && !a.active[b]) continue;               // CTA-uniform
+      attention_chunk(a, l, b, h, c, sred);
+    }
+    grid_sync(a.sync, target, G);
+    // ---- P3: combine chunks -> attention rows; out-proj + bias + residual
+    for (int i = tid; i < BR * D; i += NTHR) {
+      const int r = i / D, col = i - r * D;
+      float o = 0.f;
+      if (r < B) {
+        const float* p = a.part + (long long)(r * NH + (col >> 5)) * a.nch * PART_LD;
+        float M = -CUDART_INF_F;
+        for (int c = 0; c < a.nch; ++c) M = fmaxf(M, __ldcg(p + c * PART_LD));
+        float num = 0.f, den = 0.f;
+        for (int c = 0; c < a.nch; ++c) {
+          const float mc = __ldcg(p + c * PART_LD);
+          const float wgt = (mc == -CUDART_INF_F) ? 0.f : expf(mc - M);
+          num = fmaf(__ldcg(p + c * PART_LD + 4 + (col & 31)), wgt, num);
+          den = fmaf(__ldcg(p + c * PART_LD + 1), wgt, den);
+        }
+        o = num / den;
+      }
+      xs[i] = o;
+    }
+    __syncthreads();
+    gemv<BR>(L.wout, D, D, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
+      if (r < B) a.lnin[(long long)r * D + n] = v + __ldg(L.bout + n) + __ldcg(a.h + (long long)r * D + n);
+    });
+    grid_sync(a.sync, target, G);
+    // ---- P4: LN1 -> FFN1 (+ ReLU)
+    layernorm_rows<BR>(xs, a.lnin, L.ln1g, L.ln1b, blockIdx.x == 0 ? a.h1 : nullptr, B, warp, lane);
+    __syncthreads();
+    gemv<BR>(L.wff1, D, FF, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
+      if (r < B) a.ff[(long long)r * FF + n] = fmaxf(v + __ldg(L.bff1 + n), 0.f);
+    });
+    grid_sync(a.sync, target, G);
+    // ---- P5: FFN2 + bias + residual
+    load_rows<BR>(xs, a.ff, FF, B);
+    __syncthreads();
+    gemv<BR>(L.wff2, FF, D, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
+      if (r < B) a.lnin2[(long long)r * D + n] = v + __ldg(L.bff2 + n) + __ldcg(a.h1 + (long long)r * D + n);
+    });
+    grid_sync(a.sync, target, G);
+  }
+  // ---- logits from LN2 of the last layer
+  {
+    const StepLayerPtrs P = a.layers[a.n_layers - 1];
+    layernorm_rows<BR>(xs, a.lnin2, P.ln2g, P.ln2b, nullptr, B, warp, lane);
+    __syncthreads();
+    gemv<BR>(a.wpredict, D, a.vocab, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
+      if (r < B) a.logits[(long long)r * a.ld_logits + n] = v + (a.bpredict ? __ldg(a.bpredict + n) : 0.f);
+    });
+  }
+}
+
+template <int BR>
+void launch_br(const PersistentStep& a, int grid, cudaStream_t s) {
+  constexpr size_t smem = (size_t)BR * FF * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    GENIE_CUDA(cudaFuncSetAttribute(t2s_step_persistent_kernel<BR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    configured = true;
+  }
+  t2s_step_persistent_kernel<BR><<<grid, NTHR, smem, s>>>(a);
+}
+
+}  // namespace
+
+int persistent_step_chunks(int B, int grid) {
+  int n = grid / (B * NH);
+  return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+void launch_t2s_step_persistent(const PersistentStep& a, int grid, cudaStream_t s) {
+  GENIE_CHECK(a.B >= 1 && a.B <= 8, "persistent step: batch must be 1..8");
+  GENIE_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(unsigned), s));
+  if (a.B == 1) launch_br<1>(a, grid, s);
+  else if (a.B == 2) launch_br<2>(a, grid, s);
+  else if (a.B <= 4) launch_br<4>(a, grid, s);
+  else launch_br<8>(a, grid, s);
+  GENIE_LAUNCHED("t2s_step_persistent");
+}
+
+}  // namespace genie
