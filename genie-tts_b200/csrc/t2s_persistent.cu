@@ -42,67 +42,90 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, unsig
   __syncthreads();
 }
 
-// y[r, n] = epi(n, r, sum_k W[n, k] * xs[r, k]) for the columns owned by this warp
-template <int BR, typename Epi>
-__device__ __forceinline__ void gemv(const __half* __restrict__ W, int K, int N, const float* xs, int gwarp,
-                                     int nwarps, int lane, Epi epi) {
-  for (int n0 = gwarp; n0 < N; n0 += 2 * nwarps) {
-    const int n1 = n0 + nwarps;
-    const bool two = n1 < N;
-    float acc0[BR], acc1[BR];
+// GEMV in two halves so that the weight (and bias) loads of phase p+1 are issued BEFORE the device-wide
+// barrier that ends phase p: weights are constants, so their HBM latency hides behind the barrier wait.
+// Warp gw owns column gw (and gw + nwarps when TWO); requires N <= (TWO ? 2 : 1) * nwarps.
+template <int KC, bool TWO>
+struct WRegs { uint4 u0[KC]; uint4 u1[TWO ? KC : 1]; float b0, b1; };
+
+template <int KC, bool TWO>
+__device__ __forceinline__ void gemv_prefetch(WRegs<KC, TWO>& w, const __half* __restrict__ W,
+                                              const float* __restrict__ bias, int N, int gwarp, int nwarps, int lane) {
+  constexpr int K = KC * 256;
+  const int n0 = gwarp, n1 = gwarp + nwarps;
+  w.b0 = 0.f; w.b1 = 0.f;
 #pragma unroll
-    for (int r = 0; r < BR; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
-    const __half* w0 = W + (long long)n0 * K + lane * 8;
-    const __half* w1 = W + (long long)(two ? n1 : n0) * K + lane * 8;
-    for (int kb = 0; kb < K; kb += 1024) {
-      uint4 u0[4], u1[4];
+  for (int c = 0; c < KC; ++c) w.u0[c] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int kk = kb + c * 256;
-        if (kk < K) {
-          u0[c] = __ldg(reinterpret_cast<const uint4*>(w0 + kk));
-          u1[c] = __ldg(reinterpret_cast<const uint4*>(w1 + kk));
-        }
-      }
+  for (int c = 0; c < (TWO ? KC : 1); ++c) w.u1[c] = make_uint4(0u, 0u, 0u, 0u);
+  if (n0 < N) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int kk = kb + c * 256;
-        if (kk < K) {
-          const __half2* h0 = reinterpret_cast<const __half2*>(&u0[c]);
-          const __half2* h1 = reinterpret_cast<const __half2*>(&u1[c]);
-          float wa[8], wb[8];
+    for (int c = 0; c < KC; ++c) w.u0[c] = __ldg(reinterpret_cast<const uint4*>(W + (long long)n0 * K + c * 256 + lane * 8));
+    if (bias) w.b0 = __ldg(bias + n0);
+  }
+  if (TWO && n1 < N) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fa = __half22float2(h0[e]), fb = __half22float2(h1[e]);
-            wa[2 * e] = fa.x; wa[2 * e + 1] = fa.y; wb[2 * e] = fb.x; wb[2 * e + 1] = fb.y;
-          }
+    for (int c = 0; c < KC; ++c) w.u1[c] = __ldg(reinterpret_cast<const uint4*>(W + (long long)n1 * K + c * 256 + lane * 8));
+    if (bias) w.b1 = __ldg(bias + n1);
+  }
+}
+
+// out[r, n] = act(W[n, :] . xs[r, :] + bias[n] + res[r, n])
+template <int BR, int KC, bool TWO>
+__device__ __forceinline__ void gemv_compute(const WRegs<KC, TWO>& w, int N, const float* xs, float* out, int ldo,
+                                             const float* res, bool relu, int B, int gwarp, int nwarps, int lane) {
+  constexpr int K = KC * 256;
+  const int n0 = gwarp, n1 = gwarp + nwarps;
+  if (n0 >= N) return;                                      // warp-uniform
+  const bool two = TWO && n1 < N;
+  float r0 = 0.f, r1 = 0.f;                                 // residual (producer data, through L2), issued early
+  if (res && lane < B) {
+    r0 = __ldcg(res + (long long)lane * ldo + n0);
+    if (two) r1 = __ldcg(res + (long long)lane * ldo + n1);
+  }
+  float acc0[BR], acc1[BR];
 #pragma unroll
-          for (int r = 0; r < BR; ++r) {
-            const float4 xa = *reinterpret_cast<const float4*>(xs + r * K + kk + lane * 8);
-            const float4 xb = *reinterpret_cast<const float4*>(xs + r * K + kk + lane * 8 + 4);
-            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+  for (int r = 0; r < BR; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              acc0[r] = fmaf(wa[e], xv[e], acc0[r]);
-              acc1[r] = fmaf(wb[e], xv[e], acc1[r]);
-            }
-          }
-        }
-      }
+  for (int c = 0; c < KC; ++c) {
+    const __half2* h0 = reinterpret_cast<const __half2*>(&w.u0[c]);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&w.u1[TWO ? c : 0]);
+    float wa[8], wb[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(h0[e]), fb = __half22float2(h1[e]);
+      wa[2 * e] = fa.x; wa[2 * e + 1] = fa.y; wb[2 * e] = fb.x; wb[2 * e + 1] = fb.y;
     }
 #pragma unroll
     for (int r = 0; r < BR; ++r) {
+      const float4 xa = *reinterpret_cast<const float4*>(xs + r * K + c * 256 + lane * 8);
+      const float4 xb = *reinterpret_cast<const float4*>(xs + r * K + c * 256 + lane * 8 + 4);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
-        acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
+      for (int e = 0; e < 8; ++e) {
+        acc0[r] = fmaf(wa[e], xv[e], acc0[r]);
+        if (TWO) acc1[r] = fmaf(wb[e], xv[e], acc1[r]);
       }
     }
+  }
 #pragma unroll
-    for (int r = 0; r < BR; ++r) {
-      if (lane == r) {
-        epi(n0, r, acc0[r]);
-        if (two) epi(n1, r, acc1[r]);
+  for (int r = 0; r < BR; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc0[r] += __shfl_xor_sync(0xffffffffu, acc0[r], o);
+      if (TWO) acc1[r] += __shfl_xor_sync(0xffffffffu, acc1[r], o);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < BR; ++r) {
+    if (lane == r && r < B) {
+      float v0 = acc0[r] + w.b0 + r0;
+      if (relu) v0 = fmaxf(v0, 0.f);
+      out[(long long)r * ldo + n0] = v0;
+      if (two) {
+        float v1 = acc1[r] + w.b1 + r1;
+        if (relu) v1 = fmaxf(v1, 0.f);
+        out[(long long)r * ldo + n1] = v1;
       }
     }
   }
@@ -154,16 +177,43 @@ __device__ __forceinline__ void load_rows(float* xs, const float* src, int K, in
   }
 }
 
-// one (utterance, head, key chunk): partial softmax statistics over the chunk's keys -> part[36]
-__device__ __forceinline__ void attention_chunk(const PersistentStep& a, int layer, int b, int h, int c, float* sred) {
+// one (utterance, head, key chunk): partial softmax statistics over the chunk's keys -> part[36].
+// The first pass of cached K / V rows (written by earlier steps) is fetched BEFORE the barrier that publishes
+// this step's q: att_prefetch / att_run.
+struct AttItem { int b, h, c, T, lo, hi; float* K; float* V; float4 k4[2], v4[2]; bool valid; };
+
+__device__ __forceinline__ void att_prefetch(AttItem& it, const PersistentStep& a, int layer) {
+  const int item = blockIdx.x;
+  it.valid = item < a.B * NH * a.nch;
+  if (!it.valid) return;
+  it.c = item % a.nch;
+  const int bh = item / a.nch;
+  it.h = bh % NH; it.b = bh / NH;
+  if (a.active && !a.active[it.b]) { it.valid = false; return; }
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  it.T = a.kv_len[it.b];                                     // cached tokens; the new token is key index T
+  const int total = it.T + 1;
+  const int cs = (total + a.nch - 1) / a.nch;
+  it.lo = it.c * cs; it.hi = min(it.lo + cs, total);
+  it.K = a.kv + (long long)it.b * a.utt_stride + (long long)layer * a.layer_stride + (long long)it.h * a.cap * 32;
+  it.V = it.K + a.v_off;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int j = it.lo + u * 32 + grp;
+    it.k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); it.v4[u] = it.k4[u];
+    if (j < it.hi && j < it.T) {
+      it.k4[u] = __ldg(reinterpret_cast<const float4*>(it.K + (long long)j * 32 + sub * 4));
+      it.v4[u] = __ldg(reinterpret_cast<const float4*>(it.V + (long long)j * 32 + sub * 4));
+    }
+  }
+}
+
+__device__ __forceinline__ void att_run(AttItem& it, const PersistentStep& a, float* sred) {
+  if (!it.valid) return;                                    // CTA-uniform
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = tid >> 3, sub = tid & 7;                  // 32 groups of 8 lanes, one key per group per pass
-  const int T = a.kv_len[b];                                // cached tokens; the new token is key index T
-  const int total = T + 1;
-  const int cs = (total + a.nch - 1) / a.nch;
-  const int lo = c * cs, hi = min(lo + cs, total);
-  float* K = a.kv + (long long)b * a.utt_stride + (long long)layer * a.layer_stride + (long long)h * a.cap * 32;
-  float* V = K + a.v_off;
+  const int b = it.b, h = it.h, c = it.c, T = it.T, lo = it.lo, hi = it.hi;
+  float* K = it.K; float* V = it.V;
   const float* qrow = a.qkv + (long long)b * 3 * D + h * 32 + sub * 4;
   float4 q4 = __ldcg(reinterpret_cast<const float4*>(qrow));
   q4.x *= a.scale; q4.y *= a.scale; q4.z *= a.scale; q4.w *= a.scale;
@@ -180,8 +230,11 @@ __device__ __forceinline__ void attention_chunk(const PersistentStep& a, int lay
       k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); v4[u] = k4[u];
       if (ok[u]) {
         if (j < T) {
-          k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
-          v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+          if (j0 == lo) { k4[u] = it.k4[u]; v4[u] = it.v4[u]; }
+          else {
+            k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
+            v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+          }
         } else {                                            // this step's token: from the QKV rows, and into the cache
           k4[u] = __ldcg(reinterpret_cast<const float4*>(qrow + D));
           v4[u] = __ldcg(reinterpret_cast<const float4*>(qrow + 2 * D));
@@ -243,6 +296,8 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
   const int B = a.B;
   unsigned target = 0;
 
+  WRegs<2, true> wq;                                        // QKV / FFN1 / logits: K = 512, up to two columns
+  gemv_prefetch<2, true>(wq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gwarp, nwarps, lane);
   for (int l = 0; l < a.n_layers; ++l) {
     const StepLayerPtrs L = a.layers[l];
     // ---- P1: layer input rows (embedding for layer 0, LN2 of the previous layer otherwise) -> QKV
@@ -253,17 +308,14 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
       layernorm_rows<BR>(xs, a.lnin2, P.ln2g, P.ln2b, blockIdx.x == 0 ? a.h : nullptr, B, warp, lane);
     }
     __syncthreads();
-    gemv<BR>(L.wqkv, D, 3 * D, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
-      if (r < B) a.qkv[(long long)r * 3 * D + n] = v + __ldg(L.bqkv + n);
-    });
+    gemv_compute<BR, 2, true>(wq, 3 * D, xs, a.qkv, 3 * D, nullptr, false, B, gwarp, nwarps, lane);
+    AttItem it;
+    att_prefetch(it, a, l);                                 // cached K / V rows: in flight across the barrier
     grid_sync(a.sync, target, G);
     // ---- P2: attention partials (+ cache append)
-    for (int item = blockIdx.x; item < B * NH * a.nch; item += G) {
-      const int c = item % a.nch, bh = item / a.nch;
-      const int h = bh % NH, b = bh / NH;
-      if (a.active && !a.active[b]) continue;               // CTA-uniform
-      attention_chunk(a, l, b, h, c, sred);
-    }
+    att_run(it, a, sred);
+    WRegs<2, false> wo;
+    gemv_prefetch<2, false>(wo, L.wout, L.bout, D, gwarp, nwarps, lane);
     grid_sync(a.sync, target, G);
     // ---- P3: combine chunks -> attention rows; out-proj + bias + residual
     for (int i = tid; i < BR * D; i += NTHR) {
@@ -271,37 +323,46 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
       float o = 0.f;
       if (r < B) {
         const float* p = a.part + (long long)(r * NH + (col >> 5)) * a.nch * PART_LD;
+        float mc[8], lc[8], ac[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          mc[c] = -CUDART_INF_F; lc[c] = 0.f; ac[c] = 0.f;
+          if (c < a.nch) {
+            mc[c] = __ldcg(p + c * PART_LD); lc[c] = __ldcg(p + c * PART_LD + 1);
+            ac[c] = __ldcg(p + c * PART_LD + 4 + (col & 31));
+          }
+        }
         float M = -CUDART_INF_F;
-        for (int c = 0; c < a.nch; ++c) M = fmaxf(M, __ldcg(p + c * PART_LD));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) M = fmaxf(M, mc[c]);
         float num = 0.f, den = 0.f;
-        for (int c = 0; c < a.nch; ++c) {
-          const float mc = __ldcg(p + c * PART_LD);
-          const float wgt = (mc == -CUDART_INF_F) ? 0.f : expf(mc - M);
-          num = fmaf(__ldcg(p + c * PART_LD + 4 + (col & 31)), wgt, num);
-          den = fmaf(__ldcg(p + c * PART_LD + 1), wgt, den);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float wgt = (mc[c] == -CUDART_INF_F) ? 0.f : expf(mc[c] - M);
+          num = fmaf(ac[c], wgt, num);
+          den = fmaf(lc[c], wgt, den);
         }
         o = num / den;
       }
       xs[i] = o;
     }
     __syncthreads();
-    gemv<BR>(L.wout, D, D, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
-      if (r < B) a.lnin[(long long)r * D + n] = v + __ldg(L.bout + n) + __ldcg(a.h + (long long)r * D + n);
-    });
+    gemv_compute<BR, 2, false>(wo, D, xs, a.lnin, D, a.h, false, B, gwarp, nwarps, lane);
+    gemv_prefetch<2, true>(wq, L.wff1, L.bff1, FF, gwarp, nwarps, lane);
     grid_sync(a.sync, target, G);
     // ---- P4: LN1 -> FFN1 (+ ReLU)
     layernorm_rows<BR>(xs, a.lnin, L.ln1g, L.ln1b, blockIdx.x == 0 ? a.h1 : nullptr, B, warp, lane);
     __syncthreads();
-    gemv<BR>(L.wff1, D, FF, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
-      if (r < B) a.ff[(long long)r * FF + n] = fmaxf(v + __ldg(L.bff1 + n), 0.f);
-    });
+    gemv_compute<BR, 2, true>(wq, FF, xs, a.ff, FF, nullptr, true, B, gwarp, nwarps, lane);
+    WRegs<8, false> w2;
+    gemv_prefetch<8, false>(w2, L.wff2, L.bff2, D, gwarp, nwarps, lane);
     grid_sync(a.sync, target, G);
     // ---- P5: FFN2 + bias + residual
     load_rows<BR>(xs, a.ff, FF, B);
     __syncthreads();
-    gemv<BR>(L.wff2, FF, D, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
-      if (r < B) a.lnin2[(long long)r * D + n] = v + __ldg(L.bff2 + n) + __ldcg(a.h1 + (long long)r * D + n);
-    });
+    gemv_compute<BR, 8, false>(w2, D, xs, a.lnin2, D, a.h1, false, B, gwarp, nwarps, lane);
+    if (l + 1 < a.n_layers) gemv_prefetch<2, true>(wq, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, gwarp, nwarps, lane);
+    else gemv_prefetch<2, true>(wq, a.wpredict, a.bpredict, a.vocab, gwarp, nwarps, lane);
     grid_sync(a.sync, target, G);
   }
   // ---- logits from LN2 of the last layer
@@ -309,9 +370,7 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
     const StepLayerPtrs P = a.layers[a.n_layers - 1];
     layernorm_rows<BR>(xs, a.lnin2, P.ln2g, P.ln2b, nullptr, B, warp, lane);
     __syncthreads();
-    gemv<BR>(a.wpredict, D, a.vocab, xs, gwarp, nwarps, lane, [&](int n, int r, float v) {
-      if (r < B) a.logits[(long long)r * a.ld_logits + n] = v + (a.bpredict ? __ldg(a.bpredict + n) : 0.f);
-    });
+    gemv_compute<BR, 2, true>(wq, a.vocab, xs, a.logits, a.ld_logits, nullptr, false, B, gwarp, nwarps, lane);
   }
 }
 
@@ -336,6 +395,8 @@ int persistent_step_chunks(int B, int grid) {
 
 void launch_t2s_step_persistent(const PersistentStep& a, int grid, cudaStream_t s) {
   GENIE_CHECK(a.B >= 1 && a.B <= 8, "persistent step: batch must be 1..8");
+  GENIE_CHECK(grid * NWARP >= a.vocab && 2 * grid * NWARP >= FF && grid >= a.B * NH * a.nch,
+              "persistent step: grid too small for one column pair / one attention item per warp / CTA");
   GENIE_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(unsigned), s));
   if (a.B == 1) launch_br<1>(a, grid, s);
   else if (a.B == 2) launch_br<2>(a, grid, s);
