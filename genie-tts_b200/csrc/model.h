@@ -123,7 +123,8 @@ struct Model {
   int use_tc = 1, tc_vits = 1, tc_min_rows = 9, skinny_max_rows = 8;
   int* tc_err = nullptr;
   // persistent decode step (batch <= skinny_max_rows): per-layer pointer table, barrier words, grid size
-  void* step_layers_dev = nullptr; unsigned* step_sync = nullptr; int num_sms = 0; int persistent_step = 1;
+  void* step_layers_dev = nullptr; unsigned* step_sync = nullptr; int num_sms = 0;
+  int persistent_step = 4;             // largest batch that takes the persistent step (0 = off, <= 8)
   // debug
   bool record_logits = false, keep = false;
   std::vector<float> logits_host;

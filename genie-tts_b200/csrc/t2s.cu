@@ -68,7 +68,8 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   const PdlScope pdl_scope(B > m.skinny_max_rows ? 1 : 0);
   launch_decode_embed(w.h, w.hist, w.hist_ld, w.hist_len, w.active, m.audio_emb, m.audio_alpha, m.div_term, B, s);
   const float scale = 1.0f / std::sqrt(32.0f);
-  const bool persistent = m.persistent_step && B <= 8 && B <= m.skinny_max_rows && m.layers[0].qkv.w_f16 &&
+  // measured (90 steps): batch 1 / 2 / 4 / 8 = 37 / 43 / 53 / 77 ms persistent vs 58 / - / 60 / 70 ms kernel chain
+  const bool persistent = m.persistent_step && B <= m.persistent_step && B <= m.skinny_max_rows && m.layers[0].qkv.w_f16 &&
                           m.predict.w_f16 && w.ppart != nullptr && m.step_layers_dev != nullptr;
   if (persistent) {
     // batch <= 8: all 24 layers + logits in one resident kernel (t2s_persistent.cu)
@@ -347,7 +348,7 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   w.stop_step = d_stop; w.kv = KV; w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off;
   w.cap = bt.cap; w.hist_ld = bt.hist_ld;
 
-  if (m.persistent_step && B <= 8) ensure_persistent_step(m);
+  if (m.persistent_step && B <= m.persistent_step) ensure_persistent_step(m);
   // the graph bakes pointers and scalar args; re-capture when any of them changes
   const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (m.use_tc ? 4 : 0) | (cfg.top_k << 4) |
                     (m.tc_min_rows << 16);

@@ -180,7 +180,11 @@ __device__ __forceinline__ void load_rows(float* xs, const float* src, int K, in
 // one (utterance, head, key chunk): partial softmax statistics over the chunk's keys -> part[36].
 // The first pass of cached K / V rows (written by earlier steps) is fetched BEFORE the barrier that publishes
 // this step's q: att_prefetch / att_run.
-struct AttItem { int b, h, c, T, lo, hi; float* K; float* V; float4 k4[2], v4[2]; bool valid; };
+struct AttItem {
+  int b, h, c, T, lo, hi; float* K; float* V; float4 k4[2], v4[2]; bool valid, has_new;
+  uint4 wq[4][2], wk[4][2], wv[4][2];      // this warp's 4 q (k, v) columns of head h: rows of Wqkv, 2 x 256 k
+  float bq[4], bk[4], bv[4];
+};
 
 __device__ __forceinline__ void att_prefetch(AttItem& it, const PersistentStep& a, int layer) {
   const int item = blockIdx.x;
@@ -197,6 +201,27 @@ __device__ __forceinline__ void att_prefetch(AttItem& it, const PersistentStep& 
   it.lo = it.c * cs; it.hi = min(it.lo + cs, total);
   it.K = a.kv + (long long)it.b * a.utt_stride + (long long)layer * a.layer_stride + (long long)it.h * a.cap * 32;
   it.V = it.K + a.v_off;
+  it.has_new = it.lo <= it.T && it.T < it.hi;                // this chunk holds the step's own token
+  {
+    // q (and, for the chunk with the new token, k / v) columns of this head: warp w owns columns 4w..4w+3
+    const StepLayerPtrs L = a.layers[layer];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col0 = it.h * 32 + warp * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        it.wq[j][c] = __ldg(reinterpret_cast<const uint4*>(L.wqkv + (long long)(col0 + j) * D + c * 256 + lane * 8));
+        if (it.has_new) {
+          it.wk[j][c] = __ldg(reinterpret_cast<const uint4*>(L.wqkv + (long long)(D + col0 + j) * D + c * 256 + lane * 8));
+          it.wv[j][c] = __ldg(reinterpret_cast<const uint4*>(L.wqkv + (long long)(2 * D + col0 + j) * D + c * 256 + lane * 8));
+        }
+      }
+      it.bq[j] = __ldg(L.bqkv + col0 + j);
+      it.bk[j] = __ldg(L.bqkv + D + col0 + j);
+      it.bv[j] = __ldg(L.bqkv + 2 * D + col0 + j);
+    }
+  }
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int j = it.lo + u * 32 + grp;
@@ -208,15 +233,49 @@ __device__ __forceinline__ void att_prefetch(AttItem& it, const PersistentStep& 
   }
 }
 
-__device__ __forceinline__ void att_run(AttItem& it, const PersistentStep& a, float* sred) {
+// dot of 4 weight rows (2 x 256-k chunks per lane) with the activation row x[512] in shared memory
+__device__ __forceinline__ void dot4(const uint4 (&w)[4][2], const float (&bias)[4], const float* x, int lane, float* out4) {
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const float4 xa = *reinterpret_cast<const float4*>(x + c * 256 + lane * 8);
+    const float4 xb = *reinterpret_cast<const float4*>(x + c * 256 + lane * 8 + 4);
+    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2* hp = reinterpret_cast<const __half2*>(&w[j][c]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(hp[e]);
+        acc[j] = fmaf(f.x, xv[2 * e], acc[j]);
+        acc[j] = fmaf(f.y, xv[2 * e + 1], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    if (lane == j) out4[j] = acc[j] + bias[j];
+  }
+}
+
+// x: this utterance's layer-input row in shared memory; sqkv: [96] scratch for q | k_new | v_new of the head
+__device__ __forceinline__ void att_run(AttItem& it, const PersistentStep& a, const float* x, float* sqkv, float* sred) {
   if (!it.valid) return;                                    // CTA-uniform
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = tid >> 3, sub = tid & 7;                  // 32 groups of 8 lanes, one key per group per pass
   const int b = it.b, h = it.h, c = it.c, T = it.T, lo = it.lo, hi = it.hi;
   float* K = it.K; float* V = it.V;
-  const float* qrow = a.qkv + (long long)b * 3 * D + h * 32 + sub * 4;
-  float4 q4 = __ldcg(reinterpret_cast<const float4*>(qrow));
+  dot4(it.wq, it.bq, x, lane, sqkv + warp * 4);
+  if (it.has_new) {
+    dot4(it.wk, it.bk, x, lane, sqkv + 32 + warp * 4);
+    dot4(it.wv, it.bv, x, lane, sqkv + 64 + warp * 4);
+  }
+  __syncthreads();
+  float4 q4 = *reinterpret_cast<const float4*>(sqkv + sub * 4);
   q4.x *= a.scale; q4.y *= a.scale; q4.z *= a.scale; q4.w *= a.scale;
+  (void)b;
 
   float m = -CUDART_INF_F, l = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -236,8 +295,8 @@ __device__ __forceinline__ void att_run(AttItem& it, const PersistentStep& a, fl
             v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
           }
         } else {                                            // this step's token: from the QKV rows, and into the cache
-          k4[u] = __ldcg(reinterpret_cast<const float4*>(qrow + D));
-          v4[u] = __ldcg(reinterpret_cast<const float4*>(qrow + 2 * D));
+          k4[u] = *reinterpret_cast<const float4*>(sqkv + 32 + sub * 4);
+          v4[u] = *reinterpret_cast<const float4*>(sqkv + 64 + sub * 4);
           if (T < a.cap) {
             *reinterpret_cast<float4*>(K + (long long)T * 32 + sub * 4) = k4[u];
             *reinterpret_cast<float4*>(V + (long long)T * 32 + sub * 4) = v4[u];
@@ -296,24 +355,26 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
   const int B = a.B;
   unsigned target = 0;
 
-  WRegs<2, true> wq;                                        // QKV / FFN1 / logits: K = 512, up to two columns
-  gemv_prefetch<2, true>(wq, a.layers[0].wqkv, a.layers[0].bqkv, 3 * D, gwarp, nwarps, lane);
+  __shared__ __align__(16) float sqkv[96];
+  WRegs<2, true> wq;                                        // FFN1 / logits: K = 512, up to two columns
+  AttItem it;
+  att_prefetch(it, a, 0);
   for (int l = 0; l < a.n_layers; ++l) {
     const StepLayerPtrs L = a.layers[l];
-    // ---- P1: layer input rows (embedding for layer 0, LN2 of the previous layer otherwise) -> QKV
-    if (l == 0) {
-      load_rows<BR>(xs, a.h, D, B);
-    } else {
-      const StepLayerPtrs P = a.layers[l - 1];
-      layernorm_rows<BR>(xs, a.lnin2, P.ln2g, P.ln2b, blockIdx.x == 0 ? a.h : nullptr, B, warp, lane);
+    // ---- PA: layer-input row of this CTA's utterance (embedding for layer 0, LN2 of the previous layer
+    // otherwise) -> its own q (k_new, v_new) columns -> attention partials over its key chunk (+ cache append).
+    // CTAs (h = 0, c = 0) publish the row: it is the residual of the out-projection.
+    if (it.valid) {
+      float* pub = (it.h == 0 && it.c == 0) ? a.h + (long long)it.b * D : nullptr;
+      if (l == 0) {
+        for (int i = tid; i < D; i += NTHR) xs[i] = __ldcg(a.h + (long long)it.b * D + i);
+      } else if (warp == 0) {
+        const StepLayerPtrs P = a.layers[l - 1];
+        layernorm_rows<1>(xs, a.lnin2 + (long long)it.b * D, P.ln2g, P.ln2b, pub, 1, 0, lane);
+      }
     }
     __syncthreads();
-    gemv_compute<BR, 2, true>(wq, 3 * D, xs, a.qkv, 3 * D, nullptr, false, B, gwarp, nwarps, lane);
-    AttItem it;
-    att_prefetch(it, a, l);                                 // cached K / V rows: in flight across the barrier
-    grid_sync(a.sync, target, G);
-    // ---- P2: attention partials (+ cache append)
-    att_run(it, a, sred);
+    att_run(it, a, xs, sqkv, sred);
     WRegs<2, false> wo;
     gemv_prefetch<2, false>(wo, L.wout, L.bout, D, gwarp, nwarps, lane);
     grid_sync(a.sync, target, G);
@@ -361,7 +422,7 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
     load_rows<BR>(xs, a.ff, FF, B);
     __syncthreads();
     gemv_compute<BR, 8, false>(w2, D, xs, a.lnin2, D, a.h1, false, B, gwarp, nwarps, lane);
-    if (l + 1 < a.n_layers) gemv_prefetch<2, true>(wq, a.layers[l + 1].wqkv, a.layers[l + 1].bqkv, 3 * D, gwarp, nwarps, lane);
+    if (l + 1 < a.n_layers) att_prefetch(it, a, l + 1);
     else gemv_prefetch<2, true>(wq, a.wpredict, a.bpredict, a.vocab, gwarp, nwarps, lane);
     grid_sync(a.sync, target, G);
   }
