@@ -291,6 +291,7 @@ def main():
         genie.tts_batch(model, [prompt], [seqs[i % B]], None, sampling=sp)
         lat.append(1000 * (time.perf_counter() - tl0))
     first_audio_ms = float(np.median(lat[2:]))
+    t_b1 = model.last_timing()          # stage events of the last batch-1 call
 
     tt = torch.tensor([dt, dt_e], dtype=torch.float64, device=dev)
     aa = torch.tensor([audio_s, e_audio], dtype=torch.float64, device=dev)
@@ -325,6 +326,9 @@ def main():
         # (4) prefill (tensor): 150.99 MFLOP per position + 24*4*S^2*512 attention
         S = np.asarray([60 + len(q) + 132 for q in seqs], dtype=np.float64)
         pre_tf = float((S * 150.99e6 + 24 * 4 * S * S * 512).sum()) / (sm["prefill"] * 1e-3) / 1e12
+        b1_ms_tok = t_b1["decode_ms"] / max(1, t_b1["steps"])
+        b1_T = 60 + len(seqs[11 % B]) + 132 + TOKENS / 2
+        b1_gbs = (152.364e6 + 98304.0 * b1_T) / (b1_ms_tok * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
@@ -360,6 +364,11 @@ def main():
                  "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "share_of_step": sm["decode"] / step_ms},
                 {"stage": "t2s prefill (tc_conv_gemm split-fp16 + attention)", "bound": "tensor", "achieved": pre_tf,
                  "peak": tf_peak, "unit": "TFLOP/s", "frac": pre_tf / tf_peak, "share_of_step": sm["prefill"] / step_ms},
+                # batch 1 (first-audio path): one persistent kernel per token; bytes = fp16 weights + fp32 KV read
+                {"stage": "t2s decode batch 1 (t2s_step_persistent_kernel)", "bound": "hbm",
+                 "achieved": b1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": b1_gbs / hbm_peak,
+                 "ms_per_token": b1_ms_tok, "stage_ms": {"prefill": t_b1["prefill_ms"], "decode": t_b1["decode_ms"],
+                                                         "vits": t_b1["vits_ms"]}},
             ],
         }
         if not args.no_cpu_baseline:

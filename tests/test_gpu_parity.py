@@ -163,6 +163,49 @@ def test_v2pp_english_paragraph_shape(v2pp):
     prompt.close()
 
 
+@pytest.mark.gpu
+def test_persistent_step_matches_kernel_chain_and_oracle(v2):
+    """Batch <= 4 decodes with ONE resident kernel per token (t2s_persistent.cu, device-wide barriers); the same
+    batches through the per-layer kernel chain (option persistent_step=0) and the oracle must give the same
+    tokens, and logits within the batch-regime tolerance."""
+    from genie_tts.engine import SamplingParams
+    from oracle import gsv_port as P
+    m, pm = v2
+    steps = 12
+    sp = SamplingParams(greedy=True, max_steps=steps)
+    prs = [make_prompt_inputs(seed=400 + i, Lr=10 + 7 * i, Ts=48 + 16 * i, n_audio=32000, bert=(i == 1)) for i in range(2)]
+    prompts = [_prompt(m, p) for p in prs]
+    try:
+        for B in (1, 3, 4):
+            txs = [make_text_inputs(seed=500 + 10 * B + i, Lt=8 + 5 * i, bert=(i % 2 == 1)) for i in range(B)]
+            pid = [i % 2 for i in range(B)]
+            args = ([prompts[p] for p in pid], [t["text_seq"] for t in txs], [t["text_bert"] for t in txs], sp)
+            out = {}
+            for mode in (4, 0):
+                m.set_option("persistent_step", mode)
+                m.record_logits(True)
+                ys, idx = m.t2s_generate(*args)
+                lg = m.read_logits().reshape(-1, B, 1025)
+                m.record_logits(False)
+                ys_g, idx_g = m.t2s_generate(*args)                    # CUDA-graph replay of the same step
+                assert all(np.array_equal(a, b_) for a, b_ in zip(ys, ys_g)) and idx == idx_g
+                out[mode] = (ys, idx, lg)
+            m.set_option("persistent_step", 4)
+            assert all(np.array_equal(a, b_) for a, b_ in zip(out[4][0], out[0][0])) and out[4][1] == out[0][1]
+            n = min(len(out[4][2]), len(out[0][2]))
+            assert np.abs(out[4][2][:n] - out[0][2][:n]).max() < 3e-4
+            for b in range(B):
+                r = P.t2s_generate(pm, prs[pid[b]]["ref_seq"], prs[pid[b]]["ref_bert"], txs[b]["text_seq"],
+                                   txs[b]["text_bert"], prs[pid[b]]["ssl_content"], max_steps=steps)
+                assert np.array_equal(out[4][0][b], r.y_full[0]) and out[4][1][b] == r.idx
+    finally:
+        m.set_option("persistent_step", 4)
+        m.record_logits(False)
+        for p in prompts:
+            p.close()
+
+
+
 def test_tc_selftest_shapes():
     """tcgen05 implicit-GEMM (incl. halo-staged multi-tap path) vs the exact SIMT kernel on random data."""
     import ctypes as C
