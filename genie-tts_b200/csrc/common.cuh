@@ -102,6 +102,7 @@ struct ConvGemm {
   // zero padded to a multiple of 64; optional low part (w - fp16(w)); tc_split_a: x = x_hi + x_lo
   const __half* tc_w = nullptr; const __half* tc_wlo = nullptr; int tc_kpad = 0; int tc_split_a = 0;
   int tc_nt = 0;                               // force the N tile (0 = by Cout)
+  const __half* tc_tiles = nullptr;            // pre-tiled weights for tc_halo_bulk_kernel (wide k-tap convs)
   // split-K: CTA (n-tile, ks) reduces k-blocks [ks*KB/ksplit, (ks+1)*KB/ksplit) and stores the raw partial
   // at y + ks*split_stride; bias / residual / activation are then applied by the consumer (layernorm)
   int ksplit = 1; long long split_stride = 0;
@@ -110,6 +111,8 @@ void launch_conv_gemm(const ConvGemm& p, cudaStream_t s);
 void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s);
 // k-tap convs with the activation halo staged once per CTA (tc_halo_conv.cu); false => not applicable
 bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s);
+bool pretile_w128_supported(int Cin, int Cout, int ntaps);
+void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s);
 bool skinny_gemm_supported(const ConvGemm& p);
 void launch_skinny_gemm(const ConvGemm& p, cudaStream_t s);
 

@@ -33,7 +33,7 @@ struct RawTensor {
 };
 
 // tcgen05 operand: fp16 [Cout][kpad] (K = tap*Cin + ci, zero padded to x64) + optional low part
-struct TcW { const __half* hi = nullptr; const __half* lo = nullptr; int kpad = 0; };
+struct TcW { const __half* hi = nullptr; const __half* lo = nullptr; int kpad = 0; const __half* tiles = nullptr; };
 struct Linear {            // y = x W^T + b ; W [N,K] row-major
   const void* w = nullptr; int w_f16 = 0; const float* b = nullptr; int N = 0, K = 0; TcW tc;
 };

@@ -57,6 +57,12 @@ void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exa
   p.M = std::max(M1, rows - M1); p.M_out = p.M;
   p.y = y0;
   launch_conv_gemm(p, s);
+  __half* tiles = nullptr;
+  if (pretile_w128_supported(Cin, Cout, ntaps) && kpad == K) {
+    GENIE_CUDA(cudaMalloc(&tiles, (size_t)Cout * kpad * 2));
+    launch_pretile_w128(hi, Cout, kpad, Cin, ntaps, tiles, s);
+    p.tc_tiles = tiles;
+  }
   p.y = y1; p.tc_w = hi; p.tc_wlo = mode >= 3 ? lo : nullptr; p.tc_kpad = kpad; p.tc_split_a = mode >= 2;
   launch_tc_conv_gemm(p, err, s);
   GENIE_CUDA(cudaDeviceSynchronize());
@@ -89,7 +95,7 @@ void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exa
     rm = std::max(rm, std::fabs(a[i]));
   }
   cudaFree(x); cudaFree(w); cudaFree(b); cudaFree(r); cudaFree(y0); cudaFree(y1); cudaFree(off); cudaFree(err);
-  cudaFree(hi); cudaFree(lo);
+  cudaFree(hi); cudaFree(lo); if (tiles) cudaFree(tiles);
   GENIE_CHECK(herr == 0, "tcgen05 pipeline timed out in selftest");
   *max_err = me; *ref_max = rm;
 }

@@ -269,6 +269,228 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Wide layers (Cin >= 128): warp-specialised variant.  The weights are pre-tiled at load time
+// ([n-tile][tap][slab] -> one contiguous, already swizzled 128 x 64 fp16 tile of 16 KB), so a single
+// thread streams them with cp.async.bulk into a 4-slot ring (mbarrier expect_tx / complete_tx) and issues
+// the MMAs; slot reuse is gated by tcgen05.commit.  The 8 loader warps stage the halo tile, signal it
+// through an mbarrier and go straight to waiting for the accumulator: there is no CTA-wide barrier in
+// the k-loop, and with two CTAs per SM one CTA's epilogue overlaps the other's MMAs.
+// ---------------------------------------------------------------------------
+constexpr int BNT = 128;                            // output columns per CTA
+constexpr int BTHR = NTHR + 32;                     // 8 loader / epilogue warps + 1 producer / MMA warp
+constexpr uint32_t BTILE = BNT * 128;               // 16 KB weight tile
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void pretile_w128_kernel(const __half* __restrict__ hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles) {
+  const int slabs = Cin / 64;
+  const long long total = (long long)(Cout / BNT) * ntaps * slabs * BNT * 8;     // 16-byte chunks
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i & 7), n = (int)((i >> 3) % BNT);
+  const long long unit = i / (BNT * 8);
+  const int sl = (int)(unit % slabs), tap = (int)((unit / slabs) % ntaps), nt = (int)(unit / ((long long)slabs * ntaps));
+  const uint4 v = *reinterpret_cast<const uint4*>(hi + (long long)(nt * BNT + n) * kpad + tap * Cin + sl * 64 + c8 * 8);
+  const uint32_t off = (uint32_t)(n * 128 + c8 * 16);
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tiles) + unit * BTILE + (off ^ (((off >> 7) & 7u) << 4))) = v;
+}
+
+__global__ void __launch_bounds__(BTHR, 2) tc_halo_bulk_kernel(ConvGemm p, HaloGeom g, int* err_flag) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT], a_ready, acc_ready;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_to[128];
+  __shared__ __align__(16) float s_bias[BNT];
+
+  const int seg = blockIdx.z;
+  int in0 = 0, Tin = p.M, out0 = 0, Tout = p.M_out;
+  if (p.in_off) { in0 = p.in_off[seg]; Tin = p.in_off[seg + 1] - in0; }
+  if (p.out_off) { out0 = p.out_off[seg]; Tout = p.out_off[seg + 1] - out0; }
+  const int nq = Tin + p.q_extra;
+  const int q0 = blockIdx.x * 128;
+  if (q0 >= nq) return;
+  const int n0 = (int)blockIdx.y * BNT;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base;
+  const uint32_t sW = base + (uint32_t)g.slabs * g.slab_bytes;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)BNT));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&a_ready, NTHR);
+    mbar_init(&acc_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 128) {
+    const int q = q0 + tid;
+    const int to = q * p.out_mul + p.out_add;
+    s_to[tid] = (q < nq && to >= 0 && to < Tout) ? to : -1;
+    float bsum = 0.f;
+    const int n = n0 + tid;
+    if (n < p.Cout) {
+      if (p.bias) bsum += p.bias[n];
+      if (p.bias2) bsum += p.bias2[(long long)seg * p.ldb2 + n];
+    }
+    s_bias[tid] = bsum;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+
+  if (warp == NTHR / 32) {
+    // ===== producer + MMA issuer: one thread
+    if (lane == 0) {
+      const uint8_t* tiles = reinterpret_cast<const uint8_t*>(p.tc_tiles) + (size_t)blockIdx.y * g.NU * BTILE;
+      const int npre = g.NU < NSLOT ? g.NU : NSLOT;
+      for (int u = 0; u < npre; ++u) {
+        mbar_expect_tx(&full[u], BTILE);
+        bulk_g2s(sW + (uint32_t)u * BTILE, tiles + (size_t)u * BTILE, BTILE, &full[u]);
+      }
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+      ok = mbar_wait(&a_ready, 0u) && ok;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int u = 0; u < g.NU; ++u) {
+        const int slot = u % NSLOT;
+        ok = mbar_wait(&full[slot], (uint32_t)((u / NSLOT) & 1)) && ok;
+        const int tap = u / g.slabs, sl = u - tap * g.slabs;
+        const int shift = p.in_shift0 + tap * p.in_shift_step - g.lo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t aaddr = sA + (uint32_t)sl * g.slab_bytes + (uint32_t)shift * 128u + j * 32;
+          const uint32_t waddr = sW + (uint32_t)slot * BTILE + j * 32;
+          umma_f16(tmem, desc_hi | (uint64_t)((aaddr & 0x3FFFFu) >> 4), desc_hi | (uint64_t)((waddr & 0x3FFFFu) >> 4),
+                   idesc, (uint32_t)((u | j) != 0));
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     ::"r"(smem_u32(&empty[slot])) : "memory");
+        // refill the slot of the PREVIOUS unit (its MMAs finish while this unit's run)
+        if (u >= 1) {
+          const int v = u - 1 + NSLOT, ps = (u - 1) % NSLOT;
+          if (v < g.NU) {
+            ok = mbar_wait(&empty[ps], (uint32_t)(((u - 1) / NSLOT) & 1)) && ok;
+            mbar_expect_tx(&full[ps], BTILE);
+            bulk_g2s(sW + (uint32_t)ps * BTILE, tiles + (size_t)v * BTILE, BTILE, &full[ps]);
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                   ::"r"(smem_u32(&acc_ready)) : "memory");
+      if (!ok && err_flag) atomicExch(err_flag, 1);
+    }
+  } else {
+    // ===== loader / epilogue warps: halo tile once, then wait for the accumulator
+    {
+      const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
+      const float pre = p.pre_slope;
+      const int cq = p.Cin >> 2;
+      const int totalA = g.R * cq;
+      const int tbase = q0 + g.lo;
+      for (int i0 = 0; i0 < totalA; i0 += NTHR * 8) {
+        float4 v[8];
+        uint32_t so[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = i0 + k * NTHR + tid;
+          const int rr = idx / cq, f = idx - rr * cq;
+          const int t = tbase + rr;
+          const int c = f * 4;
+          const uint32_t off = (uint32_t)(rr * 128 + (c & 63) * 2);
+          so[k] = idx < totalA ? (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4)) : 0xffffffffu;
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < totalA && (unsigned)t < (unsigned)Tin)
+            v[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + c));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (so[k] == 0xffffffffu) continue;
+          float4 a = v[k];
+          a.x = fmaxf(a.x, a.x * pre); a.y = fmaxf(a.y, a.y * pre);
+          a.z = fmaxf(a.z, a.z * pre); a.w = fmaxf(a.w, a.w * pre);
+          const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(sbase + so[k]) = pk;
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+    mbar_arrive(&a_ready);
+    ok = mbar_wait(&acc_ready, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok && err_flag) atomicExch(err_flag, 1);
+    // all 8 warps are past acc_ready only after every MMA has completed: the halo tile can be reused; the
+    // per-warp epilogue tiles are disjoint, so no further CTA-wide barrier is needed here
+    tc_epi::Args ea;
+    ea.y = p.y; ea.res = p.res; ea.acc = p.accumulate ? p.y : nullptr;
+    ea.ldy = p.ldy; ea.ldr = p.ldr;
+    ea.act = p.act; ea.slope = p.act == ACT_RELU ? 0.f : p.act_slope; ea.oscale = p.out_scale;
+    ea.Cout = p.Cout;
+    ea.vec = tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout);
+    float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
+    const int rq = (warp & 3) * 32;
+    if (ok) {
+      for (int c0 = (warp >> 2) * 32; c0 < BNT; c0 += 64) {
+        uint32_t v[32];
+        tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)c0, true, v);
+        tc_epi::store_chunk<32>(v, tile, s_bias + c0, s_to + rq, out0, n0 + c0, ea, lane);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)BNT));
+  }
+}
+
+bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
+  HaloGeom g;
+  const int s_first = p.in_shift0, s_last = p.in_shift0 + (p.ntaps - 1) * p.in_shift_step;
+  g.lo = s_first < s_last ? s_first : s_last;
+  const int hi = s_first < s_last ? s_last : s_first;
+  g.R = 128 + (hi - g.lo);
+  g.slabs = p.Cin / 64;
+  g.slab_bytes = (uint32_t)(((size_t)g.R * 128 + 1023) / 1024 * 1024);
+  g.NU = p.ntaps * g.slabs;
+  g.U = 1; g.NI = g.NU; g.slot_bytes = BTILE; g.flags = flags;
+  size_t smem = (size_t)g.slabs * g.slab_bytes + (size_t)NSLOT * BTILE;
+  if (smem < EPI_BYTES) smem = EPI_BYTES;
+  smem += 1024;
+  if (smem > 200 * 1024) return false;
+  static size_t configured = 0;
+  if (smem > configured) {
+    GENIE_CUDA(cudaFuncSetAttribute(tc_halo_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int nq = p.M + p.q_extra;
+  dim3 grid((nq + 127) / 128, p.Cout / BNT, p.B);
+  tc_halo_bulk_kernel<<<grid, BTHR, smem, s>>>(p, g, err_flag);
+  GENIE_LAUNCHED("tc_halo_bulk");
+  return true;
+}
+
 template <int NT, int MT, int ROWB>
 bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   HaloGeom g;
@@ -303,6 +525,8 @@ bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   return true;
 }
 
+int g_halo_bulk_max_cin = []() { const char* e = getenv("GENIE_HALO_BULK_MAX_CIN"); return e ? atoi(e) : 128; }();
+
 // GENIE_TC_HALO: -1 disables the path, > 0 = debug flags (HaloGeom::flags); default 0 = on
 int halo_mode() {
   static int mode = [] {
@@ -313,6 +537,14 @@ int halo_mode() {
 }
 
 }  // namespace
+
+// fp16 [Cout][kpad] -> pre-swizzled 128 x 64 tiles [Cout/128][tap][Cin/64] for tc_halo_bulk_kernel
+bool pretile_w128_supported(int Cin, int Cout, int ntaps) { return Cin % 64 == 0 && Cin >= 128 && Cout % BNT == 0 && ntaps >= 2; }
+void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s) {
+  const long long total = (long long)(Cout / BNT) * ntaps * (Cin / 64) * BNT * 8;
+  pretile_w128_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(hi, Cout, kpad, Cin, ntaps, tiles);
+  GENIE_LAUNCHED("pretile_w128");
+}
 
 // k-tap convs whose activation halo fits in shared memory; false => caller uses tc_conv_gemm
 bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
@@ -327,6 +559,8 @@ bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   if (p.Cin == 32 && p.Cout <= 32) return launch_halo<32, 4, 64>(p, mode, err_flag, s);
   // wider layers: the per-tap gather of tc_gemm.cu at two CTAs per SM is faster than one halo CTA per SM
   // (measured: C=256 k=11 586 vs 1269 us, C=128 k=7 1067 vs 1194 us) unless forced for testing
+  if (p.Cin % 64 == 0 && p.Cin >= 128 && p.Cin <= g_halo_bulk_max_cin && p.tc_tiles != nullptr && p.Cout % BNT == 0 && !(mode & 1))
+    return launch_halo_bulk(p, mode, err_flag, s);
   if (p.Cin % 64 != 0 || (p.Cin > 64 && !(mode & 1))) return false;
   if (p.Cout <= 64) return launch_halo<64, 2, 128>(p, mode, err_flag, s);
   return launch_halo<128, 1, 128>(p, mode, err_flag, s);

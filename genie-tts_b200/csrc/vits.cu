@@ -34,6 +34,7 @@ void run_conv(Model& m, const Conv& c, const float* x, int ldx, float* y, int ld
   if (!sg.off) { p.B = 1; p.M = sg.rows; p.M_out = sg.rows; }
   if (m.use_tc && c.tc.hi && sg.off != nullptr && o.cin0 == 0 && cin == c.Cin) {
     p.tc_w = c.tc.hi + (long long)o.co0 * c.tc.kpad; p.tc_kpad = c.tc.kpad;
+    if (o.co0 == 0 && p.Cout == c.Cout) p.tc_tiles = c.tc.tiles;
     p.tc_wlo = m.tc_vits >= 3 ? c.tc.lo + (long long)o.co0 * c.tc.kpad : nullptr;
     p.tc_split_a = m.tc_vits >= 2;
     launch_tc_conv_gemm(p, m.tc_err, m.stream);

@@ -181,6 +181,12 @@ struct Finalizer {
     pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, co_stride, tap_stride, ntaps, Cin, Cout, t.kpad, hi, lo);
     GENIE_LAUNCHED("pack_tc");
     t.hi = hi; t.lo = lo;
+    if (tap_stride == Cin && co_stride == (long long)ntaps * Cin && pretile_w128_supported(Cin, Cout, ntaps)) {
+      __half* tiles = dev_alloc<__half>(m.owned, n);
+      m.weight_bytes += n * 2;
+      launch_pretile_w128(hi, Cout, t.kpad, Cin, ntaps, tiles, s);
+      t.tiles = tiles;
+    }
     return t;
   }
   void pack_conv(Conv& c) { c.tc = pack(c.w, (long long)c.k * c.Cin, c.Cin, c.k, c.Cin, c.Cout); }
