@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "tc_epilogue.cuh"
 
+#include <cstdlib>
+
 namespace genie {
 namespace {
 
@@ -303,6 +305,10 @@ template <int SPLIT_A, int W_LO>
 void dispatch_nt(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   // smallest tile that covers Cout in one CTA column; wide layers take the widest tile whose stage ring
   // still leaves room for two CTAs per SM (256 for single-pass fp16, 128 for the hi/lo split forms)
+  // hi/lo-split activations: every N tile re-converts the same A rows, so the wide tile wins although only one
+  // CTA fits per SM (measured at 24 200 rows: K=2048 N=512 293 -> 226 us, K=512 N=1536 221 -> 214 us)
+  static const int nt_env = [] { const char* e = getenv("GENIE_TC_NT_SPLIT"); return e ? atoi(e) : 256; }();
+  if (SPLIT_A == 2 && !W_LO && nt_env == 256 && p.tc_nt == 0 && p.Cout > 128) { launch_tc<256, SPLIT_A, W_LO>(p, err_flag, s); return; }
   constexpr bool wide_ok = tc_min_blocks<256, SPLIT_A, W_LO>() == 2;
   constexpr bool mid_ok = tc_min_blocks<128, SPLIT_A, W_LO>() == 2;
   if (p.tc_nt == 32 || (p.tc_nt == 0 && p.Cout <= 32)) launch_tc<32, SPLIT_A, W_LO>(p, err_flag, s);
