@@ -72,7 +72,6 @@ __device__ __forceinline__ uint32_t swz(int r, int c8) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
 }
 
-constexpr int NTHR = 256;                           // 8 warps: loaders for the k-loop, 2 x 4 TMEM-quarter epilogue warps
 
 template <int NT, int SPLIT_A, int W_LO>
 constexpr size_t tc_smem_bytes() { return 2 * ((size_t)BM * 128 * SPLIT_A + (size_t)NT * 128 * (1 + W_LO)) + 1024; }
@@ -80,8 +79,15 @@ constexpr size_t tc_smem_bytes() { return 2 * ((size_t)BM * 128 * SPLIT_A + (siz
 template <int NT, int SPLIT_A, int W_LO>
 constexpr int tc_min_blocks() { return tc_smem_bytes<NT, SPLIT_A, W_LO>() <= 113 * 1024 ? 2 : 1; }
 
+// 8 warps per CTA where two CTAs share an SM, 16 where the stage ring only leaves room for one: the loaders
+// (fp32 -> fp16 hi/lo conversion) and the epilogue need the warps, the MMAs are issued by one thread either way
 template <int NT, int SPLIT_A, int W_LO>
-__global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
+constexpr int tc_threads() { return tc_min_blocks<NT, SPLIT_A, W_LO>() == 2 ? 256 : 512; }
+
+template <int NT, int SPLIT_A, int W_LO>
+__global__ void __launch_bounds__(tc_threads<NT, SPLIT_A, W_LO>(), tc_min_blocks<NT, SPLIT_A, W_LO>())
+tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
+  constexpr int NTHR = tc_threads<NT, SPLIT_A, W_LO>();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
@@ -152,13 +158,14 @@ __global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_c
   const __half* __restrict__ wlo = p.tc_wlo;
   bool ok = true;
 
-  // loader geometry: A tile = 128 rows x 16 float4; thread -> column group c4, rows ar0 + 16 * it
+  // loader geometry: A tile = 128 rows x 16 float4; thread -> column group c4, rows ar0 + ARS * it
+  constexpr int ARS = NTHR / 16, WRS = NTHR / 8;    // row steps (multiples of 8: the swizzle phase is kept)
   const int c4 = tid & 15, ar0 = tid >> 4;
-  const uint32_t a_off0 = swz(ar0, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;   // rows step by 16 -> +2048 bytes
-  constexpr int AIT = BM * 16 / NTHR;               // 8
-  constexpr int WIT = (NT * 8 + NTHR - 1) / NTHR;   // uint4 per thread per W tile
-  const int wn0 = tid >> 3, wc8 = tid & 7;          // W tile: rows wn0 + 32 * it, 16-byte chunk wc8
-  const uint32_t w_off0 = swz(wn0, wc8);            // rows step by 32 -> +4096 bytes
+  const uint32_t a_off0 = swz(ar0, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;   // rows step by ARS -> +ARS*128 bytes
+  constexpr int AIT = BM / ARS;                     // 8 (4)
+  constexpr int WIT = (NT + WRS - 1) / WRS;         // uint4 per thread per W tile
+  const int wn0 = tid >> 3, wc8 = tid & 7;          // W tile: rows wn0 + WRS * it, 16-byte chunk wc8
+  const uint32_t w_off0 = swz(wn0, wc8);            // rows step by WRS -> +WRS*128 bytes
 
   const int kb_lo = (int)((long long)KB * ks / p.ksplit), kb_hi = (int)((long long)KB * (ks + 1) / p.ksplit);
   for (int kb = kb_lo; kb < kb_hi; ++kb) {
@@ -177,12 +184,12 @@ __global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_c
       const int t0 = q0 + ar0 + p.in_shift0 + tap * p.in_shift_step;
       const bool kok = kk < Ktot;
       const float* __restrict__ xp = xg + (long long)t0 * p.ldx + ci;
-      const long long rstep = 16ll * p.ldx;
+      const long long rstep = (long long)ARS * p.ldx;
 #pragma unroll
       for (int it = 0; it < AIT; ++it) {
-        const int t = t0 + it * 16;
+        const int t = t0 + it * ARS;
         av[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kok && (q0 + ar0 + it * 16) < nq && (unsigned)t < (unsigned)Tin)
+        if (kok && (q0 + ar0 + it * ARS) < nq && (unsigned)t < (unsigned)Tin)
           av[it] = __ldg(reinterpret_cast<const float4*>(xp + it * rstep));
       }
     }
@@ -192,12 +199,12 @@ __global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_c
       const long long wdelta = wlo - whi;
 #pragma unroll
       for (int it = 0; it < WIT; ++it) {
-        const int n = wn0 + it * 32;
+        const int n = wn0 + it * WRS;
         wv[it] = make_uint4(0u, 0u, 0u, 0u);
         if (W_LO) wl[it] = wv[it];
         if (n < n_mma && n0 + n < p.Cout) {
-          wv[it] = __ldg(reinterpret_cast<const uint4*>(wp + (long long)it * 32 * p.tc_kpad));
-          if (W_LO) wl[it] = __ldg(reinterpret_cast<const uint4*>(wp + (long long)it * 32 * p.tc_kpad + wdelta));
+          wv[it] = __ldg(reinterpret_cast<const uint4*>(wp + (long long)it * WRS * p.tc_kpad));
+          if (W_LO) wl[it] = __ldg(reinterpret_cast<const uint4*>(wp + (long long)it * WRS * p.tc_kpad + wdelta));
         }
       }
     }
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_c
       v.x = fmaxf(v.x, v.x * pre); v.y = fmaxf(v.y, v.y * pre);
       v.z = fmaxf(v.z, v.z * pre); v.w = fmaxf(v.w, v.w * pre);
       const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-      const uint32_t off = a_off0 + (uint32_t)it * 2048u;
+      const uint32_t off = a_off0 + (uint32_t)it * (ARS * 128u);
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&h01);
       pk.y = *reinterpret_cast<const uint32_t*>(&h23);
@@ -226,9 +233,9 @@ __global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_c
     // ---- W tile: n_mma rows x 64 k (pre-packed fp16, zero padded in K)
 #pragma unroll
     for (int it = 0; it < WIT; ++it) {
-      if (wn0 + it * 32 < n_mma) {
-        *reinterpret_cast<uint4*>(sW + w_off0 + (uint32_t)it * 4096u) = wv[it];
-        if (W_LO) *reinterpret_cast<uint4*>(sW + W_BYTES + w_off0 + (uint32_t)it * 4096u) = wl[it];
+      if (wn0 + it * WRS < n_mma) {
+        *reinterpret_cast<uint4*>(sW + w_off0 + (uint32_t)it * (WRS * 128u)) = wv[it];
+        if (W_LO) *reinterpret_cast<uint4*>(sW + W_BYTES + w_off0 + (uint32_t)it * (WRS * 128u)) = wl[it];
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(NTHR, tc_min_blocks<NT, SPLIT_A, W_LO>()) tc_c
   float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
   const int rq = (warp & 3) * 32;                               // first row of this warp's lane quarter
   if (ok) {
-    for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
+    for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += NTHR / 4) {
       uint32_t v[32];
       const bool full = n_mma - c0 >= 32;
       tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)c0, full, v);
@@ -297,7 +304,7 @@ void launch_tc(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   }
   const int nq = p.M + p.q_extra;
   dim3 grid((nq + BM - 1) / BM, ((p.Cout + NT - 1) / NT) * p.ksplit, p.B);
-  tc_conv_gemm_kernel<NT, SPLIT_A, W_LO><<<grid, NTHR, smem, s>>>(p, err_flag);
+  tc_conv_gemm_kernel<NT, SPLIT_A, W_LO><<<grid, tc_threads<NT, SPLIT_A, W_LO>(), smem, s>>>(p, err_flag);
   GENIE_LAUNCHED("tc_conv_gemm");
 }
 
