@@ -30,8 +30,9 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, unsig
   __syncthreads();
   if (threadIdx.x == 0) {
     target += G;
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    // arrive: release-ordered reduction without a return value (no round trip before the poll starts); the
+    // bar.sync above makes the other threads' writes part of what this release publishes
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     for (unsigned spins = 0;; ++spins) {
       unsigned v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
