@@ -306,8 +306,10 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
   if (FUSED) pdl_trigger();
   // kv_len / active are written by the sampler, the cache rows < kv_len by earlier steps: all complete before
   // this step's first kernel started, so they may be read ahead of pdl_wait (only the QKV partials may not)
-  if (active && !active[b]) return;
-  const int T = kv_len[b] + (FUSED ? 0 : t_add);           // cached tokens to stream
+  const int kvl = kv_len[b];                                // both loads in flight before the branch: the start of
+  const int act = active ? active[b] : 1;                   // this kernel is a chain of dependent round trips
+  if (!act) return;
+  const int T = kvl + (FUSED ? 0 : t_add);                  // cached tokens to stream
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = lane >> 3, sub = lane & 7;
   float* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;

@@ -8,6 +8,7 @@ from synth import make_prompt_inputs, make_text_inputs
 B = int(sys.argv[1]); steps = int(sys.argv[2]); vits = len(sys.argv) > 3 and sys.argv[3] == "vits"
 m = B200Model(fixture_dir("v2", 0))
 m.set_option("use_graph", int(os.environ.get("USE_GRAPH", "1")))
+m.set_option("time_attention", int(os.environ.get("TIME_ATT", "0")))
 pr = make_prompt_inputs(seed=1, Lr=60, Ts=264, n_audio=169600)
 prompt = m.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"])
 rng = np.random.default_rng(0)
