@@ -230,8 +230,12 @@ def main():
     audio_dev = torch.zeros(B * TOKENS * 1280, dtype=torch.float32, device=dev)
     stage_ms = {"prefill": [], "decode": [], "vits": [], "generator": []}
 
+    dbg = os.environ.get("BENCH_DEBUG") == "1"
+
     def step_device():
+        w0 = time.perf_counter()
         y_len, idx = model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev)
+        w1 = time.perf_counter()
         t = model.last_timing()
         # host glue of the reference (Inference.py:41-44,108-109) on the small token matrix
         y = y_dev.cpu().numpy()
@@ -239,8 +243,13 @@ def main():
         sems = [s if len(s) else np.zeros(1, np.int64) for s in sems]
         sl = np.asarray([len(s) for s in sems], dtype=np.int32)
         sem_dev = torch.from_numpy(np.concatenate(sems)).to(dev)
+        w2 = time.perf_counter()
         alen = model.vits_decode_device(prompts, seq_dev, lens, sem_dev, sl, audio_dev, seed=sp.seed)
+        w3 = time.perf_counter()
         t2 = model.last_timing()
+        if dbg and rank == 0:
+            print(f"[dbg] t2s call {1e3 * (w1 - w0):.2f} ms (stages {t['t2s_ms']:.2f}), glue {1e3 * (w2 - w1):.2f} ms, "
+                  f"vits call {1e3 * (w3 - w2):.2f} ms (stage {t2['vits_ms']:.2f})", file=sys.stderr)
         stage_ms["prefill"].append(t["prefill_ms"]); stage_ms["decode"].append(t["decode_ms"])
         stage_ms["vits"].append(t2["vits_ms"]); stage_ms["generator"].append(t2["generator_ms"])
         return float(alen.sum()) / 32000.0, t2
@@ -256,17 +265,17 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = N.lib().genie_launch_count()
-    barrier()
+    N.lib().genie_profiler_range(1)     # no-op unless run under `ncu --profile-from-start off`; outside the timed
+    barrier()                           # region: the first cudaProfilerStart of a process costs tens of ms
     t0 = time.perf_counter()
     audio_s = 0.0
     last_t = None
-    N.lib().genie_profiler_range(1)     # no-op unless run under `ncu --profile-from-start off`
     for _ in range(args.steps):
         a, last_t = step_device()
         audio_s += a
-    N.lib().genie_profiler_range(0)
     barrier()
     dt = time.perf_counter() - t0
+    N.lib().genie_profiler_range(0)
     launches = N.lib().genie_launch_count() - launches0
     clk = clocks.stop()
 
