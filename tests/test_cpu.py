@@ -235,3 +235,59 @@ def test_gloo_world_size_2_sharding(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ---------------------------------------------------------------- dynamic batching front
+class _FakeSynth:
+    """Stands in for GENIE.tts_batch: tags each waveform with its phoneme count, records batch sizes."""
+
+    def __init__(self, delay=0.02, fail_on=None):
+        self.batches, self.delay, self.fail_on = [], delay, fail_on
+
+    def tts_batch(self, model, prompts, text_seqs, text_berts=None, sampling=None, zp_noise=None):
+        import time
+        time.sleep(self.delay)
+        self.batches.append((len(prompts), None if text_berts is None else [b.shape for b in text_berts]))
+        if self.fail_on is not None and any(len(s) == self.fail_on for s in text_seqs):
+            raise ValueError("bad request in batch")
+        return [np.full(3, float(len(s)) + 1000.0 * p, np.float32) for p, s in zip(prompts, text_seqs)]
+
+
+def test_batch_scheduler_batches_orders_and_survives_errors():
+    from concurrent.futures import wait
+    from genie_tts.Scheduler import BatchScheduler, ReplicaPool
+    synth = _FakeSynth()
+    sch = BatchScheduler(model=None, synthesizer=synth, max_batch=16, max_wait_ms=30.0)
+    futs = [sch.submit(i % 3, np.arange(5 + i), np.ones((5 + i, 1024), np.float32) if i == 7 else None) for i in range(40)]
+    wait(futs, timeout=30)
+    for i, f in enumerate(futs):                               # every request gets ITS result, whatever the batching
+        assert f.result()[0] == 5 + i + 1000.0 * (i % 3)
+    st = sch.stats.summary()
+    assert st["requests"] == 40 and st["batches"] < 40 and st["max_batch"] <= 16 and st["latency_ms_p50"] > 0
+    assert sum(n for n, _ in synth.batches) == 40
+    # a batch containing BERT rows passes zero rows for the others (reference: zeros == no features)
+    shapes = [b for _, b in synth.batches if b is not None]
+    assert shapes and all(s[1] == 1024 for batch in shapes for s in batch)
+    # an exception fails only that batch; the worker keeps serving
+    synth.fail_on = 9
+    bad = sch.submit(0, np.arange(9))
+    with pytest.raises(ValueError):
+        bad.result(timeout=10)
+    synth.fail_on = None
+    assert sch.submit(0, np.arange(4)).result(timeout=10)[0] == 4.0
+    with pytest.raises(ValueError):
+        sch.submit(0, np.zeros(0))
+    assert sch.load == 0
+    sch.close()
+    with pytest.raises(RuntimeError):
+        sch.submit(0, np.arange(3))
+    # replica pool: least-loaded dispatch, one prompt handle per replica
+    s0, s1 = (BatchScheduler(None, _FakeSynth(delay=0.05), max_batch=4, max_wait_ms=1.0, name=f"r{i}") for i in range(2))
+    pool = ReplicaPool([s0, s1])
+    fs = [pool.submit([0, 1], np.arange(10)) for _ in range(16)]
+    wait(fs, timeout=30)
+    used = {int(f.result()[0]) // 1000 for f in fs}
+    assert used == {0, 1}
+    with pytest.raises(ValueError):
+        pool.submit([0], np.arange(3))
+    pool.close()

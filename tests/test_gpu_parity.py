@@ -269,3 +269,48 @@ def test_error_paths(v2, tmp_path):
     with pytest.raises(N.GenieNativeError):
         m.make_prompt(pr["ref_seq"], None, pr["ssl_content"][:, :, :1], pr["ref_audio"])   # Ts < 2
     prompt.close()
+
+
+@pytest.mark.gpu
+def test_batch_scheduler_concurrent_requests_match_single(v2):
+    """24 requests submitted from 6 threads are served as a few batched calls; each request must get the result the
+    same sentence gets on its own.  Checked on the semantic tokens (exact): the vocoder's z_p noise is drawn per
+    (seed, position in the batch), as unseeded in the reference, so waveforms are only compared for length."""
+    import threading
+    from genie_tts.Core.Inference import GENIE, finish_t2s, strip_eos
+    from genie_tts.Scheduler import BatchScheduler
+    from genie_tts.engine import SamplingParams
+    m, _ = v2
+    sp = SamplingParams(greedy=True, max_steps=10, fixed_steps=10, seed=5)
+    pr = make_prompt_inputs(seed=600, Lr=20, Ts=64, n_audio=32000)
+    prompt = _prompt(m, pr)
+
+    class TokenSynth:
+        def tts_batch(self, model, prompts, text_seqs, text_berts=None, sampling=None, zp_noise=None):
+            ys, idx = model.t2s_generate(prompts, text_seqs, text_berts, sampling)
+            return [strip_eos(finish_t2s(y, i)).reshape(-1) for y, i in zip(ys, idx)]
+
+    txs = [make_text_inputs(seed=610 + i, Lt=8 + (i % 7)) for i in range(24)]
+    for synth in (TokenSynth(), GENIE()):
+        sch = BatchScheduler(m, synthesizer=synth, sampling=sp, max_batch=16, max_wait_ms=20.0)
+        futs = [None] * len(txs)
+
+        def client(k):
+            for i in range(k, len(txs), 6):
+                futs[i] = sch.submit(prompt, txs[i]["text_seq"])
+
+        th = [threading.Thread(target=client, args=(k,)) for k in range(6)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        got = [f.result(timeout=120) for f in futs]
+        st = sch.stats.summary()
+        sch.close()
+        assert st["requests"] == 24 and st["batches"] < 24
+        for i in (0, 5, 11, 23):
+            ref = synth.tts_batch(m, [prompt], [txs[i]["text_seq"]], None, sampling=sp)[0]
+            assert len(ref) == len(got[i]) and len(ref) > 0
+            if isinstance(synth, TokenSynth):
+                assert np.array_equal(ref, got[i])
+            else:
+                assert len(ref) % 1280 == 0 and np.isfinite(got[i]).all()
+    prompt.close()
