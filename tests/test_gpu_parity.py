@@ -314,3 +314,35 @@ def test_batch_scheduler_concurrent_requests_match_single(v2):
             else:
                 assert len(ref) % 1280 == 0 and np.isfinite(got[i]).all()
     prompt.close()
+
+
+@pytest.mark.gpu
+def test_long_sequences_all_decode_paths(v2):
+    """Config-3 lengths: prefill over 360 positions (6 flash-attention tiles), 260 decode steps (KV up to 620, several
+    key rounds per attention CTA / chunk).  The persistent step (batch 2), the kernel chain (batch 2, option off)
+    and the tensor-core batch path (batch 12) must all reproduce the oracle's greedy tokens."""
+    from genie_tts.engine import SamplingParams
+    from oracle import gsv_port as P
+    m, pm = v2
+    steps = 260
+    sp = SamplingParams(greedy=True, max_steps=steps)
+    pr = make_prompt_inputs(seed=700, Lr=80, Ts=300, n_audio=64000)
+    prompt = _prompt(m, pr)
+    txs = [make_text_inputs(seed=710 + i, Lt=130 - 9 * i) for i in range(12)]
+    try:
+        r0 = P.t2s_generate(pm, pr["ref_seq"], pr["ref_bert"], txs[0]["text_seq"], txs[0]["text_bert"], pr["ssl_content"],
+                            max_steps=steps)
+        r1 = P.t2s_generate(pm, pr["ref_seq"], pr["ref_bert"], txs[1]["text_seq"], txs[1]["text_bert"], pr["ssl_content"],
+                            max_steps=steps)
+        for mode in (4, 0):
+            m.set_option("persistent_step", mode)
+            ys, idx = m.t2s_generate([prompt] * 2, [t["text_seq"] for t in txs[:2]], None, sp)
+            assert np.array_equal(ys[0], r0.y_full[0]) and idx[0] == r0.idx
+            assert np.array_equal(ys[1], r1.y_full[0]) and idx[1] == r1.idx
+        m.set_option("persistent_step", 4)
+        ys, idx = m.t2s_generate([prompt] * 12, [t["text_seq"] for t in txs], None, sp)
+        assert np.array_equal(ys[0], r0.y_full[0]) and idx[0] == r0.idx
+        assert np.array_equal(ys[1], r1.y_full[0]) and idx[1] == r1.idx
+    finally:
+        m.set_option("persistent_step", 4)
+        prompt.close()
