@@ -33,6 +33,7 @@ struct HaloGeom {
   int lo = 0;                 // smallest tap shift: halo row rr holds input row q0 + lo + rr
   int R = 0;                  // rows staged per CTA
   int slabs = 1;              // 64-channel slabs (1 for Cin <= 64)
+  int cpad = 0;               // channels per staged row incl. zero padding (24 -> 32, 48 -> 64, 96 -> 128)
   uint32_t slab_bytes = 0;
   int U = 1, NU = 1, NI = 1;  // units (tap, slab) per ring slot / total / ring iterations
   uint32_t slot_bytes = 0;
@@ -140,8 +141,11 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
       if (n >= n_mma) continue;
       const int u = u0 + ul;
       const int tap = u / g.slabs, sl = u - tap * g.slabs;
-      const bool valid = n0 + n < p.Cout;
-      const __half* src = whi + (long long)(n0 + n) * p.tc_kpad + tap * p.Cin + sl * 64 + c * 8;
+      // channel-padded layers: chunks beyond Cin read the next tap's weights (finite, multiplied by the zero
+      // padding of the activation tile); only the end of the packed row needs the guard
+      const int kcol = tap * p.Cin + sl * 64 + c * 8;
+      const bool valid = n0 + n < p.Cout && kcol + 8 <= p.tc_kpad;
+      const __half* src = whi + (long long)(n0 + n) * p.tc_kpad + kcol;
       const uint32_t off = (uint32_t)(n * ROWB + c * 16);
       cp_async16(dst + (uint32_t)ul * UNIT_BYTES + (off ^ (((off >> 7) & SWMASK) << 4)), valid ? src : whi,
                  valid ? 16 : 0);
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   if (!(g.flags & 2)) {
     const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
     const float pre = p.pre_slope;                  // 0 <= pre <= 1: lrelu(v) == max(v, v * pre)
-    const int cq = p.Cin >> 2;                      // float4 per row
+    const int cq = g.cpad >> 2;                     // float4 per staged row (channels >= Cin are zero padding)
     const int totalA = g.R * cq;
     const int tbase = q0 + g.lo;
     for (int i0 = 0; i0 < totalA; i0 += NTHR * 8) {
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
         const uint32_t off = (uint32_t)(rr * ROWB + (c & 63) * 2);
         so[k] = idx < totalA ? (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & SWMASK) << 4)) : 0xffffffffu;
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < totalA && (unsigned)t < (unsigned)Tin)
+        if (idx < totalA && c < p.Cin && (unsigned)t < (unsigned)Tin)
           v[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)t * p.ldx + c));
       }
 #pragma unroll
@@ -471,7 +475,7 @@ bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t 
   g.lo = s_first < s_last ? s_first : s_last;
   const int hi = s_first < s_last ? s_last : s_first;
   g.R = 128 + (hi - g.lo);
-  g.slabs = p.Cin / 64;
+  g.slabs = p.Cin / 64; g.cpad = p.Cin;
   g.slab_bytes = (uint32_t)(((size_t)g.R * 128 + 1023) / 1024 * 1024);
   g.NU = p.ntaps * g.slabs;
   g.U = 1; g.NI = g.NU; g.slot_bytes = BTILE; g.flags = flags;
@@ -498,7 +502,8 @@ bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   g.lo = s_first < s_last ? s_first : s_last;
   const int hi = s_first < s_last ? s_last : s_first;
   g.R = MT * 128 + (hi - g.lo);
-  g.slabs = p.Cin > 64 ? p.Cin / 64 : 1;
+  g.cpad = p.Cin > 64 ? (p.Cin + 63) / 64 * 64 : ROWB / 2;
+  g.slabs = g.cpad > 64 ? g.cpad / 64 : 1;
   g.slab_bytes = (uint32_t)(((size_t)g.R * ROWB + 1023) / 1024 * 1024);
   g.NU = p.ntaps * g.slabs;
   g.U = (NT <= 64 ? 8192 : 16384) / (NT * ROWB);   // ring slot: 8 KB where that buys a third / fourth CTA per SM
@@ -555,8 +560,11 @@ bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   if (p.act != ACT_NONE && p.act != ACT_RELU && p.act != ACT_LRELU) return false;
   if (p.ldx % 4 != 0) return false;
   if (p.M + p.q_extra <= 0 || p.B <= 0) return true;
+  if (p.Cin % 8 != 0) return false;
   if (p.Cin == 16 && p.Cout <= 16) return launch_halo<16, 4, 32>(p, mode, err_flag, s);
-  if (p.Cin == 32 && p.Cout <= 32) return launch_halo<32, 4, 64>(p, mode, err_flag, s);
+  if (p.Cin > 16 && p.Cin <= 32 && p.Cout <= 32) return launch_halo<32, 4, 64>(p, mode, err_flag, s);   // 24 (V2ProPlus), 32
+  if (p.Cin > 32 && p.Cin < 64 && p.Cout <= 64) return launch_halo<64, 2, 128>(p, mode, err_flag, s);    // 48
+  if (p.Cin > 64 && p.Cin < 128 && p.Cout <= 128) return launch_halo<128, 1, 128>(p, mode, err_flag, s); // 96
   // wider layers: the per-tap gather of tc_gemm.cu at two CTAs per SM is faster than one halo CTA per SM
   // (measured: C=256 k=11 586 vs 1269 us, C=128 k=7 1067 vs 1194 us) unless forced for testing
   if (p.Cin % 64 == 0 && p.Cin >= 128 && p.Cin <= g_halo_bulk_max_cin && p.tc_tiles != nullptr && p.Cout % BNT == 0 && !(mode & 1))
