@@ -37,6 +37,16 @@ extern "C" {
 const char* genie_last_error(void) { return g_err.c_str(); }
 int genie_version(void) { return 100; }
 unsigned long long genie_launch_count(void) { return g_launches; }
+int genie_host_alloc(size_t bytes, void** out) {
+  return guarded([&] {
+    GENIE_CHECK(out != nullptr && bytes > 0, "bad argument");
+    GENIE_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return 0;
+  });
+}
+int genie_host_free(void* p) {
+  return guarded([&] { if (p) GENIE_CUDA(cudaFreeHost(p)); return 0; });
+}
 int genie_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -35,6 +35,8 @@ SIGNATURES = {
     "genie_version": (C.c_int, []),
     "genie_launch_count": (C.c_ulonglong, []),
     "genie_device_count": (C.c_int, []),
+    "genie_host_alloc": (C.c_int, [C.c_size_t, _P]),
+    "genie_host_free": (C.c_int, [_P]),
     "genie_model_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "genie_model_add_tensor": (C.c_int, [_P, C.c_int, C.c_char_p, _P, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "genie_model_set_constants": (C.c_int, [_P, _P, C.c_int, C.c_float, C.c_float, C.c_float]),

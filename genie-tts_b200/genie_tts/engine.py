@@ -63,6 +63,50 @@ class SamplingParams:
                           self.seed & 0xFFFFFFFFFFFFFFFF, self.max_steps, self.fixed_steps)
 
 
+class _PinnedPool:
+    """Page-locked result buffers, recycled when every numpy view of a buffer has been dropped.
+
+    ``cudaHostAlloc`` costs milliseconds, so buffers are kept: ``take(n)`` returns a float32 array of n elements
+    backed by pinned memory; a ``weakref.finalize`` on that array returns the block to the pool (slices handed to
+    callers keep the array alive through ``.base``)."""
+
+    MAX_KEEP = 8
+
+    def __init__(self):
+        import threading
+        self._free: List[Tuple[int, int]] = []          # (bytes, address)
+        self._lock = threading.Lock()
+
+    def take(self, n_floats: int) -> np.ndarray:
+        import weakref
+        nbytes = max(4, int(n_floats) * 4)
+        with self._lock:
+            fit = [i for i, (b, _) in enumerate(self._free) if b >= nbytes]
+            blk = self._free.pop(min(fit, key=lambda i: self._free[i][0])) if fit else None
+        if blk is None:
+            cap = max(1 << 20, 1 << (nbytes - 1).bit_length())        # power-of-two blocks: steady sizes get reused
+            ptr = C.c_void_p()
+            N.check(N.lib().genie_host_alloc(C.c_size_t(cap), C.byref(ptr)))
+            blk = (cap, ptr.value)
+        cap, addr = blk
+        arr = np.frombuffer((C.c_char * cap).from_address(addr), dtype=np.float32, count=int(n_floats))
+        weakref.finalize(arr, self._release, cap, addr)
+        return arr
+
+    def _release(self, cap: int, addr: int) -> None:
+        with self._lock:
+            if len(self._free) < self.MAX_KEEP:
+                self._free.append((cap, addr))
+                return
+        try:
+            N.lib().genie_host_free(C.c_void_p(addr))
+        except Exception:
+            pass
+
+
+_pinned = _PinnedPool()
+
+
 class B200Model:
     def __init__(self, model_dir: str, device: int = 0):
         N.require_gpu()
@@ -169,7 +213,7 @@ class B200Model:
                                     for z, s_ in zip(zp_noise, sems)])
         # one fresh buffer per call (every sample is written by the library); the per-utterance results are
         # views into it, so the 1280 samples per token cross the host memory bus once
-        audio = np.empty(int(sl.sum()) * 1280, dtype=np.float32)
+        audio = _pinned.take(int(sl.sum()) * 1280)       # page-locked: the device-to-host copy runs at DMA speed
         alen = np.zeros(B, dtype=np.int32)
         hs = (C.c_void_p * B)(*[p._h for p in prompts])
         seq_cat, sem_cat = np.concatenate(seqs), np.concatenate(sems)   # keep alive across the call

@@ -39,6 +39,10 @@ int genie_version(void);
 /* kernels launched by this library since load (bench.py: gpu_launches) */
 unsigned long long genie_launch_count(void);
 int genie_device_count(void);
+/* page-locked host buffers for result payloads (the 1280 samples per token of genie_vits_decode cross PCIe at
+ * DMA speed instead of through the driver's bounce buffers); the host side pools and reuses them */
+int genie_host_alloc(size_t bytes, void** out);
+int genie_host_free(void* p);
 
 /* ---- model store: replaces ModelManager.load_character / load_session_with_fp16_conversion
  * (src/genie_tts/ModelManager.py:59-114, 231-310).  The host side parses the .onnx
