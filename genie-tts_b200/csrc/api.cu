@@ -69,6 +69,10 @@ int genie_model_create(int device, genie_model** out) {
     h->m.device = device;
     GENIE_CUDA(cudaStreamCreateWithFlags(&h->m.stream, cudaStreamNonBlocking));
     GENIE_CUDA(cudaStreamCreateWithFlags(&h->m.stream2, cudaStreamNonBlocking));
+    GENIE_CUDA(cudaStreamCreateWithFlags(&h->m.stream3, cudaStreamNonBlocking));
+    GENIE_CUDA(cudaStreamCreateWithFlags(&h->m.stream4, cudaStreamNonBlocking));
+    GENIE_CUDA(cudaEventCreateWithFlags(&h->m.ev_join3, cudaEventDisableTiming));
+    GENIE_CUDA(cudaEventCreateWithFlags(&h->m.ev_join4, cudaEventDisableTiming));
     GENIE_CUDA(cudaEventCreateWithFlags(&h->m.ev_fork, cudaEventDisableTiming));
     GENIE_CUDA(cudaEventCreateWithFlags(&h->m.ev_join, cudaEventDisableTiming));
     *out = h;
@@ -282,6 +286,7 @@ int genie_set_option(genie_model* h, const char* key, int value) {
   if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
   if (std::strcmp(key, "decode_split_min") == 0) { h->m.decode_split_min = value; h->m.step_graph_flags = -1; return 0; }
+  if (std::strcmp(key, "decode_branches") == 0) { h->m.decode_branches = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "skinny_max_rows") == 0) { h->m.skinny_max_rows = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_min_rows") == 0) { h->m.tc_min_rows = value; h->m.step_graph_flags = -1; return 0; }
   g_err = std::string("unknown option ") + key;

@@ -83,6 +83,7 @@ struct SamplerArgs {
   int* active;             // [B] cleared on stop (when honour_stop)
   int* stop_step;          // [B] step index at which stop fired (or -1)
   int B;
+  int utt_base;            // index of row 0 in the whole batch (Philox key): a split batch samples like the whole one
   int top_k; float temperature; float penalty;
   int greedy; unsigned long long seed; int step;
   int honour_stop; int advance_kv; int check_stop;

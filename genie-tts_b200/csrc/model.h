@@ -75,9 +75,12 @@ struct Workspace {
 struct Model {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;     // second branch of the decode-step graph
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int decode_split_min = 1 << 30;     // measured: halves are latency-bound like the whole batch, no gain
+  // the decode-step graph runs the batch as up to 4 independent branches (contiguous utterance ranges) on
+  // their own streams: every decode kernel is latency-bound, so the branches overlap
+  cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
+  int decode_split_min = 64;          // batches >= this are split; decode_branches = number of branches
+  int decode_branches = 2;
   bool finalized = false, v2pp = false;
   std::unordered_map<std::string, RawTensor> raw[4];
   std::vector<void*> owned;           // device allocations owned by the model
@@ -117,6 +120,7 @@ struct Model {
   cudaGraphExec_t step_graph = nullptr; int step_graph_B = 0; unsigned long long step_graph_gen = 0;
   int step_graph_cap = 0; int step_graph_flags = 0; int step_graph_hist_ld = 0;
   unsigned long long step_graph_seed = 0; float step_graph_temp = 0.f, step_graph_pen = 0.f;
+  unsigned long long step_graph_launches = 0;   // kernels per replay (counted at capture)
   int use_graph = 1;
   // tcgen05 path: 0 = exact SIMT everywhere; T2S always runs x_hi+x_lo against fp16-exact weights;
   // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
     float pr = lg[i] / denom;
     float q = 1.f;
     if (!a.greedy) q = a.dbg_noise ? a.dbg_noise[(long long)b * V + i]
-                                   : philox_normal(a.seed, (uint32_t)b, (uint32_t)n, (uint32_t)i);
+                                   : philox_normal(a.seed, (uint32_t)(b + a.utt_base), (uint32_t)n, (uint32_t)i);
     ArgVal c; c.v = pr / q; c.i = i;
     loc = better(loc, c);
   }

@@ -37,6 +37,7 @@ struct StepBufs {
   float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part, *part2, *ppart;
   int *hist, *hist_len, *kv_len, *active, *stop_step;
   float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld; long long part_stride;
+  int utt_base;   // first utterance of this branch within the batch
 };
 
 // pointer table / barrier words of the persistent step (allocated outside any stream capture)
@@ -87,6 +88,7 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
     const T2SLayer& L = m.layers[l];
     const long long ps = w.part_stride;   // rows of the WHOLE batch
     const bool small_tc = m.use_tc && B > m.skinny_max_rows && B <= 128;
+    const int r0 = 0;   // partial-sum buffers belong to the branch (see the capture code): rows start at 0
     if (small_tc) {
       // single-shot tcgen05 GEMMs (tc_small_gemm.cu): every output is a split-K partial; bias, residual,
       // activation and the KV append are applied by the consumer kernels
@@ -94,25 +96,25 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
         SmallGemm g;
         g.x = x; g.ldx = ldx; g.a_nsplit = a_ns; g.a_stride = ps * (ldx / D); g.a_bias = a_bias; g.a_relu = a_relu;
         g.w = reinterpret_cast<const __half*>(Lw.w); g.ldw = Lw.K; g.N = Lw.N; g.K = Lw.K; g.M = B;
-        g.y = w.part; g.ldy = Lw.N; g.split_stride = ps * (Lw.N / D);
+        g.y = w.part + (size_t)r0 * Lw.N; g.ldy = Lw.N; g.split_stride = ps * (Lw.N / D);
         launch_tc_small_gemm(g, nt, m.tc_err, s);
       };
       gemm(L.qkv, w.h, D, 1, nullptr, 0, 32);                                   // 2 partials [B,1536]
-      launch_decode_attention_fused(w.part, 2, ps * 3, L.qkv.b, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off,
+      launch_decode_attention_fused(w.part + (size_t)r0 * 3 * D, 2, ps * 3, L.qkv.b, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off,
                                     w.kv_len, w.active, B, w.cap, scale, s);
       gemm(L.out, w.att, D, 1, nullptr, 0, 32);                                 // 2 partials [B,512]
-      launch_layernorm(w.part, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 2, ps, L.out.b);
+      launch_layernorm(w.part + (size_t)r0 * D, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 2, ps, L.out.b);
       gemm(L.ff1, w.h1, D, 1, nullptr, 0, 32);                                  // 2 partials [B,2048]
       // FFN2 reads relu(sum FFN1 partials + bias) as its A operand: partials live in w.part, so its own
       // output partials go to w.part2
       {
         SmallGemm g;
-        g.x = w.part; g.ldx = 4 * D; g.a_nsplit = 2; g.a_stride = ps * 4; g.a_bias = L.ff1.b; g.a_relu = 1;
+        g.x = w.part + (size_t)r0 * 4 * D; g.ldx = 4 * D; g.a_nsplit = 2; g.a_stride = ps * 4; g.a_bias = L.ff1.b; g.a_relu = 1;
         g.w = reinterpret_cast<const __half*>(L.ff2.w); g.ldw = L.ff2.K; g.N = D; g.K = 4 * D; g.M = B;
-        g.y = w.part2; g.ldy = D; g.split_stride = ps;
+        g.y = w.part2 + (size_t)r0 * D; g.ldy = D; g.split_stride = ps;
         launch_tc_small_gemm(g, 32, m.tc_err, s);                               // 8 partials [B,512]
       }
-      launch_layernorm(w.part2, w.h1, L.ln2_g, L.ln2_b, w.h, B, D, s, 8, ps, L.ff2.b);
+      launch_layernorm(w.part2 + (size_t)r0 * D, w.h1, L.ln2_g, L.ln2_b, w.h, B, D, s, 8, ps, L.ff2.b);
       continue;
     }
     const bool sk = true;   // B <= skinny_max_rows (or tcgen05 disabled): weight-streaming SIMT GEMV path
@@ -140,7 +142,7 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   if (!persistent) run_linear(m, m.predict, w.h, D, w.logits, V, B);
   SamplerArgs a{};
   a.logits = w.logits; a.ld = V; a.hist = w.hist; a.hist_ld = w.hist_ld; a.hist_len = w.hist_len;
-  a.kv_len = w.kv_len; a.active = w.active; a.stop_step = w.stop_step; a.B = B;
+  a.kv_len = w.kv_len; a.active = w.active; a.stop_step = w.stop_step; a.B = B; a.utt_base = w.utt_base;
   a.top_k = cfg.top_k; a.temperature = cfg.temperature; a.penalty = cfg.penalty; a.greedy = cfg.greedy;
   a.seed = cfg.seed; a.step = 0; a.honour_stop = cfg.fixed_steps > 0 ? 0 : 1; a.advance_kv = 1; a.check_stop = 1;
   a.dbg_noise = nullptr;
@@ -365,26 +367,36 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       unsigned long long launches_before = g_launches;
       GENIE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
-        if (B >= m.decode_split_min && m.stream2) {
-          // two independent halves of the batch as parallel graph branches: every decode kernel is
-          // latency-bound on a fraction of the SMs, so the halves overlap (one half's KV-bound
-          // attention runs under the other half's GEMMs)
-          const int b1 = B / 2;
+        int nb = (B >= m.decode_split_min && m.stream2) ? m.decode_branches : 1;
+        if (nb > 4) nb = 4;
+        while (nb > 1 && B / nb < 16) --nb;              // every branch stays on the tensor-core path
+        if (nb > 1) {
+          // independent utterance ranges as parallel graph branches: every decode kernel is latency-bound
+          // (or, the attention, bandwidth-bound with few resources), so the branches overlap
+          cudaStream_t bs[4] = {s, m.stream2, m.stream3, m.stream4};
+          cudaEvent_t bj[4] = {nullptr, m.ev_join, m.ev_join3, m.ev_join4};
           GENIE_CUDA(cudaEventRecord(m.ev_fork, s));
-          GENIE_CUDA(cudaStreamWaitEvent(m.stream2, m.ev_fork, 0));
-          decode_step(m, w, b1, cfg);
-          StepBufs w2 = w;
-          w2.h += (size_t)b1 * D; w2.qkv += (size_t)b1 * 3 * D; w2.att += (size_t)b1 * D; w2.tmp += (size_t)b1 * D;
-          w2.h1 += (size_t)b1 * D; w2.ff += (size_t)b1 * 4 * D; w2.logits += (size_t)b1 * V;
-          w2.part += (size_t)b1 * D; w2.part2 += (size_t)b1 * D; w2.hist += (size_t)b1 * w.hist_ld; w2.hist_len += b1; w2.kv_len += b1;
-          w2.active += b1; w2.stop_step += b1; w2.kv += (size_t)b1 * w.utt_stride;
-          w2.part_stride = w.part_stride;
           cudaStream_t keep = m.stream;
-          m.stream = m.stream2;
-          try { decode_step(m, w2, B - b1, cfg); } catch (...) { m.stream = keep; throw; }
+          try {
+            for (int k = 0; k < nb; ++k) {
+              const int b0 = (int)((long long)B * k / nb), b1 = (int)((long long)B * (k + 1) / nb);
+              StepBufs w2 = w;
+              w2.h += (size_t)b0 * D; w2.qkv += (size_t)b0 * 3 * D; w2.att += (size_t)b0 * D; w2.tmp += (size_t)b0 * D;
+              w2.h1 += (size_t)b0 * D; w2.ff += (size_t)b0 * 4 * D; w2.logits += (size_t)b0 * V;
+              // private slice of the partial-sum buffers ([split][rows][N] views with N changing per use must
+              // not overlap between branches that run in different phases): 8 * rows * D floats per branch
+              w2.part += (size_t)8 * b0 * D; w2.part2 += (size_t)8 * b0 * D; w2.part_stride = (long long)(b1 - b0) * D;
+              w2.hist += (size_t)b0 * w.hist_ld;
+              w2.hist_len += b0; w2.kv_len += b0; w2.active += b0; w2.stop_step += b0;
+              w2.kv += (size_t)b0 * w.utt_stride; w2.utt_base = b0;
+              if (k > 0) GENIE_CUDA(cudaStreamWaitEvent(bs[k], m.ev_fork, 0));
+              m.stream = bs[k];
+              decode_step(m, w2, b1 - b0, cfg);
+              if (k > 0) GENIE_CUDA(cudaEventRecord(bj[k], bs[k]));
+            }
+          } catch (...) { m.stream = keep; throw; }
           m.stream = keep;
-          GENIE_CUDA(cudaEventRecord(m.ev_join, m.stream2));
-          GENIE_CUDA(cudaStreamWaitEvent(s, m.ev_join, 0));
+          for (int k = 1; k < nb; ++k) GENIE_CUDA(cudaStreamWaitEvent(s, bj[k], 0));
         } else {
           decode_step(m, w, B, cfg);
         }
@@ -394,6 +406,7 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
         throw;
       }
       GENIE_CUDA(cudaStreamEndCapture(s, &g));
+      m.step_graph_launches = g_launches - launches_before;
       g_launches = launches_before;            // capture does not launch
       GENIE_CUDA(cudaGraphInstantiate(&m.step_graph, g, 0));
       cudaGraphDestroy(g);
@@ -401,7 +414,7 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       m.step_graph_seed = cfg.seed; m.step_graph_temp = cfg.temperature; m.step_graph_pen = cfg.penalty;
     }
   }
-  const unsigned long long per_step_launches = 3 + NL * 8ull;
+  const unsigned long long per_step_launches = m.step_graph_launches;
   int rc = 0;
   std::vector<int> h_act(B, 1);
   int steps_done = 0;

@@ -14,7 +14,6 @@ namespace {
 
 constexpr int KS = 256;                       // K slice per CTA
 constexpr int NKB = KS / 64;                  // 4 swizzle-128B k-blocks
-constexpr int NTHR = 512;                     // 16 warps: the whole A slice of the CTA is one batch of loads
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -37,8 +36,16 @@ __device__ __forceinline__ uint32_t swz(int r, int c8) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4));
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* err_flag) {
+// THR = 512: rows 0..127 (batch <= 128).  THR = 256: rows 0..63 only (batch <= 64; operand rows 64..127 stay
+// uninitialised, their accumulator rows are never read) with half the register file, so that a bandwidth-bound
+// kernel of the other half-batch (decode attention) can share the SM.
+template <int NT, int THR>
+__global__ void __launch_bounds__(THR) tc_small_gemm_kernel(SmallGemm p, int* err_flag) {
+  constexpr int NTHR = THR, RSTEP = THR / 16;
+  // THR = 256 stores 64 operand rows per k-block: the 128-row MMA then reads rows 64..127 from the next
+  // k-block / the weight tiles (in bounds, finite or not: those accumulator rows are never read), and two
+  // such CTAs (81 KB, half the registers each) fit on an SM
+  constexpr uint32_t ABYTES = THR == 256 ? 8192u : 16384u;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -48,8 +55,8 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sA = smem_raw + (base - smem_u32(smem_raw));     // [hi|lo][NKB][128 x 128 B]
-  uint8_t* sAlo = sA + NKB * 16384;
-  uint8_t* sW = sAlo + NKB * 16384;                          // [NKB][NT x 128 B]
+  uint8_t* sAlo = sA + NKB * ABYTES;
+  uint8_t* sW = sAlo + NKB * ABYTES;                          // [NKB][NT x 128 B]
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
     const float* colp = p.x + k0 + c4 * 4;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int r = r0 + (j >> 2) * 32;
+      const int r = r0 + (j >> 2) * RSTEP;
       av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < p.M) av[j] = __ldcg(reinterpret_cast<const float4*>(colp + (long long)r * p.ldx + (j & 3) * 64));
     }
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
       float4 tv[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int r = r0 + (j >> 2) * 32;
+        const int r = r0 + (j >> 2) * RSTEP;
         tv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < p.M) tv[j] = __ldcg(reinterpret_cast<const float4*>(cs + (long long)r * p.ldx + (j & 3) * 64));
       }
@@ -111,7 +118,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
                                : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int r = r0 + i * 32;
+      const int r = r0 + i * RSTEP;
       float4 v = av[i * 4 + kb];
       if (r < p.M) {
         v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
       const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
       const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y);
       const __half2 l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
-      const uint32_t off = (uint32_t)kb * 16384u + swz(r, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;
+      const uint32_t off = (uint32_t)kb * ABYTES + swz(r, c4 >> 1) + (uint32_t)(c4 & 1) * 8u;
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&h01); pk.y = *reinterpret_cast<const uint32_t*>(&h23);
       *reinterpret_cast<uint2*>(sA + off) = pk;
@@ -148,8 +155,8 @@ __global__ void __launch_bounds__(NTHR) tc_small_gemm_kernel(SmallGemm p, int* e
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint64_t db = umma_desc(aW + kb * (NT * 128) + j * 32);
-        umma_f16(tmem, umma_desc(aA + kb * 16384 + j * 32), db, idesc, (uint32_t)((kb | j) != 0));
-        umma_f16(tmem, umma_desc(aL + kb * 16384 + j * 32), db, idesc, 1u);
+        umma_f16(tmem, umma_desc(aA + kb * ABYTES + j * 32), db, idesc, (uint32_t)((kb | j) != 0));
+        umma_f16(tmem, umma_desc(aL + kb * ABYTES + j * 32), db, idesc, 1u);
       }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(&bar)) : "memory");
@@ -238,15 +245,15 @@ __global__ void qkv_finish_kernel(const float* __restrict__ part, int nsplit, lo
   }
 }
 
-template <int NT>
+template <int NT, int THR>
 void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
-  constexpr size_t smem = 2 * NKB * 16384 + (size_t)NKB * NT * 128 + 1024;
+  constexpr size_t smem = 2 * NKB * (THR == 256 ? 8192 : 16384) + (size_t)NKB * NT * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_small_gemm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GENIE_CUDA(cudaFuncSetAttribute(tc_small_gemm_kernel<NT, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  launch_pdl(tc_small_gemm_kernel<NT>, dim3((p.N + NT - 1) / NT, p.K / KS), dim3(NTHR), smem, s, p, err_flag);
+  launch_pdl(tc_small_gemm_kernel<NT, THR>, dim3((p.N + NT - 1) / NT, p.K / KS), dim3(THR), smem, s, p, err_flag);
   GENIE_LAUNCHED("tc_small_gemm");
 }
 
@@ -254,7 +261,9 @@ void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
 
 void launch_tc_small_gemm(const SmallGemm& p, int nt, int* err_flag, cudaStream_t s) {
   GENIE_CHECK(p.M >= 1 && p.M <= 128 && p.K % KS == 0 && p.ldx % 4 == 0 && p.ldw % 8 == 0, "tc_small_gemm: bad shape");
-  if (nt == 64) launch_nt<64>(p, err_flag, s); else launch_nt<32>(p, err_flag, s);
+  if (nt == 64) launch_nt<64, 512>(p, err_flag, s);
+  else if (p.M <= 64) launch_nt<32, 256>(p, err_flag, s);
+  else launch_nt<32, 512>(p, err_flag, s);
 }
 
 void launch_qkv_finish(const float* part, int nsplit, long long split_stride, const float* bias, float* q,

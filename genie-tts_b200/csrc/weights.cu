@@ -20,6 +20,10 @@ Model::~Model() {
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
   if (stream2) cudaStreamDestroy(stream2);
+  if (stream3) cudaStreamDestroy(stream3);
+  if (stream4) cudaStreamDestroy(stream4);
+  if (ev_join3) cudaEventDestroy(ev_join3);
+  if (ev_join4) cudaEventDestroy(ev_join4);
   if (stream) cudaStreamDestroy(stream);
 }
 

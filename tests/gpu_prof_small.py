@@ -9,6 +9,10 @@ B = int(sys.argv[1]); steps = int(sys.argv[2]); vits = len(sys.argv) > 3 and sys
 m = B200Model(fixture_dir("v2", 0))
 m.set_option("use_graph", int(os.environ.get("USE_GRAPH", "1")))
 m.set_option("time_attention", int(os.environ.get("TIME_ATT", "0")))
+if os.environ.get("BRANCHES"):
+    m.set_option("decode_branches", int(os.environ["BRANCHES"]))
+if os.environ.get("SPLIT"):
+    m.set_option("decode_split_min", int(os.environ["SPLIT"]))
 pr = make_prompt_inputs(seed=1, Lr=60, Ts=264, n_audio=169600)
 prompt = m.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"])
 rng = np.random.default_rng(0)

@@ -347,3 +347,33 @@ def test_long_sequences_all_decode_paths(v2):
     finally:
         m.set_option("persistent_step", 4)
         prompt.close()
+
+
+@pytest.mark.gpu
+def test_split_branch_decode_matches_unsplit(v2):
+    """Batches >= 64 replay the decode step as two graph branches (utterance ranges on two streams, private
+    partial-sum buffers).  Greedy and seeded sampling must give exactly the tokens of the unsplit eager step, and
+    selected utterances the tokens of a run on their own."""
+    from genie_tts.engine import SamplingParams
+    m, _ = v2
+    pr = make_prompt_inputs(seed=800, Lr=14, Ts=40, n_audio=32000)
+    prompt = _prompt(m, pr)
+    B = 70
+    txs = [make_text_inputs(seed=810 + i, Lt=7 + (i % 9)) for i in range(B)]
+    seqs = [t["text_seq"] for t in txs]
+    try:
+        for sp in (SamplingParams(greedy=True, max_steps=8), SamplingParams(seed=11, max_steps=8, fixed_steps=8)):
+            m.set_option("decode_split_min", 64)
+            ys_split, idx_split = m.t2s_generate([prompt] * B, seqs, None, sp)          # graph, 2 branches
+            m.set_option("decode_split_min", 1 << 30)
+            ys_one, idx_one = m.t2s_generate([prompt] * B, seqs, None, sp)              # graph, 1 branch
+            assert all(np.array_equal(a, b_) for a, b_ in zip(ys_split, ys_one)) and idx_split == idx_one
+        m.set_option("decode_split_min", 64)
+        sp = SamplingParams(greedy=True, max_steps=8)
+        ys, idx = m.t2s_generate([prompt] * B, seqs, None, sp)
+        for b in (0, 34, 35, 69):
+            y1, i1 = m.t2s_generate([prompt], [seqs[b]], None, sp)
+            assert np.array_equal(ys[b], y1[0]) and idx[b] == i1[0]
+    finally:
+        m.set_option("decode_split_min", 64)
+        prompt.close()
