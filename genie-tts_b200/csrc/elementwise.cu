@@ -233,29 +233,48 @@ __global__ void fill_kernel(float* y, float a, long long n) {
 
 // conv_post (Cout = 1, k = 7, no bias) fused with the preceding leaky-relu(0.01)
 // and the final tanh (vits#[8450-8452]).  One thread per output sample.
-__global__ void conv_post_tanh_kernel(const float* __restrict__ x, int C, const float* __restrict__ w,
-                                      float* __restrict__ audio, const int* __restrict__ off) {
-  extern __shared__ float ws[];   // [7*C]
+// Each input row is read ONCE: the thread that owns row t computes its 7 tap contributions
+// d[t][j] = sum_c lrelu(x[t][c]) * w[j][c]; the outputs are then sums over neighbouring rows in shared
+// memory.  (The first version re-read every row for each of its 7 taps: 742 us for 737 MB.)
+constexpr int CP_ROWS = 256, CP_OUT = CP_ROWS - 6;
+__global__ void __launch_bounds__(CP_ROWS) conv_post_tanh_kernel(const float* __restrict__ x, int C,
+                                                                 const float* __restrict__ w,
+                                                                 float* __restrict__ audio, const int* __restrict__ off) {
+  extern __shared__ float ws[];   // [7*C] weights | [CP_ROWS][7] tap contributions
+  float* d = ws + 7 * C;
   for (int i = threadIdx.x; i < 7 * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const int b = blockIdx.y;
   const int r0 = off[b], T = off[b + 1] - r0;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  float acc = 0.f;
-  for (int j = 0; j < 7; ++j) {
-    int ti = t + j - 3;
-    if (ti < 0 || ti >= T) continue;
+  const int t0 = blockIdx.x * CP_OUT;
+  if (t0 >= T) return;
+  const int ti = t0 - 3 + (int)threadIdx.x;                 // row owned by this thread
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ti >= 0 && ti < T) {
     const float* xr = x + (long long)(r0 + ti) * C;
     for (int c = 0; c < C; c += 4) {
       float4 v = *reinterpret_cast<const float4*>(xr + c);
       v.x = v.x > 0.f ? v.x : v.x * 0.01f; v.y = v.y > 0.f ? v.y : v.y * 0.01f;
       v.z = v.z > 0.f ? v.z : v.z * 0.01f; v.w = v.w > 0.f ? v.w : v.w * 0.01f;
-      acc = fmaf(v.x, ws[j * C + c], acc); acc = fmaf(v.y, ws[j * C + c + 1], acc);
-      acc = fmaf(v.z, ws[j * C + c + 2], acc); acc = fmaf(v.w, ws[j * C + c + 3], acc);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        acc[j] = fmaf(v.x, ws[j * C + c], acc[j]); acc[j] = fmaf(v.y, ws[j * C + c + 1], acc[j]);
+        acc[j] = fmaf(v.z, ws[j * C + c + 2], acc[j]); acc[j] = fmaf(v.w, ws[j * C + c + 3], acc[j]);
+      }
     }
   }
-  audio[r0 + t] = tanhf(acc);
+#pragma unroll
+  for (int j = 0; j < 7; ++j) d[threadIdx.x * 7 + j] = acc[j];
+  __syncthreads();
+  const int t = t0 + (int)threadIdx.x;
+  if ((int)threadIdx.x < CP_OUT && t < T) {
+    // out[t] = sum_j x[t + j - 3] . w[j]: row t + j - 3 sits at slot threadIdx.x + j.  Same order of the
+    // j-sum as before; the c-sum is now per tap (rounding differs in the last bits only)
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) o += d[(threadIdx.x + j) * 7 + j];
+    audio[r0 + t] = tanhf(o);
+  }
 }
 
 // spectrogram framing (vits#[3-36]): reflect pad 704 each side, frames of 2048 hop 640,
@@ -444,7 +463,7 @@ void launch_fill(float* y, float a, long long n, cudaStream_t s) {
 void launch_conv_post_tanh(const float* x, int C, const float* w, float* audio, const int* off, int B, int maxT,
                            cudaStream_t s) {
   if (B <= 0 || maxT <= 0) return;
-  conv_post_tanh_kernel<<<dim3(nblk(maxT, 256), B), 256, 7 * C * sizeof(float), s>>>(x, C, w, audio, off);
+  conv_post_tanh_kernel<<<dim3(nblk(maxT, CP_OUT), B), CP_ROWS, (7 * C + CP_ROWS * 7) * sizeof(float), s>>>(x, C, w, audio, off);
   GENIE_LAUNCHED("conv_post_tanh");
 }
 void launch_stft_frames(const float* audio, int n, float* frames, int F, cudaStream_t s) {

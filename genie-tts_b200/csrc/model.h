@@ -43,6 +43,9 @@ struct Conv {              // repacked [Cout][k][Cin] fp32 (weight-norm folded)
 struct ConvT {             // repacked [k][Cout][Cin] fp32
   const float* w = nullptr; const float* b = nullptr; int Cout = 0, Cin = 0, k = 0, stride = 0, pad = 0;
   TcW tc[10];              // one packed matrix per output phase r = (t_out + pad) mod stride
+  // k == stride, pad == 0: the phases do not overlap, so the layer is ONE linear map [T, Cin] -> [T, k*Cout]
+  // whose output rows are the k output frames side by side (= the channels-last output as it is)
+  TcW tc_fused; const float* bias_fused = nullptr;
 };
 
 struct T2SLayer {

@@ -45,6 +45,24 @@ void run_conv(Model& m, const Conv& c, const float* x, int ldx, float* y, int ld
 
 void run_convt(Model& m, const ConvT& c, const float* x, float* y, const Seg& in, const Seg& out, float pre_slope) {
   const long long tap_sz = (long long)c.Cout * c.Cin;
+  if (c.bias_fused && in.off && out.off) {
+    // k == stride, pad == 0: one linear layer, every input row read once (was one launch per phase)
+    ConvGemm p;
+    p.x = x; p.ldx = c.Cin; p.w = c.w; p.w_f16 = 0; p.w_co_stride = c.Cin; p.w_tap_stride = 0;
+    p.bias = c.bias_fused; p.y = y; p.ldy = c.Cout * c.k;
+    p.Cin = c.Cin; p.Cout = c.Cout * c.k; p.ntaps = 1; p.in_shift0 = 0; p.in_shift_step = 1;
+    p.pre_slope = pre_slope;
+    p.in_off = in.off; p.out_off = in.off; p.B = in.B; p.M = in.maxT; p.M_out = in.maxT;   // out.off[b] == k * in.off[b]
+    if (m.use_tc && c.tc_fused.hi) {
+      p.tc_w = c.tc_fused.hi; p.tc_kpad = c.tc_fused.kpad;
+      p.tc_wlo = m.tc_vits >= 3 ? c.tc_fused.lo : nullptr;
+      p.tc_split_a = m.tc_vits >= 2;
+      launch_tc_conv_gemm(p, m.tc_err, m.stream);
+    } else {
+      launch_conv_gemm(p, m.stream);
+    }
+    return;
+  }
   for (int r = 0; r < c.stride; ++r) {
     int ntaps = (c.k - r + c.stride - 1) / c.stride;
     if (ntaps <= 0) continue;

@@ -200,6 +200,15 @@ struct Finalizer {
       const int ntaps = (c.k - r + c.stride - 1) / c.stride;
       if (ntaps > 0) c.tc[r] = pack(c.w + r * tap_sz, c.Cin, c.stride * tap_sz, ntaps, c.Cin, c.Cout);
     }
+    if (c.k == c.stride && c.pad == 0 && c.Cin % 4 == 0) {
+      c.tc_fused = pack(c.w, c.Cin, 0, 1, c.Cin, c.Cout * c.k);
+      float* bf = dev_alloc<float>(m.owned, (size_t)c.Cout * c.k);
+      for (int r = 0; r < c.k; ++r) {
+        if (c.b) GENIE_CUDA(cudaMemcpyAsync(bf + (size_t)r * c.Cout, c.b, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, s));
+        else GENIE_CUDA(cudaMemsetAsync(bf + (size_t)r * c.Cout, 0, (size_t)c.Cout * 4, s));
+      }
+      c.bias_fused = bf;
+    }
   }
   void pack_linear(Linear& L) {
     if (L.w_f16 && L.K % 64 == 0) { L.tc.hi = reinterpret_cast<const __half*>(L.w); L.tc.lo = nullptr; L.tc.kpad = L.K; }
