@@ -446,15 +446,6 @@ void launch_attention(const Attn& p, cudaStream_t s) {
   GENIE_LAUNCHED("attention");
 }
 
-void launch_decode_attention_raw(const float* q, float* o, const float* kv_base, long long utt_stride,
-                                 long long layer_off, long long v_off, const int* kv_len, const int* active,
-                                 int B, int cap, float scale, int t_add, int ldq, cudaStream_t s) {
-  if (B <= 0) return;
-  decode_attention_kernel<false><<<dim3(16, B), 128, 0, s>>>(q, 1, 0, nullptr, o, const_cast<float*>(kv_base), utt_stride,
-                                                             layer_off, v_off, kv_len, active, cap, scale, t_add, ldq);
-  GENIE_LAUNCHED("decode_attention");
-}
-
 void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
                                    float* kv_base, long long utt_stride, long long layer_off, long long v_off,
                                    const int* kv_len, const int* active, int B, int cap, float scale, cudaStream_t s) {

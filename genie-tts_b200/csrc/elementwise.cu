@@ -218,18 +218,6 @@ __global__ void zp_kernel(const float* stats, const float* noise, float* zp, flo
   zp[i] = m + nz * expf(logs) * scale;
 }
 
-__global__ void add_inplace_kernel(float* y, const float* x, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] += x[i];
-}
-__global__ void scale_inplace_kernel(float* y, float a, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] *= a;
-}
-__global__ void fill_kernel(float* y, float a, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = a;
-}
 
 // conv_post (Cout = 1, k = 7, no bias) fused with the preceding leaky-relu(0.01)
 // and the final tanh (vits#[8450-8452]).  One thread per output sample.
@@ -352,12 +340,6 @@ __global__ void vq_argmax_kernel(const float* x2, const float* xe, const float* 
   if (lane == 0) codes[row] = bi;
 }
 
-__global__ void copy_cols_kernel(const float* src, int lds, int c0, float* dst, int ldd, int d0, int C, int rows) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows * C) return;
-  int c = (int)(i % C); long long r = i / C;
-  dst[r * ldd + d0 + c] = src[r * lds + c0 + c];
-}
 
 __global__ void transpose_kernel(const float* src, int rows, int cols, float* dst) {
   __shared__ float tile[32][33];
@@ -445,21 +427,6 @@ void launch_zp(const float* stats, const float* noise, float* zp, float scale, i
   zp_kernel<<<nblk((long long)rows * 192, 256), 256, 0, s>>>(stats, noise, zp, scale, rows);
   GENIE_LAUNCHED("zp");
 }
-void launch_add_inplace(float* y, const float* x, long long n, cudaStream_t s) {
-  if (n <= 0) return;
-  add_inplace_kernel<<<nblk(n, 256), 256, 0, s>>>(y, x, n);
-  GENIE_LAUNCHED("add_inplace");
-}
-void launch_scale_inplace(float* y, float a, long long n, cudaStream_t s) {
-  if (n <= 0) return;
-  scale_inplace_kernel<<<nblk(n, 256), 256, 0, s>>>(y, a, n);
-  GENIE_LAUNCHED("scale_inplace");
-}
-void launch_fill(float* y, float a, long long n, cudaStream_t s) {
-  if (n <= 0) return;
-  fill_kernel<<<nblk(n, 256), 256, 0, s>>>(y, a, n);
-  GENIE_LAUNCHED("fill");
-}
 void launch_conv_post_tanh(const float* x, int C, const float* w, float* audio, const int* off, int B, int maxT,
                            cudaStream_t s) {
   if (B <= 0 || maxT <= 0) return;
@@ -496,11 +463,6 @@ void launch_row_sqnorm(const float* x, int ld, int C, int rows, float* out, cuda
   if (rows <= 0) return;
   row_sqnorm_kernel<<<nblk(rows, 8), 256, 0, s>>>(x, ld, C, rows, out);
   GENIE_LAUNCHED("row_sqnorm");
-}
-void launch_copy_cols(const float* src, int lds, int c0, float* dst, int ldd, int d0, int C, int rows, cudaStream_t s) {
-  if (rows <= 0) return;
-  copy_cols_kernel<<<nblk((long long)rows * C, 256), 256, 0, s>>>(src, lds, c0, dst, ldd, d0, C, rows);
-  GENIE_LAUNCHED("copy_cols");
 }
 void launch_transpose(const float* src, int rows, int cols, float* dst, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return;

@@ -4,9 +4,6 @@
 
 namespace genie {
 
-void launch_decode_attention_raw(const float* q, float* o, const float* kv_base, long long utt_stride,
-                                 long long layer_off, long long v_off, const int* kv_len, const int* active,
-                                 int B, int cap, float scale, int t_add, int ldq, cudaStream_t s);
 
 // QKV split-K partials [nsplit][B][1536] (+ bias) -> q, append k/v at kv_len[b], attend over kv_len[b] + 1 tokens
 void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
@@ -45,9 +42,6 @@ struct SmallGemm {
   float* y = nullptr; int ldy = 0; long long split_stride = 0;
 };
 void launch_tc_small_gemm(const SmallGemm& p, int nt, int* err_flag, cudaStream_t s);
-void launch_qkv_finish(const float* part, int nsplit, long long split_stride, const float* bias, float* q,
-                       float* kv_base, long long utt_stride, long long layer_off, long long v_off, int cap,
-                       const int* kv_len, const int* active, int B, cudaStream_t s);
 
 // ---- persistent decode step for batch <= 8 (t2s_persistent.cu)
 struct StepLayerPtrs {
@@ -101,9 +95,6 @@ void launch_flip_channels(const float* x, float* y, int C, int rows, cudaStream_
 void launch_sub_cols(float* z, int ldz, int col0, const float* m, int ldm, int C, int rows, cudaStream_t s);
 // zp = m + noise * exp(logs) * scale ; stats [rows, 384] = (m | logs); noise may be null (zeros)
 void launch_zp(const float* stats, const float* noise, float* zp, float scale, int rows, cudaStream_t s);
-void launch_add_inplace(float* y, const float* x, long long n, cudaStream_t s);
-void launch_scale_inplace(float* y, float a, long long n, cudaStream_t s);
-void launch_fill(float* y, float a, long long n, cudaStream_t s);
 // audio[t] = tanh( sum_{j<7,c<C} lrelu(x[t+j-3, c], 0.01) * w[j*C+c] )   per segment
 void launch_conv_post_tanh(const float* x, int C, const float* w, float* audio, const int* off, int B, int maxT,
                            cudaStream_t s);
@@ -117,8 +108,6 @@ void launch_prelu_add(float* ge, const float* add, const float* slope, int C, cu
 void launch_vq_argmax(const float* x, int ldx, const float* xe2, const float* e2, int rows, long long* codes,
                       cudaStream_t s);
 void launch_row_sqnorm(const float* x, int ld, int C, int rows, float* out, cudaStream_t s);
-// copy strided columns:  dst[r, :C] = src[r, c0:c0+C]
-void launch_copy_cols(const float* src, int lds, int c0, float* dst, int ldd, int d0, int C, int rows, cudaStream_t s);
 void launch_transpose(const float* src, int rows, int cols, float* dst, cudaStream_t s);   // dst[c, r] = src[r, c]
 
 }  // namespace genie

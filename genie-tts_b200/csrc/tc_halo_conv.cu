@@ -37,7 +37,7 @@ struct HaloGeom {
   uint32_t slab_bytes = 0;
   int U = 1, NU = 1, NI = 1;  // units (tap, slab) per ring slot / total / ring iterations
   uint32_t slot_bytes = 0;
-  int flags = 0;              // debug: 1 force wide layers onto this path, 2 skip halo load, 4 skip MMAs, 8 skip epilogue stores, 16 skip weight loads
+  int flags = 0;              // GENIE_TC_HALO bit 0: force wide layers onto the cp.async kernel (testing)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,7 +131,6 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   const __half* __restrict__ whi = p.tc_w;
   // ---- weight ring: iteration `it` = units [it*U, it*U + nu) into slot it % NSLOT
   auto load_w = [&](int it) {
-    if (g.flags & 16) return;
     const int u0 = it * g.U;
     const int nu = min(g.U, g.NU - u0);
     const uint32_t dst = sW + (uint32_t)(it % NSLOT) * g.slot_bytes;
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   }
 
   // ---- activation halo tile: each input element is loaded, activated, rounded and stored once
-  if (!(g.flags & 2)) {
+  {
     const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
     const float pre = p.pre_slope;                  // 0 <= pre <= 1: lrelu(v) == max(v, v * pre)
     const int cq = g.cpad >> 2;                     // float4 per staged row (channels >= Cin are zero padding)
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
       const int u0 = it * g.U;
       const int nu = min(g.U, g.NU - u0);
       const uint32_t wslot = sW + (uint32_t)(it % NSLOT) * g.slot_bytes;
-      for (int ul = 0; ul < ((g.flags & 4) ? 0 : nu); ++ul) {
+      for (int ul = 0; ul < nu; ++ul) {
         const int u = u0 + ul;
         const int tap = u / g.slabs, sl = u - tap * g.slabs;
         const int shift = p.in_shift0 + tap * p.in_shift_step - g.lo;
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
   const int rq = (warp & 3) * 32;
   const int ncc = (n_mma + 31) >> 5;                // column chunks per accumulator
-  if (ok && !(g.flags & 8)) {
+  if (ok) {
     for (int chunk = warp >> 2; chunk < MT * ncc; chunk += 2) {
       const int mt = chunk / ncc, c0 = (chunk - mt * ncc) * 32;
       if (q0 + mt * 128 >= nq) break;
@@ -532,7 +531,7 @@ bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
 
 int g_halo_bulk_max_cin = []() { const char* e = getenv("GENIE_HALO_BULK_MAX_CIN"); return e ? atoi(e) : 128; }();
 
-// GENIE_TC_HALO: -1 disables the path, > 0 = debug flags (HaloGeom::flags); default 0 = on
+// GENIE_TC_HALO: -1 disables the path, 1 forces wide layers onto the cp.async kernel; default 0 = on
 int halo_mode() {
   static int mode = [] {
     const char* e = getenv("GENIE_TC_HALO");

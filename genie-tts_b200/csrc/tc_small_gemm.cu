@@ -5,7 +5,7 @@
 // store), one barrier, 32 back-to-back MMAs (x_hi and x_lo against the fp16-exact weights), one
 // commit: the latency chain is launch -> loads -> MMA -> read-out instead of 8 dependent k-blocks.
 // Outputs are raw split-K partials; the consumers sum them and apply bias / residual / activation:
-// LayerNorm (elementwise.cu), qkv_finish (below) or this kernel's own A-operand loader (FFN2 reads
+// LayerNorm (elementwise.cu), the fused decode attention (attention.cu) or this kernel's own A-operand loader (FFN2 reads
 // relu(sum FFN1 partials + bias)).
 #include "kernels.cuh"
 
@@ -216,35 +216,6 @@ __global__ void __launch_bounds__(THR) tc_small_gemm_kernel(SmallGemm p, int* er
   }
 }
 
-// q[b,:] = sum partials + bias ; K/V rows -> head-major cache at position kv_len[b]
-__global__ void qkv_finish_kernel(const float* __restrict__ part, int nsplit, long long split_stride,
-                                  const float* __restrict__ bias, float* __restrict__ q,
-                                  float* __restrict__ kv_base, long long utt_stride, long long layer_off,
-                                  long long v_off, int cap, const int* __restrict__ kv_len,
-                                  const int* __restrict__ active, int B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // float4 index over B x 1536 / 4
-  if (i >= B * 384) return;
-  const int b = i / 384, c = (i % 384) * 4;
-  if (active && !active[b]) return;
-  const float* src = part + (long long)b * 1536 + c;
-  float4 v = *reinterpret_cast<const float4*>(src);
-  for (int sp = 1; sp < nsplit; ++sp) {
-    const float4 t = *reinterpret_cast<const float4*>(src + sp * split_stride);
-    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  }
-  const float4 bb = *reinterpret_cast<const float4*>(bias + c);
-  v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-  if (c < 512) {
-    *reinterpret_cast<float4*>(q + (long long)b * 512 + c) = v;
-  } else {
-    const int isv = c >= 1024, col = c - (isv ? 1024 : 512);
-    const int h = col >> 5, e = col & 31;
-    float* dst = kv_base + (long long)b * utt_stride + layer_off + (isv ? v_off : 0) +
-                 ((long long)h * cap + kv_len[b]) * 32 + e;
-    *reinterpret_cast<float4*>(dst) = v;
-  }
-}
-
 template <int NT, int THR>
 void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
   constexpr size_t smem = 2 * NKB * (THR == 256 ? 8192 : 16384) + (size_t)NKB * NT * 128 + 1024;
@@ -266,13 +237,5 @@ void launch_tc_small_gemm(const SmallGemm& p, int nt, int* err_flag, cudaStream_
   else launch_nt<32, 512>(p, err_flag, s);
 }
 
-void launch_qkv_finish(const float* part, int nsplit, long long split_stride, const float* bias, float* q,
-                       float* kv_base, long long utt_stride, long long layer_off, long long v_off, int cap,
-                       const int* kv_len, const int* active, int B, cudaStream_t s) {
-  if (B <= 0) return;
-  qkv_finish_kernel<<<(B * 384 + 255) / 256, 256, 0, s>>>(part, nsplit, split_stride, bias, q, kv_base, utt_stride,
-                                                        layer_off, v_off, cap, kv_len, active, B);
-  GENIE_LAUNCHED("qkv_finish");
-}
 
 }  // namespace genie
