@@ -198,23 +198,57 @@ void genie_prompt_destroy(genie_prompt* p) {
   delete p;
 }
 
+namespace {
+SamplingCfg sampling_cfg(const Model& m, const genie_sampling* sp) {
+  SamplingCfg cfg;
+  cfg.top_k = (sp && sp->top_k > 0) ? sp->top_k : m.top_k;
+  cfg.temperature = (sp && sp->temperature > 0.f) ? sp->temperature : m.temperature;
+  cfg.penalty = (sp && sp->repetition_penalty > 0.f) ? sp->repetition_penalty : m.penalty;
+  cfg.greedy = sp ? sp->greedy : 0;
+  cfg.seed = sp ? sp->seed : 0;
+  cfg.max_steps = (sp && sp->max_steps > 0) ? sp->max_steps : 500;
+  cfg.fixed_steps = sp ? sp->fixed_steps : 0;
+  return cfg;
+}
+}  // namespace
+
 int genie_t2s_generate(genie_model* h, genie_prompt* const* prompts, int B, const int64_t* text_seq,
                        const int* text_len, const float* text_bert, const genie_sampling* sp,
                        const volatile int* cancel, int io_on_device, int64_t* y, int y_ld, int* y_len, int* idx) {
   return guarded([&] {
     GENIE_CHECK(h && prompts && text_seq && text_len, "null argument");
     Model& m = h->m;
-    SamplingCfg cfg;
-    cfg.top_k = (sp && sp->top_k > 0) ? sp->top_k : m.top_k;
-    cfg.temperature = (sp && sp->temperature > 0.f) ? sp->temperature : m.temperature;
-    cfg.penalty = (sp && sp->repetition_penalty > 0.f) ? sp->repetition_penalty : m.penalty;
-    cfg.greedy = sp ? sp->greedy : 0;
-    cfg.seed = sp ? sp->seed : 0;
-    cfg.max_steps = (sp && sp->max_steps > 0) ? sp->max_steps : 500;
-    cfg.fixed_steps = sp ? sp->fixed_steps : 0;
     std::vector<Prompt*> ps(B);
     for (int b = 0; b < B; ++b) { GENIE_CHECK(prompts[b], "null prompt"); ps[b] = &prompts[b]->p; }
-    return t2s_generate(m, ps.data(), B, text_seq, text_len, text_bert, cfg, cancel, io_on_device, y, y_ld, y_len, idx);
+    return t2s_generate(m, ps.data(), B, text_seq, text_len, text_bert, sampling_cfg(m, sp), cancel, io_on_device, y,
+                        y_ld, y_len, idx);
+  });
+}
+
+int genie_t2s_prefill(genie_model* h, genie_prompt* const* prompts, int B, const int64_t* text_seq,
+                      const int* text_len, const float* text_bert, const genie_sampling* sp, int io_on_device) {
+  return guarded([&] {
+    GENIE_CHECK(h && prompts && text_seq && text_len, "null argument");
+    Model& m = h->m;
+    std::vector<Prompt*> ps(B);
+    for (int b = 0; b < B; ++b) { GENIE_CHECK(prompts[b], "null prompt"); ps[b] = &prompts[b]->p; }
+    t2s_prefill(m, ps.data(), B, text_seq, text_len, text_bert, sampling_cfg(m, sp), io_on_device);
+    return 0;
+  });
+}
+
+int genie_t2s_decode_steps(genie_model* h, int n_steps, const volatile int* cancel, int* n_active, int* steps_done) {
+  return guarded([&] {
+    GENIE_CHECK(h && n_steps >= 0, "bad argument");
+    return t2s_decode_steps(h->m, n_steps, cancel, n_active, steps_done);
+  });
+}
+
+int genie_t2s_read(genie_model* h, int io_on_device, int64_t* y, int y_ld, int* y_len, int* idx) {
+  return guarded([&] {
+    GENIE_CHECK(h, "null argument");
+    t2s_read(h->m, io_on_device, y, y_ld, y_len, idx);
+    return 0;
   });
 }
 

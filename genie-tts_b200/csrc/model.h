@@ -137,6 +137,7 @@ struct Model {
   std::vector<float> logits_host;
   std::map<std::string, std::vector<float>> kept;
   float timing[12] = {0};      // [8] decode-attention us / launch, [9] its KV MB / launch (time_attention option)
+  std::shared_ptr<void> t2s_session;   // batch between t2s_prefill and t2s_read (t2s.cu)
   int time_attention = 0;      // > 0: after t2s_generate replay the fused decode attention this many times per layer
 
   ~Model();
@@ -165,6 +166,10 @@ void prompt_build(Model& m, Prompt& p, const int64_t* ref_seq, int Lr, const flo
                   const float* ref_audio, int n_audio, const float* sv_emb, const float* ge_in, int ge_dim,
                   const float* ge_adv_in);
 struct SamplingCfg { int top_k; float temperature, penalty; int greedy; unsigned long long seed; int max_steps, fixed_steps; };
+void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
+                 const float* text_bert, const SamplingCfg& cfg, int io_dev);
+int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_active, int* steps_done);
+void t2s_read(Model& m, int io_dev, int64_t* y, int y_ld, int* y_len, int* idx);
 int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
                  const float* text_bert, const SamplingCfg& cfg, const volatile int* cancel, int io_dev,
                  int64_t* y, int y_ld, int* y_len, int* idx);

@@ -40,6 +40,39 @@ struct StepBufs {
   int utt_base;   // first utterance of this branch within the batch
 };
 
+// State of one batch between genie_t2s_prefill and genie_t2s_read: everything the decode loop and the result
+// read-out need.  The buffers live in the model's workspace, so a model has one live session at a time.
+struct T2SSession {
+  Batch bt; SamplingCfg cfg{}; int B = 0, max_steps = 0;
+  float* LOGITS = nullptr; int* HIST = nullptr; long long* Y64 = nullptr;
+  int *d_histlen = nullptr, *d_kvlen = nullptr, *d_active = nullptr, *d_stop = nullptr;
+  StepBufs w{};
+  bool can_graph = false;
+  int steps_done = 0;
+  bool all_stopped = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;                       // prefill
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> decode_spans;  // one pair per decode_steps call
+  ~T2SSession() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (auto& e : decode_spans) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  }
+};
+
+T2SSession& session_of(Model& m) {
+  GENIE_CHECK(m.t2s_session != nullptr, "no T2S batch in flight: call genie_t2s_prefill first");
+  return *static_cast<T2SSession*>(m.t2s_session.get());
+}
+
+void record_step_logits(Model& m, const T2SSession& S) {
+  if (!m.record_logits) return;
+  std::vector<float>& rec = m.logits_host;
+  const size_t o = rec.size();
+  rec.resize(o + (size_t)S.B * V);
+  GENIE_CUDA(cudaMemcpyAsync(rec.data() + o, S.LOGITS, (size_t)S.B * V * 4, cudaMemcpyDeviceToHost, m.stream));
+  GENIE_CUDA(cudaStreamSynchronize(m.stream));
+}
+
 // pointer table / barrier words of the persistent step (allocated outside any stream capture)
 void ensure_persistent_step(Model& m) {
   if (!m.step_layers_dev) {
@@ -151,18 +184,23 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
 
 }  // namespace
 
-int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len_in,
-                 const float* text_bert, const SamplingCfg& cfg, const volatile int* cancel, int io_dev,
-                 int64_t* y_out, int y_ld, int* y_len_out, int* idx_out) {
+// encoder + first-stage graph for a batch: embeddings, 24 prefill layers into the KV cache, first sampled token;
+// leaves the decode-step buffers and graph ready (Inference.py:76-93)
+void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len_in,
+                 const float* text_bert, const SamplingCfg& cfg, int io_dev) {
   GENIE_CHECK(m.finalized, "model not finalized");
   GENIE_CHECK(B > 0, "empty batch");
   cudaStream_t s = m.stream;
   GENIE_CUDA(cudaSetDevice(m.device));
   const int max_steps = cfg.fixed_steps > 0 ? cfg.fixed_steps : cfg.max_steps;
+  m.t2s_session.reset();
+  std::shared_ptr<T2SSession> sess_ptr = std::make_shared<T2SSession>();
+  T2SSession& S = *sess_ptr;
+  S.cfg = cfg; S.B = B; S.max_steps = max_steps;
 
   // ---- text lengths (device-resident payload: lengths are still host metadata)
   std::vector<int> text_len(text_len_in, text_len_in + B);
-  Batch bt; bt.B = B;
+  Batch& bt = S.bt; bt.B = B;
   bt.row_off.push_back(0); bt.txt_off.push_back(0);
   bool any_bert = text_bert != nullptr;
   for (int b = 0; b < B; ++b) {
@@ -180,7 +218,6 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   bt.cap = ((bt.maxS + max_steps + 1 + 15) / 16) * 16;
   int maxLy = *std::max_element(bt.Ly.begin(), bt.Ly.end());
   bt.hist_ld = maxLy + max_steps + 2;
-  GENIE_CHECK(y_ld >= bt.hist_ld || y_out == nullptr, "y_ld too small: need >= " + std::to_string(bt.hist_ld));
 
   Workspace& ws = m.ws;
   const int R = bt.rows;
@@ -235,8 +272,8 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   int* d_stop = d_active + (B + 1); int* d_ly = d_stop + (B + 1);
   int* d_txt_pos = d_ly + (B + 1); int* d_row2utt = d_txt_pos + bt.txt_rows; int* d_aud_pos = d_row2utt + R;
 
-  cudaEvent_t ev0, ev1, ev2;
-  GENIE_CUDA(cudaEventCreate(&ev0)); GENIE_CUDA(cudaEventCreate(&ev1)); GENIE_CUDA(cudaEventCreate(&ev2));
+  GENIE_CUDA(cudaEventCreate(&S.ev0)); GENIE_CUDA(cudaEventCreate(&S.ev1));
+  cudaEvent_t ev0 = S.ev0, ev1 = S.ev1;
   GENIE_CUDA(cudaEventRecord(ev0, s));
 
   // ---- K1: x = Emb_text[ref||text] + bert_proj(bert) + alpha*PE(1..Lx)   (t2s_encoder#[49-83])
@@ -317,16 +354,10 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
     launch_gather_rows(LAST, D, X, D, LASTIDX, B, 1, s);
     run_linear(m, m.predict, LAST, D, LOGITS, V, B);
   }
-  std::vector<float>& rec = m.logits_host;
-  rec.clear();
-  auto record = [&]() {
-    if (!m.record_logits) return;
-    size_t o = rec.size();
-    rec.resize(o + (size_t)B * V);
-    GENIE_CUDA(cudaMemcpyAsync(rec.data() + o, LOGITS, (size_t)B * V * 4, cudaMemcpyDeviceToHost, s));
-    GENIE_CUDA(cudaStreamSynchronize(s));
-  };
-  record();
+  S.LOGITS = LOGITS; S.HIST = HIST; S.Y64 = Y64;
+  S.d_histlen = d_histlen; S.d_kvlen = d_kvlen; S.d_active = d_active; S.d_stop = d_stop;
+  m.logits_host.clear();
+  record_step_logits(m, S);
   {
     SamplerArgs a{};
     a.logits = LOGITS; a.ld = V; a.hist = HIST; a.hist_ld = bt.hist_ld; a.hist_len = d_histlen; a.kv_len = d_kvlen;
@@ -337,8 +368,9 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   }
   GENIE_CUDA(cudaEventRecord(ev1, s));
 
-  // ---- decode loop (Inference.py:95-106)
-  StepBufs w{};
+  // ---- decode-step buffers and graph (Inference.py:95-106 runs in t2s_decode_steps)
+  StepBufs& w = S.w;
+  w = StepBufs{};
   w.h = ws.get<float>("t2s.step.h", (size_t)B * D); w.qkv = ws.get<float>("t2s.step.qkv", (size_t)B * 3 * D);
   w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
   w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
@@ -355,6 +387,7 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (m.use_tc ? 4 : 0) | (cfg.top_k << 4) |
                     (m.tc_min_rows << 16);
   const bool can_graph = m.use_graph && !m.record_logits && !g_sync_debug;
+  S.can_graph = can_graph;
   if (can_graph) {
     bool stale = !m.step_graph || m.step_graph_B != B || m.step_graph_gen != ws.generation ||
                  m.step_graph_cap != bt.cap || m.step_graph_flags != flags || m.step_graph_hist_ld != bt.hist_ld;
@@ -414,40 +447,79 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       m.step_graph_seed = cfg.seed; m.step_graph_temp = cfg.temperature; m.step_graph_pen = cfg.penalty;
     }
   }
-  const unsigned long long per_step_launches = m.step_graph_launches;
+  m.t2s_session = sess_ptr;
+}
+
+// up to n_steps more decode steps for the batch in flight (stage graph + sampler per step, Inference.py:95-106);
+// returns GENIE_CANCELLED (2) when the host flag fired, 0 otherwise
+int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_active_out, int* steps_done_out) {
+  T2SSession& S = session_of(m);
+  cudaStream_t s = m.stream;
+  GENIE_CUDA(cudaSetDevice(m.device));
+  const int B = S.B;
+  const SamplingCfg& cfg = S.cfg;
   int rc = 0;
   std::vector<int> h_act(B, 1);
-  int steps_done = 0;
   const int poll_every = 8;
-  for (int step = 0; step < max_steps; ++step) {
+  cudaEvent_t ea, eb;
+  GENIE_CUDA(cudaEventCreate(&ea)); GENIE_CUDA(cudaEventCreate(&eb));
+  S.decode_spans.emplace_back(ea, eb);
+  GENIE_CUDA(cudaEventRecord(ea, s));
+  for (int k = 0; k < n_steps && S.steps_done < S.max_steps && !S.all_stopped; ++k) {
     if (cancel && *cancel) { rc = 2 /* GENIE_CANCELLED */; break; }
-    if (can_graph) {
+    if (S.can_graph) {
       GENIE_CUDA(cudaGraphLaunch(m.step_graph, s));
-      g_launches += per_step_launches;
+      g_launches += m.step_graph_launches;
     } else {
-      decode_step(m, w, B, cfg);
+      decode_step(m, S.w, B, cfg);
     }
-    ++steps_done;
-    record();
-    if (cfg.fixed_steps <= 0 && ((step + 1) % poll_every == 0 || m.record_logits)) {
-      GENIE_CUDA(cudaMemcpyAsync(h_act.data(), d_active, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+    ++S.steps_done;
+    record_step_logits(m, S);
+    if (cfg.fixed_steps <= 0 && (S.steps_done % poll_every == 0 || m.record_logits)) {
+      GENIE_CUDA(cudaMemcpyAsync(h_act.data(), S.d_active, B * sizeof(int), cudaMemcpyDeviceToHost, s));
       GENIE_CUDA(cudaStreamSynchronize(s));
       bool any = false;
       for (int b = 0; b < B; ++b) any = any || h_act[b];
-      if (!any) break;
+      if (!any) S.all_stopped = true;
     }
   }
-  GENIE_CUDA(cudaEventRecord(ev2, s));
+  GENIE_CUDA(cudaEventRecord(eb, s));
+  if (n_active_out) {
+    int n = 0;
+    if (cfg.fixed_steps > 0) n = S.steps_done < S.max_steps ? B : 0;
+    else if (!S.all_stopped && S.steps_done < S.max_steps) {
+      GENIE_CUDA(cudaMemcpyAsync(h_act.data(), S.d_active, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+      GENIE_CUDA(cudaStreamSynchronize(s));
+      for (int b = 0; b < B; ++b) n += h_act[b] ? 1 : 0;
+      if (n == 0) S.all_stopped = true;
+    }
+    *n_active_out = n;
+  }
+  if (steps_done_out) *steps_done_out = S.steps_done;
+  return rc;
+}
+
+// tokens generated so far (prompt tokens + generated, per utterance) and the reference's loop index
+void t2s_read(Model& m, int io_dev, int64_t* y_out, int y_ld, int* y_len_out, int* idx_out) {
+  T2SSession& S = session_of(m);
+  cudaStream_t s = m.stream;
+  GENIE_CUDA(cudaSetDevice(m.device));
+  const int B = S.B;
+  const Batch& bt = S.bt;
+  const SamplingCfg& cfg = S.cfg;
+  const StepBufs& w = S.w;
+  const int steps_done = S.steps_done;
+  GENIE_CHECK(y_ld >= bt.hist_ld || y_out == nullptr, "y_ld too small: need >= " + std::to_string(bt.hist_ld));
 
   // ---- results
   std::vector<int> h_len(B), h_stopv(B), h_kvlen_final(B);
-  GENIE_CUDA(cudaMemcpyAsync(h_len.data(), d_histlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-  GENIE_CUDA(cudaMemcpyAsync(h_kvlen_final.data(), d_kvlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
-  GENIE_CUDA(cudaMemcpyAsync(h_stopv.data(), d_stop, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  GENIE_CUDA(cudaMemcpyAsync(h_len.data(), S.d_histlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  GENIE_CUDA(cudaMemcpyAsync(h_kvlen_final.data(), S.d_kvlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  GENIE_CUDA(cudaMemcpyAsync(h_stopv.data(), S.d_stop, B * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (y_out) {
-    hist_to_i64_kernel<<<B, 256, 0, s>>>(HIST, bt.hist_ld, d_histlen, Y64, bt.hist_ld, B);
+    hist_to_i64_kernel<<<B, 256, 0, s>>>(S.HIST, bt.hist_ld, S.d_histlen, S.Y64, bt.hist_ld, B);
     GENIE_LAUNCHED("hist_to_i64");
-    GENIE_CUDA(cudaMemcpy2DAsync(y_out, (size_t)y_ld * 8, Y64, (size_t)bt.hist_ld * 8, (size_t)bt.hist_ld * 8, B,
+    GENIE_CUDA(cudaMemcpy2DAsync(y_out, (size_t)y_ld * 8, S.Y64, (size_t)bt.hist_ld * 8, (size_t)bt.hist_ld * 8, B,
                                  io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   }
   GENIE_CUDA(cudaStreamSynchronize(s));
@@ -490,9 +562,23 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
     cudaEventDestroy(ea); cudaEventDestroy(eb);
   }
   float t01 = 0, t12 = 0;
-  cudaEventElapsedTime(&t01, ev0, ev1); cudaEventElapsedTime(&t12, ev1, ev2);
+  cudaEventElapsedTime(&t01, S.ev0, S.ev1);
+  for (auto& e : S.decode_spans) {
+    float t = 0;
+    cudaEventElapsedTime(&t, e.first, e.second);
+    t12 += t;
+  }
   m.timing[0] = t01; m.timing[1] = t12; m.timing[2] = t01 + t12; m.timing[3] = (float)steps_done;
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+}
+
+// Inference.py:63-106 in one call: prefill, decode to the stop condition / budget, read the tokens
+int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
+                 const float* text_bert, const SamplingCfg& cfg, const volatile int* cancel, int io_dev,
+                 int64_t* y_out, int y_ld, int* y_len_out, int* idx_out) {
+  t2s_prefill(m, prompts, B, text_seq, text_len, text_bert, cfg, io_dev);
+  const int max_steps = cfg.fixed_steps > 0 ? cfg.fixed_steps : cfg.max_steps;
+  const int rc = t2s_decode_steps(m, max_steps, cancel, nullptr, nullptr);
+  t2s_read(m, io_dev, y_out, y_ld, y_len_out, idx_out);
   return rc;
 }
 

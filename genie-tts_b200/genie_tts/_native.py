@@ -50,6 +50,9 @@ SIGNATURES = {
     "genie_prompt_destroy": (None, [_P]),
     "genie_t2s_generate": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P, _P, _P, C.POINTER(Sampling), _P, C.c_int,
                                      _P, C.c_int, _P, _P]),
+    "genie_t2s_prefill": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P, _P, _P, C.POINTER(Sampling), C.c_int]),
+    "genie_t2s_decode_steps": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "genie_t2s_read": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "genie_vits_decode": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_ulonglong, C.c_float,
                                     C.c_int, _P, _P]),
     "genie_debug_record_logits": (C.c_int, [_P, C.c_int]),

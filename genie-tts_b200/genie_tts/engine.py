@@ -195,6 +195,45 @@ class B200Model:
         N.check(rc)
         return [y[b, :y_len[b]].copy() for b in range(B)], [int(i) for i in idx]
 
+    # -- T2S in pieces: prefill / decode_steps / read (streaming, polling between chunks of steps) --------
+    def t2s_prefill(self, prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
+                    text_berts: Optional[Sequence[Optional[np.ndarray]]] = None,
+                    sampling: Optional[SamplingParams] = None) -> None:
+        """Encoder + first-stage pass for the batch; it stays in flight inside the model until the next prefill."""
+        sp = sampling or SamplingParams()
+        B = len(prompts)
+        seqs = [_i64(t) for t in text_seqs]
+        lens = np.asarray([len(t) for t in seqs], dtype=np.int32)
+        cat = np.concatenate(seqs)
+        bert = None
+        if text_berts is not None and any(b is not None and np.any(b) for b in text_berts):
+            bert = np.concatenate([_f32(b) if b is not None else np.zeros((len(s), 1024), np.float32)
+                                   for b, s in zip(text_berts, seqs)], axis=0)
+        steps = sp.fixed_steps if sp.fixed_steps > 0 else (sp.max_steps if sp.max_steps > 0 else 500)
+        self._inflight = (B, max(p.n_prompt_tokens for p in prompts) + steps + 2)
+        hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        csp = sp.to_c()
+        N.check(N.lib().genie_t2s_prefill(self._h, hs, B, _ptr(cat), _ptr(lens), _ptr(bert), C.byref(csp), 0))
+
+    def t2s_decode_steps(self, n_steps: int, cancel_flag: Optional[C.c_int] = None) -> Tuple[int, int, bool]:
+        """Up to ``n_steps`` more decode steps; returns (utterances still decoding, steps so far, cancelled)."""
+        n_active, done = C.c_int(0), C.c_int(0)
+        rc = N.lib().genie_t2s_decode_steps(self._h, int(n_steps),
+                                            C.cast(C.pointer(cancel_flag), C.c_void_p) if cancel_flag is not None else None,
+                                            C.byref(n_active), C.byref(done))
+        if rc != N.CANCELLED:
+            N.check(rc)
+        return n_active.value, done.value, rc == N.CANCELLED
+
+    def t2s_read(self) -> Tuple[List[np.ndarray], List[int]]:
+        """(y_full per utterance, idx per utterance) for what the batch in flight has generated so far."""
+        B, y_ld = self._inflight
+        y = np.zeros((B, y_ld), dtype=np.int64)
+        y_len = np.zeros(B, dtype=np.int32)
+        idx = np.zeros(B, dtype=np.int32)
+        N.check(N.lib().genie_t2s_read(self._h, 0, _ptr(y), y_ld, _ptr(y_len), _ptr(idx)))
+        return [y[b, :y_len[b]].copy() for b in range(B)], [int(i) for i in idx]
+
     # -- SoVITS -----------------------------------------------------------------
     def vits_decode(self, prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
                     semantic: Sequence[np.ndarray], zp_noise: Optional[Sequence[np.ndarray]] = None,

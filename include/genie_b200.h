@@ -106,6 +106,19 @@ int genie_t2s_generate(genie_model* m, genie_prompt* const* prompts, int B, cons
                        const int* text_len, const float* text_bert, const genie_sampling* sampling,
                        const volatile int* cancel, int io_on_device, int64_t* y, int y_ld, int* y_len, int* idx);
 
+/* The same work in three calls (t2s_prefill / t2s_decode_steps), for callers that stream tokens, poll
+ * between chunks of steps or interleave other work: prefill = encoder.run + first_stage_decoder.run
+ * (Inference.py:76-93) for the batch, leaving it "in flight" inside the model (one batch in flight per model: the
+ * KV cache and step buffers are the model's workspace); decode_steps = up to n_steps iterations of the
+ * stage-decoder loop (Inference.py:95-106), stopping early when every utterance has stopped or the sampling's
+ * max_steps / fixed_steps budget is used (n_active = utterances still decoding, steps_done = loop iterations so
+ * far; GENIE_CANCELLED when the host flag fired); read = y / y_len / idx as documented above for what has been
+ * generated so far.  genie_t2s_generate == prefill + decode_steps(budget) + read. */
+int genie_t2s_prefill(genie_model* m, genie_prompt* const* prompts, int B, const int64_t* text_seq,
+                      const int* text_len, const float* text_bert, const genie_sampling* sampling, int io_on_device);
+int genie_t2s_decode_steps(genie_model* m, int n_steps, const volatile int* cancel, int* n_active, int* steps_done);
+int genie_t2s_read(genie_model* m, int io_on_device, int64_t* y, int y_ld, int* y_len, int* idx);
+
 /* ---- SoVITS: replaces vocoder.run (Inference.py:46-61) for a batch.
  * sem: int64 concat of semantic tokens (sum sem_len, every id < 1024);
  * zp_noise: f32 concat per utterance of [192, 2*sem_len[b]] (the graph's RandomNormalLike

@@ -377,3 +377,39 @@ def test_split_branch_decode_matches_unsplit(v2):
     finally:
         m.set_option("decode_split_min", 64)
         prompt.close()
+
+
+@pytest.mark.gpu
+def test_prefill_decode_steps_read_equals_generate(v2):
+    """genie_t2s_prefill + chunks of genie_t2s_decode_steps + genie_t2s_read reproduce genie_t2s_generate exactly
+    (greedy with natural stop, and seeded sampling with a fixed budget), report progress, and honour the cancel flag."""
+    import ctypes as C
+    from genie_tts.engine import SamplingParams
+    m, _ = v2
+    pr = make_prompt_inputs(seed=900, Lr=16, Ts=48, n_audio=32000)
+    prompt = _prompt(m, pr)
+    try:
+        for B, sp in ((3, SamplingParams(greedy=True, max_steps=21)), (12, SamplingParams(seed=4, max_steps=17, fixed_steps=17))):
+            txs = [make_text_inputs(seed=910 + i, Lt=9 + i) for i in range(B)]
+            seqs = [t["text_seq"] for t in txs]
+            ys_ref, idx_ref = m.t2s_generate([prompt] * B, seqs, None, sp)
+            m.t2s_prefill([prompt] * B, seqs, None, sp)
+            y0, _ = m.t2s_read()                                       # after prefill: prompt + the first token
+            assert all(len(a) == prompt.n_prompt_tokens + 1 for a in y0)
+            seen, n_active = 0, B
+            while n_active > 0:
+                n_active, done, cancelled = m.t2s_decode_steps(5)
+                assert not cancelled and done >= seen and done - seen <= 5
+                seen = done
+                if seen > 200:
+                    break
+            ys, idx = m.t2s_read()
+            assert all(np.array_equal(a, b_) for a, b_ in zip(ys, ys_ref)) and idx == idx_ref
+            n_active, done2, _ = m.t2s_decode_steps(5)                 # budget used / all stopped: nothing more happens
+            assert done2 == seen and n_active == 0
+        flag = C.c_int(1)
+        m.t2s_prefill([prompt], [make_text_inputs(seed=930, Lt=10)["text_seq"]], None, SamplingParams(greedy=True, max_steps=9))
+        n_active, done, cancelled = m.t2s_decode_steps(9, cancel_flag=flag)
+        assert cancelled and done == 0
+    finally:
+        prompt.close()
