@@ -401,6 +401,7 @@ void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       GENIE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       try {
         int nb = (B >= m.decode_split_min && m.stream2) ? m.decode_branches : 1;
+        if (nb > 1 && (B + nb - 1) / nb > 128) nb = (B + 127) / 128;   // keep every branch on the <= 128-row GEMM
         if (nb > 4) nb = 4;
         while (nb > 1 && B / nb < 16) --nb;              // every branch stays on the tensor-core path
         if (nb > 1) {

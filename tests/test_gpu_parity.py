@@ -368,6 +368,12 @@ def test_split_branch_decode_matches_unsplit(v2):
             m.set_option("decode_split_min", 1 << 30)
             ys_one, idx_one = m.t2s_generate([prompt] * B, seqs, None, sp)              # graph, 1 branch
             assert all(np.array_equal(a, b_) for a, b_ in zip(ys_split, ys_one)) and idx_split == idx_one
+        # config-4 sized batch: 300 utterances -> 3 branches of 100 rows each on the <= 128-row GEMM
+        big = [seqs[i % B] for i in range(300)]
+        sp = SamplingParams(greedy=True, max_steps=4)
+        ys_big, idx_big = m.t2s_generate([prompt] * 300, big, None, sp)
+        for b in (0, 99, 100, 199, 200, 299):
+            assert np.array_equal(ys_big[b], ys_big[b % B]) and idx_big[b] == idx_big[b % B]   # same sentence, any branch
         m.set_option("decode_split_min", 64)
         sp = SamplingParams(greedy=True, max_steps=8)
         ys, idx = m.t2s_generate([prompt] * B, seqs, None, sp)
