@@ -103,6 +103,9 @@ struct ConvGemm {
   const __half* tc_w = nullptr; const __half* tc_wlo = nullptr; int tc_kpad = 0; int tc_split_a = 0;
   int tc_nt = 0;                               // force the N tile (0 = by Cout)
   const __half* tc_tiles = nullptr;            // pre-tiled weights for tc_halo_bulk_kernel (wide k-tap convs)
+  // fp16 hand-over between the two convs of a resblock pair (tc_halo_conv only): the producer writes
+  // fp16(lrelu(out)) to y16 instead of fp32 y, the consumer reads x16 as its A operand as is (no pre-activation)
+  const __half* x16 = nullptr; __half* y16 = nullptr;
   // split-K: CTA (n-tile, ks) reduces k-blocks [ks*KB/ksplit, (ks+1)*KB/ksplit) and stores the raw partial
   // at y + ks*split_stride; bias / residual / activation are then applied by the consumer (layernorm)
   int ksplit = 1; long long split_stride = 0;
@@ -111,6 +114,7 @@ void launch_conv_gemm(const ConvGemm& p, cudaStream_t s);
 void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s);
 // k-tap convs with the activation halo staged once per CTA (tc_halo_conv.cu); false => not applicable
 bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s);
+bool tc_halo_fp16_pair_ok(int C, int ntaps);   // both convs of a C -> C pair take tc_halo_conv_kernel
 bool pretile_w128_supported(int Cin, int Cout, int ntaps);
 void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s);
 bool skinny_gemm_supported(const ConvGemm& p);

@@ -9,6 +9,7 @@
 // first version, one 4-byte load per lane and row, ran at ~1 TB/s and was 60% of the kernel).
 #pragma once
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace genie {
 namespace tc_epi {
@@ -22,6 +23,8 @@ struct Args {
   int act; float slope, oscale;                     // ACT_NONE or (leaky-)ReLU as max(x, x * slope)
   int Cout;
   bool vec;                                         // 16-byte path legal (alignment, Cout % 4 == 0)
+  __half* y16 = nullptr; int ldy16 = 0;             // fp16 output instead of y (no residual / accumulate): the
+                                                    // consumer conv reads it as its ready-made A operand
 };
 
 __device__ __forceinline__ bool vec_ok(const float* y, int ldy, const float* res, int ldr, int Cout) {
@@ -50,7 +53,24 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
     *reinterpret_cast<float4*>(tile + lane * TILE_LD + 4 * k) = o;
   }
   __syncwarp();
-  if (a.vec) {
+  if (a.y16) {
+    constexpr int CPR = CW / 4, RPP = 32 / CPR, NP = 32 / RPP;
+    const int rsub = lane / CPR, c4 = lane % CPR;
+    const int n = ncol0 + c4 * 4;
+    if (n < a.Cout) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int to = rows[i * RPP + rsub];
+        if (to < 0) continue;
+        const float4 t = *reinterpret_cast<const float4*>(tile + (i * RPP + rsub) * TILE_LD + c4 * 4);
+        const __half2 h01 = __floats2half2_rn(t.x, t.y), h23 = __floats2half2_rn(t.z, t.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(a.y16 + (out0 + to) * a.ldy16 + n) = pk;
+      }
+    }
+  } else if (a.vec) {
     constexpr int CPR = CW / 4;                     // lanes per row
     constexpr int RPP = 32 / CPR;                   // rows per pass
     constexpr int NP = 32 / RPP;                    // passes

@@ -337,6 +337,7 @@ void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   const int nq = p.M + p.q_extra;
   if (nq <= 0 || p.B <= 0) return;
   if (try_launch_tc_halo_conv(p, err_flag, s)) return;
+  GENIE_CHECK(!p.x16 && !p.y16, "tc_conv_gemm: fp16 hand-over is a tc_halo_conv feature");
   const bool wlo = p.tc_wlo != nullptr;
   if (p.tc_split_a) {
     if (wlo) dispatch_nt<2, 1>(p, err_flag, s); else dispatch_nt<2, 0>(p, err_flag, s);

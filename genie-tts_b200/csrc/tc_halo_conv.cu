@@ -157,7 +157,32 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   }
 
   // ---- activation halo tile: each input element is loaded, activated, rounded and stored once
-  {
+  if (p.x16) {
+    // ready-made operand rows (fp16, already activated): 16-byte copies into the swizzled tile
+    const __half* __restrict__ xh = p.x16 + (long long)in0 * p.Cin;
+    const int c8n = g.cpad >> 3;                    // 16-byte chunks per staged row
+    const int totalA = g.R * c8n;
+    const int tbase = q0 + g.lo;
+    for (int i0 = 0; i0 < totalA; i0 += NTHR * 8) {
+      uint4 v[8];
+      uint32_t so[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = i0 + k * NTHR + tid;
+        const int rr = idx / c8n, f = idx - rr * c8n;
+        const int t = tbase + rr;
+        const int c = f * 8;
+        const uint32_t off = (uint32_t)(rr * ROWB + (c & 63) * 2);
+        so[k] = idx < totalA ? (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & SWMASK) << 4)) : 0xffffffffu;
+        v[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (idx < totalA && c < p.Cin && (unsigned)t < (unsigned)Tin)
+          v[k] = __ldg(reinterpret_cast<const uint4*>(xh + (long long)t * p.Cin + c));
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (so[k] != 0xffffffffu) *reinterpret_cast<uint4*>(sbase + so[k]) = v[k];
+    }
+  } else {
     const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
     const float pre = p.pre_slope;                  // 0 <= pre <= 1: lrelu(v) == max(v, v * pre)
     const int cq = g.cpad >> 2;                     // float4 per staged row (channels >= Cin are zero padding)
@@ -251,6 +276,7 @@ __global__ void __launch_bounds__(NTHR, (ROWB < 128 ? 4 : NT <= 64 ? 3 : 2)) tc_
   ea.act = p.act; ea.slope = p.act == ACT_RELU ? 0.f : p.act_slope; ea.oscale = p.out_scale;
   ea.Cout = p.Cout;
   ea.vec = tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout);
+  ea.y16 = p.y16; ea.ldy16 = p.Cout;
   float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
   const int rq = (warp & 3) * 32;
   const int ncc = (n_mma + 31) >> 5;                // column chunks per accumulator
@@ -542,6 +568,12 @@ int halo_mode() {
 
 }  // namespace
 
+// a C -> C conv pair may hand its intermediate over in fp16 when both convs take tc_halo_conv_kernel
+bool tc_halo_fp16_pair_ok(int C, int ntaps) {
+  if (halo_mode() != 0 || ntaps < 2 || C % 8 != 0) return false;
+  return C == 16 || (C > 16 && C <= 64) || (C > 64 && C < 128);
+}
+
 // fp16 [Cout][kpad] -> pre-swizzled 128 x 64 tiles [Cout/128][tap][Cin/64] for tc_halo_bulk_kernel
 bool pretile_w128_supported(int Cin, int Cout, int ntaps) { return Cin % 64 == 0 && Cin >= 128 && Cout % BNT == 0 && ntaps >= 2; }
 void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s) {
@@ -553,7 +585,7 @@ void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntap
 // k-tap convs whose activation halo fits in shared memory; false => caller uses tc_conv_gemm
 bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   const int mode = halo_mode();
-  if (mode < 0) return false;
+  if (mode < 0) { GENIE_CHECK(!p.x16 && !p.y16, "fp16 hand-over needs the halo conv kernel"); return false; }
   if (p.ntaps < 2 || p.tc_wlo != nullptr || p.tc_split_a || p.ksplit != 1 || p.tc_nt != 0) return false;
   if (p.pre_slope < 0.f || p.pre_slope > 1.f) return false;
   if (p.act != ACT_NONE && p.act != ACT_RELU && p.act != ACT_LRELU) return false;

@@ -17,6 +17,7 @@ struct ConvOpt {
   int dil = 1; float pre_slope = 1.f; int act = ACT_NONE; float act_slope = 0.f;
   const float* res = nullptr; int ldr = 0; const float* bias2 = nullptr; int ldb2 = 0;
   int accumulate = 0; int co0 = 0; int con = -1; int cin0 = 0; int cin = -1;
+  const __half* x16 = nullptr; __half* y16 = nullptr;   // fp16 hand-over inside a resblock pair (tc_halo_conv only)
 };
 void run_conv(Model& m, const Conv& c, const float* x, int ldx, float* y, int ldy, const Seg& sg, const ConvOpt& o = {}) {
   ConvGemm p;
@@ -35,6 +36,7 @@ void run_conv(Model& m, const Conv& c, const float* x, int ldx, float* y, int ld
   if (m.use_tc && c.tc.hi && sg.off != nullptr && o.cin0 == 0 && cin == c.Cin) {
     p.tc_w = c.tc.hi + (long long)o.co0 * c.tc.kpad; p.tc_kpad = c.tc.kpad;
     if (o.co0 == 0 && p.Cout == c.Cout) p.tc_tiles = c.tc.tiles;
+    p.x16 = o.x16; p.y16 = o.y16;
     p.tc_wlo = m.tc_vits >= 3 ? c.tc.lo + (long long)o.co0 * c.tc.kpad : nullptr;
     p.tc_split_a = m.tc_vits >= 2;
     launch_tc_conv_gemm(p, m.tc_err, m.stream);
@@ -393,6 +395,7 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   const unsigned long long launches_before_gen = g_launches;
   float* UP = ws.get<float>("v.up", gen_floats);
   float* GA = ws.get<float>("v.ga", gen_floats);
+  __half* GA16 = ws.get<__half>("v.ga16", gen_floats);
   float* GB = ws.get<float>("v.gb", gen_floats);
   float* GC = ws.get<float>("v.gc", gen_floats);
   {
@@ -410,10 +413,15 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       const ResBlock& Rb = m.res[i * 3 + j];
       const float* r = UP;
       float* pp[2] = {GB, GC};
+      // narrow stages are HBM-bound: conv1 hands fp16(lrelu(out)) to conv2 (exactly what conv2's loader
+      // would have produced from the fp32 tensor), 2 + 2 instead of 4 + 4 bytes per element
+      const bool h16 = m.use_tc && m.tc_vits == 1 && S.off != nullptr && tc_halo_fp16_pair_ok(C, Rb.k);
       for (int c = 0; c < 3; ++c) {
         ConvOpt a; a.dil = dils[c]; a.pre_slope = 0.1f;
+        if (h16) { a.act = ACT_LRELU; a.act_slope = 0.1f; a.y16 = GA16; }
         run_conv(m, Rb.c1[c], r, C, GA, C, S, a);
-        ConvOpt b2; b2.pre_slope = 0.1f; b2.res = r; b2.ldr = C;
+        ConvOpt b2; b2.pre_slope = h16 ? 1.f : 0.1f; b2.res = r; b2.ldr = C;
+        if (h16) b2.x16 = GA16;
         if (c < 2) {
           run_conv(m, Rb.c2[c], GA, C, pp[c], C, S, b2);
           r = pp[c];
