@@ -429,7 +429,31 @@ __global__ void __launch_bounds__(BTHR, 2) tc_halo_bulk_kernel(ConvGemm p, HaloG
     }
   } else {
     // ===== loader / epilogue warps: halo tile once, then wait for the accumulator
-    {
+    if (p.x16) {
+      const __half* __restrict__ xh = p.x16 + (long long)in0 * p.Cin;
+      const int c8n = p.Cin >> 3;
+      const int totalA = g.R * c8n;
+      const int tbase = q0 + g.lo;
+      for (int i0 = 0; i0 < totalA; i0 += NTHR * 8) {
+        uint4 v[8];
+        uint32_t so[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = i0 + k * NTHR + tid;
+          const int rr = idx / c8n, f = idx - rr * c8n;
+          const int t = tbase + rr;
+          const int c = f * 8;
+          const uint32_t off = (uint32_t)(rr * 128 + (c & 63) * 2);
+          so[k] = idx < totalA ? (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4)) : 0xffffffffu;
+          v[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (idx < totalA && (unsigned)t < (unsigned)Tin)
+            v[k] = __ldg(reinterpret_cast<const uint4*>(xh + (long long)t * p.Cin + c));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (so[k] != 0xffffffffu) *reinterpret_cast<uint4*>(sbase + so[k]) = v[k];
+      }
+    } else {
       const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
       const float pre = p.pre_slope;
       const int cq = p.Cin >> 2;
@@ -477,6 +501,7 @@ __global__ void __launch_bounds__(BTHR, 2) tc_halo_bulk_kernel(ConvGemm p, HaloG
     ea.act = p.act; ea.slope = p.act == ACT_RELU ? 0.f : p.act_slope; ea.oscale = p.out_scale;
     ea.Cout = p.Cout;
     ea.vec = tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout);
+    ea.y16 = p.y16; ea.ldy16 = p.Cout;
     float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
     const int rq = (warp & 3) * 32;
     if (ok) {
@@ -571,7 +596,8 @@ int halo_mode() {
 // a C -> C conv pair may hand its intermediate over in fp16 when both convs take tc_halo_conv_kernel
 bool tc_halo_fp16_pair_ok(int C, int ntaps) {
   if (halo_mode() != 0 || ntaps < 2 || C % 8 != 0) return false;
-  return C == 16 || (C > 16 && C <= 64) || (C > 64 && C < 128);
+  if (C == 16 || (C > 16 && C <= 64) || (C > 64 && C < 128)) return true;
+  return C % 64 == 0 && C >= 128 && C <= g_halo_bulk_max_cin && C % BNT == 0;   // tc_halo_bulk_kernel
 }
 
 // fp16 [Cout][kpad] -> pre-swizzled 128 x 64 tiles [Cout/128][tap][Cin/64] for tc_halo_bulk_kernel
