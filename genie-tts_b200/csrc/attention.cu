@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) prefill_attention32_kernel(Attn p) {
 // ---------------------------------------------------------------------------
 // FUSED: q / k_new / v_new are still split-K partials of the QKV GEMM ([nsplit][B][1536], bias deferred):
 // the CTA finishes its own 3 x 32 columns, appends k_new / v_new to the cache at position kv_len[b] and
-// attends over the kv_len[b] cached tokens plus the new one (replaces qkv_finish + t_add = 1).
+// attends over the kv_len[b] cached tokens plus the new one (no separate finish / cache-scatter kernel).
 // Four tokens per thread group are loaded per round (8 independent 16-byte loads per thread in flight):
 // the per-CTA chain is ceil(T / 64) HBM round trips instead of ceil(T / 16).
 template <bool FUSED>
