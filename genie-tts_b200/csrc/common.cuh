@@ -106,6 +106,9 @@ struct ConvGemm {
   // fp16 hand-over between the two convs of a resblock pair (tc_halo_conv only): the producer writes
   // fp16(lrelu(out)) to y16 instead of fp32 y, the consumer reads x16 as its A operand as is (no pre-activation)
   const __half* x16 = nullptr; __half* y16 = nullptr;
+  // hi/lo-split form of the same hand-over for the (x_hi + x_lo) . w linears (tc_gemm.cu, ntaps == 1): the
+  // producer writes fp16(v) and fp16(v - fp16(v)), the consumer copies both parts into its operand tiles
+  const __half* x16_lo = nullptr; __half* y16_lo = nullptr;
   // split-K: CTA (n-tile, ks) reduces k-blocks [ks*KB/ksplit, (ks+1)*KB/ksplit) and stores the raw partial
   // at y + ks*split_stride; bias / residual / activation are then applied by the consumer (layernorm)
   int ksplit = 1; long long split_stride = 0;

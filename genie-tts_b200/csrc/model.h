@@ -178,8 +178,11 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
                  float noise_scale, int io_dev, float* audio, int* audio_len);
 
 // helpers shared by the stage files
+// fp16 hi/lo pair: v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (operand hand-over between linears)
+struct Half2Part { __half* hi; __half* lo; };
 void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, int ldy, int M, int act = ACT_NONE,
-                const float* res = nullptr, int ldr = 0, int nt = 0, int ksplit = 1, long long split_stride = 0);
+                const float* res = nullptr, int ldr = 0, int nt = 0, int ksplit = 1, long long split_stride = 0, const Half2Part* a16 = nullptr,
+                const Half2Part* y16 = nullptr);
 inline bool tc_linear_ok(const Model& m, const Linear& L, int M) { return m.use_tc && L.tc.hi && M >= m.tc_min_rows; }
 void keep_tensor(Model& m, const char* name, const float* dev, long long n);
 void check_tc_error(Model& m);

@@ -5,6 +5,7 @@
 #include "model.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace genie {
 namespace {
@@ -227,6 +228,11 @@ void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   float* TMP = ws.get<float>("t2s.tmp", (size_t)R * D);
   float* H1 = ws.get<float>("t2s.h1", (size_t)R * D);
   float* FF = ws.get<float>("t2s.ff", (size_t)R * 4 * D);
+  // the same bytes viewed as two fp16 matrices [R, 2048] (hi | lo) when the FFN pair hands over in fp16
+  __half* FF16 = reinterpret_cast<__half*>(FF);
+  static const bool ffn16_env = [] { const char* e = getenv("GENIE_FFN16"); return !(e && e[0] == '0'); }();
+  const bool ffn16 = ffn16_env && m.use_tc && R >= m.tc_min_rows && R > m.skinny_max_rows && m.layers[0].ff1.tc.hi &&
+                     m.layers[0].ff2.tc.hi && !m.layers[0].ff2.tc.lo;
   float* XT = ws.get<float>("t2s.xtext", (size_t)bt.txt_rows * D);
   float* BERT = any_bert ? ws.get<float>("t2s.bert", (size_t)bt.txt_rows * 1024) : nullptr;
   long long* SEQ = ws.get<long long>("t2s.seq", bt.txt_rows);
@@ -337,8 +343,17 @@ void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
     launch_attention(a, s);
     run_linear(m, L.out, ATT, D, TMP, D, R, ACT_NONE, Hcur, D);
     launch_layernorm(TMP, nullptr, L.ln1_g, L.ln1_b, H1, R, D, s);
-    run_linear(m, L.ff1, H1, D, FF, 4 * D, R, ACT_RELU);
-    run_linear(m, L.ff2, FF, 4 * D, TMP, D, R, ACT_NONE, H1, D);
+    if (ffn16) {
+      // FFN1 writes relu(.) straight as the fp16 hi / lo operand rows FFN2 needs (the values its loader would
+      // have derived from the fp32 tensor, so nothing changes numerically; same bytes, no conversion pass in
+      // FFN2, whose 2 N tiles used to convert every row twice)
+      Half2Part ffh{FF16, FF16 + (size_t)R * 4 * D};
+      run_linear(m, L.ff1, H1, D, FF, 4 * D, R, ACT_RELU, nullptr, 0, 0, 1, 0, nullptr, &ffh);
+      run_linear(m, L.ff2, FF, 4 * D, TMP, D, R, ACT_NONE, H1, D, 0, 1, 0, &ffh, nullptr);
+    } else {
+      run_linear(m, L.ff1, H1, D, FF, 4 * D, R, ACT_RELU);
+      run_linear(m, L.ff2, FF, 4 * D, TMP, D, R, ACT_NONE, H1, D);
+    }
     launch_layernorm(TMP, nullptr, L.ln2_g, L.ln2_b, X, R, D, s);
     Hcur = X;
     if (l == 0 && m.keep) {

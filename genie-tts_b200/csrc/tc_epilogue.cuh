@@ -25,6 +25,7 @@ struct Args {
   bool vec;                                         // 16-byte path legal (alignment, Cout % 4 == 0)
   __half* y16 = nullptr; int ldy16 = 0;             // fp16 output instead of y (no residual / accumulate): the
                                                     // consumer conv reads it as its ready-made A operand
+  __half* y16_lo = nullptr;                         // + fp16(v - fp16(v)) for the hi/lo-split consumers
 };
 
 __device__ __forceinline__ bool vec_ok(const float* y, int ldy, const float* res, int ldr, int Cout) {
@@ -68,6 +69,14 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
         pk.x = *reinterpret_cast<const uint32_t*>(&h01);
         pk.y = *reinterpret_cast<const uint32_t*>(&h23);
         *reinterpret_cast<uint2*>(a.y16 + (out0 + to) * a.ldy16 + n) = pk;
+        if (a.y16_lo) {
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(t.x - f01.x, t.y - f01.y);
+          const __half2 l23 = __floats2half2_rn(t.z - f23.x, t.w - f23.y);
+          pk.x = *reinterpret_cast<const uint32_t*>(&l01);
+          pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(a.y16_lo + (out0 + to) * a.ldy16 + n) = pk;
+        }
       }
     }
   } else if (a.vec) {

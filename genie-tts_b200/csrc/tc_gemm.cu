@@ -177,7 +177,23 @@ tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
     // ---- all global loads of the stage first (independent 16-byte loads in flight), then the
     // buffer-free wait, then convert + swizzled stores; the other resident CTA covers the latency
     float4 av[AIT];
-    {
+    constexpr int HIT = SPLIT_A == 2 ? BM * 8 / NTHR : 1;     // 16-byte chunks per thread per pre-split part
+    uint4 hv[HIT], lv[HIT];
+    const bool presplit = SPLIT_A == 2 && p.x16 != nullptr;   // A arrives as fp16 hi / lo rows (linear, 1 tap)
+    if (presplit) {
+#pragma unroll
+      for (int it = 0; it < HIT; ++it) {
+        const int ci = tid + it * NTHR;
+        const int r = ci >> 3, c8 = ci & 7;
+        hv[it] = make_uint4(0u, 0u, 0u, 0u); lv[it] = hv[it];
+        const int t = q0 + r;
+        if (t < nq && t < Tin && kb * BK + c8 * 8 < Ktot) {
+          const long long o = (long long)(in0 + t) * p.Cin + kb * BK + c8 * 8;
+          hv[it] = __ldg(reinterpret_cast<const uint4*>(p.x16 + o));
+          lv[it] = __ldg(reinterpret_cast<const uint4*>(p.x16_lo + o));
+        }
+      }
+    } else {
       const int kk = kb * BK + c4 * 4;
       const int tap = kk / p.Cin;
       const int ci = kk - tap * p.Cin;
@@ -209,9 +225,18 @@ tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
       }
     }
     if (it_k >= 2) ok = mbar_wait(&bars[s], (uint32_t)(((it_k >> 1) - 1) & 1)) && ok;
-    // ---- A tile: 128 rows x 64 k (fp32 -> fp16 hi/lo, swizzled)
+    // ---- A tile: 128 rows x 64 k (fp32 -> fp16 hi/lo, swizzled; or a plain copy of the pre-split parts)
+    if (presplit) {
 #pragma unroll
-    for (int it = 0; it < AIT; ++it) {
+      for (int it = 0; it < HIT; ++it) {
+        const int ci = tid + it * NTHR;
+        const uint32_t off = swz(ci >> 3, ci & 7);
+        *reinterpret_cast<uint4*>(sA + off) = hv[it];
+        *reinterpret_cast<uint4*>(sA + A_BYTES * (SPLIT_A - 1) + off) = lv[it];
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < (presplit ? 0 : AIT); ++it) {
       float4 v = av[it];
       v.x = fmaxf(v.x, v.x * pre); v.y = fmaxf(v.y, v.y * pre);
       v.z = fmaxf(v.z, v.z * pre); v.w = fmaxf(v.w, v.w * pre);
@@ -274,6 +299,7 @@ tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
   ea.oscale = plain ? p.out_scale : 1.f;
   ea.Cout = p.Cout;
   ea.vec = tc_epi::vec_ok(ea.y, p.ldy, ea.res, p.ldr, p.Cout);
+  ea.y16 = plain ? p.y16 : nullptr; ea.y16_lo = p.y16_lo; ea.ldy16 = p.Cout;
   float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
   const int rq = (warp & 3) * 32;                               // first row of this warp's lane quarter
   if (ok) {
@@ -337,7 +363,9 @@ void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   const int nq = p.M + p.q_extra;
   if (nq <= 0 || p.B <= 0) return;
   if (try_launch_tc_halo_conv(p, err_flag, s)) return;
-  GENIE_CHECK(!p.x16 && !p.y16, "tc_conv_gemm: fp16 hand-over is a tc_halo_conv feature");
+  GENIE_CHECK(!p.x16 || (p.x16_lo && p.tc_split_a && p.ntaps == 1 && p.Cin % 8 == 0 && !p.in_off),
+              "tc_conv_gemm: a pre-split fp16 operand needs hi and lo parts, the split-A form and a plain linear layer");
+  GENIE_CHECK(!p.y16 || (p.ksplit == 1 && !p.res && !p.accumulate && p.Cout % 4 == 0), "tc_conv_gemm: fp16 output is exclusive");
   const bool wlo = p.tc_wlo != nullptr;
   if (p.tc_split_a) {
     if (wlo) dispatch_nt<2, 1>(p, err_flag, s); else dispatch_nt<2, 0>(p, err_flag, s);

@@ -341,7 +341,8 @@ void model_finalize(Model& m) {
 }
 
 void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, int ldy, int M, int act,
-                const float* res, int ldr, int nt, int ksplit, long long split_stride) {
+                const float* res, int ldr, int nt, int ksplit, long long split_stride, const Half2Part* a16,
+                const Half2Part* y16) {
   ConvGemm p;
   p.x = x; p.ldx = ldx; p.w = L.w; p.w_f16 = L.w_f16; p.w_co_stride = L.K; p.w_tap_stride = 0;
   p.bias = L.b; p.y = y; p.ldy = ldy; p.Cin = L.K; p.Cout = L.N; p.M = M; p.M_out = M; p.act = act;
@@ -354,10 +355,13 @@ void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, in
     // fp16-exact weights: (x_hi + x_lo) . w keeps the fp32 graphs' token parity
     p.tc_w = L.tc.hi; p.tc_wlo = L.tc.lo; p.tc_kpad = L.tc.kpad; p.tc_split_a = 1;
     p.tc_nt = nt; p.ksplit = ksplit; p.split_stride = split_stride;
+    if (a16) { p.x16 = a16->hi; p.x16_lo = a16->lo; }
+    if (y16) { p.y16 = y16->hi; p.y16_lo = y16->lo; }
     launch_tc_conv_gemm(p, m.tc_err, m.stream);
     return;
   }
   GENIE_CHECK(ksplit == 1, "run_linear: split-K needs the tcgen05 path");
+  GENIE_CHECK(!a16 && !y16, "run_linear: fp16 hi/lo hand-over needs the tcgen05 path");
   launch_conv_gemm(p, m.stream);
 }
 
