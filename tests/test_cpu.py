@@ -291,3 +291,19 @@ def test_batch_scheduler_batches_orders_and_survives_errors():
     with pytest.raises(ValueError):
         pool.submit([0], np.arange(3))
     pool.close()
+
+
+# ---------------------------------------------------------------- bench.py contract (reference arm runs on CPU)
+def test_bench_reference_arm_json_contract():
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio-sec/sec" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
+    assert "workload" in line["config"] and "sample" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    e2e = line["e2e"]
+    assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
