@@ -335,6 +335,8 @@ def main():
         # (4) prefill (tensor): 150.99 MFLOP per position + 24*4*S^2*512 attention
         S = np.asarray([60 + len(q) + 132 for q in seqs], dtype=np.float64)
         pre_tf = float((S * 150.99e6 + 24 * 4 * S * S * 512).sum()) / (sm["prefill"] * 1e-3) / 1e12
+        narrow_gbs = (last_t.get("narrow_conv_mb", 0.0) * 1e6 / (last_t["narrow_conv_ms"] * 1e-3) / 1e9
+                      if last_t.get("narrow_conv_ms") else 0.0)
         b1_ms_tok = t_b1["decode_ms"] / max(1, t_b1["steps"])
         b1_T = 60 + len(seqs[11 % B]) + 132 + TOKENS / 2
         b1_gbs = (152.364e6 + 98304.0 * b1_T) / (b1_ms_tok * 1e-3) / 1e9
@@ -369,6 +371,11 @@ def main():
                  "achieved": gen_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gen_tf / tf_peak,
                  "launches_per_step": n_gen, "avg_launch_ms": sm["generator"] / n_gen,
                  "share_of_step": sm["generator"] / step_ms},
+                # narrow generator stages (<= 32 channels: tc_halo_conv, fused transposed convs, conv_post): every
+                # tensor of every conv counted once per read / write, over the stage events of the last timed step
+                {"stage": "sovits generator narrow stages (C <= 32)", "bound": "hbm", "achieved": narrow_gbs,
+                 "peak": hbm_peak, "unit": "GB/s", "frac": narrow_gbs / hbm_peak,
+                 "ms": last_t.get("narrow_conv_ms"), "share_of_step": (last_t.get("narrow_conv_ms") or 0.0) / step_ms},
                 {"stage": "t2s decode step (all kernels, CUDA graph)", "bound": "hbm", "achieved": dec_gbs,
                  "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "share_of_step": sm["decode"] / step_ms},
                 {"stage": "t2s prefill (tc_conv_gemm split-fp16 + attention)", "bound": "tensor", "achieved": pre_tf,

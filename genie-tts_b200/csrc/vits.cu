@@ -403,8 +403,22 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
     run_conv(m, m.dec_pre, Z, 192, GX, C0, s2, o);
     keep_tensor(m, "g_pre", GX, (long long)R2 * C0);
   }
+  cudaEvent_t ev_narrow = nullptr;           // start of the first stage with <= 32 channels (HBM-bound part)
+  double narrow_bytes = 0.0;                 // its algorithmic bytes: every tensor read or written once per conv
   for (int i = 0; i < m.n_up; ++i) {
     const ConvT& U = m.ups[i];
+    if (U.Cout <= 32 && !ev_narrow) {
+      GENIE_CUDA(cudaEventCreate(&ev_narrow));
+      GENIE_CUDA(cudaEventRecord(ev_narrow, s));
+    }
+    if (ev_narrow) {
+      const double e_in = (double)sg[i].rows * U.Cin, e_out = (double)sg[i + 1].rows * U.Cout;
+      const bool h16p = m.use_tc && m.tc_vits == 1 && tc_halo_fp16_pair_ok(U.Cout, 3);
+      // upsampling conv: read in, write out; per resblock pair: conv1 reads x (4 B) and writes the hand-over
+      // (2 B fp16 / 4 B fp32), conv2 reads it back, reads the residual and writes (4 + 4 B); the last conv of
+      // resblocks 1 and 2 also reads the running sum
+      narrow_bytes += 4.0 * (e_in + e_out) + e_out * (9.0 * (4.0 + 4.0 + 4.0 + (h16p ? 4.0 : 8.0)) + 2.0 * 4.0);
+    }
     run_convt(m, U, GX, UP, sg[i], sg[i + 1], 0.1f);
     const Seg& S = sg[i + 1];
     const int C = U.Cout;
@@ -448,6 +462,14 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   float t01 = 0.f, t12 = 0.f;
   cudaEventElapsedTime(&t01, ev0, ev1); cudaEventElapsedTime(&t12, ev1, ev2);
   m.timing[4] = t01 + t12; m.timing[5] = t12; m.timing[6] = (float)gen_launches; m.timing[7] = (float)R2;
+  m.timing[10] = 0.f; m.timing[11] = 0.f;
+  if (ev_narrow) {
+    // narrow generator stages incl. conv_post (reads the last stage output once, writes the waveform)
+    narrow_bytes += 4.0 * ((double)sg[5].rows * m.c_last + (double)sg[5].rows);
+    cudaEventElapsedTime(&m.timing[10], ev_narrow, ev2);
+    m.timing[11] = (float)(narrow_bytes / 1e6);
+    cudaEventDestroy(ev_narrow);
+  }
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
 }
 

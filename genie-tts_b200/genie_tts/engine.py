@@ -316,7 +316,8 @@ class B200Model:
         N.check(N.lib().genie_last_timing(self._h, _ptr(t), 12))
         return {"prefill_ms": float(t[0]), "decode_ms": float(t[1]), "t2s_ms": float(t[2]), "steps": int(t[3]),
                 "vits_ms": float(t[4]), "generator_ms": float(t[5]), "generator_launches": int(t[6]),
-                "latent_rows": int(t[7]), "decode_attention_us": float(t[8]), "decode_attention_kv_mb": float(t[9])}
+                "latent_rows": int(t[7]), "decode_attention_us": float(t[8]), "decode_attention_kv_mb": float(t[9]),
+                "narrow_conv_ms": float(t[10]), "narrow_conv_mb": float(t[11])}
 
 
 class B200Prompt:

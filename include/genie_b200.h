@@ -145,7 +145,8 @@ int genie_profiler_range(int on);
 /* stage timing of the last calls (CUDA events on the library's stream), up to 12 floats:
  * [0] prefill ms, [1] decode ms, [2] t2s total ms, [3] decode steps, [4] vits ms, [5] generator ms,
  * [6] generator launches, [7] latent rows, [8] decode-attention us per launch and [9] its KV MB per launch
- * (only after a genie_t2s_generate with option time_attention > 0) */
+ * (only after a genie_t2s_generate with option time_attention > 0), [10] ms of the generator stages with <= 32
+ * channels (HBM-bound) and [11] their algorithmic MB */
 int genie_last_timing(genie_model* m, float* ms, int n);
 /* options: use_graph (CUDA-graph replay of the decode step, default 1), use_tc / tc_vits (tensor-core paths),
  * skinny_max_rows, tc_min_rows, decode_split_min (path selection, debugging),
