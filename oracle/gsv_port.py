@@ -5,7 +5,7 @@ six ONNX graphs, written as ordinary model code instead of a graph walk, plus
 the reference host loop.  Every function cites the graph nodes it restates as
 ``<graph>#[node-index]`` (node index = position in graph.node)
 or the reference file:line.  It is pinned against the reference's own graph
-files executed by ``oracle/onnx_interp.py`` (tests/test_oracle_port.py, run in
+files executed by ``oracle/onnx_interp.py`` (tests/test_cpu.py, run in
 the build container) and against the committed vectors in tests/golden/.
 The real runtime (onnxruntime 1.22.1) is not installable here: parity with it
 is unpinned.
