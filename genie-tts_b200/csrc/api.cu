@@ -319,6 +319,7 @@ int genie_set_option(genie_model* h, const char* key, int value) {
   if (std::strcmp(key, "persistent_step") == 0) { h->m.persistent_step = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "use_tc") == 0) { h->m.use_tc = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "tc_vits") == 0) { h->m.tc_vits = value; return 0; }
+  if (std::strcmp(key, "fuse_pairs") == 0) { h->m.fuse_pairs = value; return 0; }
   if (std::strcmp(key, "decode_split_min") == 0) { h->m.decode_split_min = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "decode_branches") == 0) { h->m.decode_branches = value; h->m.step_graph_flags = -1; return 0; }
   if (std::strcmp(key, "skinny_max_rows") == 0) { h->m.skinny_max_rows = value; h->m.step_graph_flags = -1; return 0; }

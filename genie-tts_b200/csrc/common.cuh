@@ -118,6 +118,10 @@ void launch_tc_conv_gemm(const ConvGemm& p, int* err_flag, cudaStream_t s);
 // k-tap convs with the activation halo staged once per CTA (tc_halo_conv.cu); false => not applicable
 bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s);
 bool tc_halo_fp16_pair_ok(int C, int ntaps);   // both convs of a C -> C pair take tc_halo_conv_kernel
+// one resblock pair (conv1 dilated, conv2 dilation 1, C -> C, C = 16 / 32) in one kernel (tc_pair_conv.cu)
+bool tc_pair_conv_supported(int C, int k);
+void launch_tc_pair_conv(const ConvGemm& conv2, const __half* w1, const float* bias1, int kpad1, int d1, int* err_flag,
+                         cudaStream_t s);
 bool pretile_w128_supported(int Cin, int Cout, int ntaps);
 void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s);
 bool skinny_gemm_supported(const ConvGemm& p);

@@ -128,6 +128,7 @@ struct Model {
   // tcgen05 path: 0 = exact SIMT everywhere; T2S always runs x_hi+x_lo against fp16-exact weights;
   // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo
   int use_tc = 1, tc_vits = 1, tc_min_rows = 9, skinny_max_rows = 8;
+  int fuse_pairs = 1;                  // narrow resblock pairs as one kernel (tc_pair_conv.cu)
   int* tc_err = nullptr;
   // persistent decode step (batch <= skinny_max_rows): per-layer pointer table, barrier words, grid size
   void* step_layers_dev = nullptr; unsigned* step_sync = nullptr; int num_sms = 0;

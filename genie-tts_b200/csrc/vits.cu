@@ -417,7 +417,10 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       // upsampling conv: read in, write out; per resblock pair: conv1 reads x (4 B) and writes the hand-over
       // (2 B fp16 / 4 B fp32), conv2 reads it back, reads the residual and writes (4 + 4 B); the last conv of
       // resblocks 1 and 2 also reads the running sum
-      narrow_bytes += 4.0 * (e_in + e_out) + e_out * (9.0 * (4.0 + 4.0 + 4.0 + (h16p ? 4.0 : 8.0)) + 2.0 * 4.0);
+      // (fused pairs, tc_pair_conv.cu: x in once, y out once = 8 B per element and pair)
+      const bool fusedp = m.use_tc && m.tc_vits == 1 && m.fuse_pairs && tc_pair_conv_supported(U.Cout, 3);
+      narrow_bytes += 4.0 * (e_in + e_out) +
+                      e_out * (9.0 * (fusedp ? 8.0 : 4.0 + 4.0 + 4.0 + (h16p ? 4.0 : 8.0)) + 2.0 * 4.0);
     }
     run_convt(m, U, GX, UP, sg[i], sg[i + 1], 0.1f);
     const Seg& S = sg[i + 1];
@@ -430,7 +433,20 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       // narrow stages are HBM-bound: conv1 hands fp16(lrelu(out)) to conv2 (exactly what conv2's loader
       // would have produced from the fp32 tensor), 2 + 2 instead of 4 + 4 bytes per element
       const bool h16 = m.use_tc && m.tc_vits == 1 && S.off != nullptr && tc_halo_fp16_pair_ok(C, Rb.k);
-      for (int c = 0; c < 3; ++c) {
+      // 16 / 32 channels: the whole pair in one kernel (x read once, intermediate never leaves the SM)
+      const bool fused = m.use_tc && m.tc_vits == 1 && S.off != nullptr && m.fuse_pairs && tc_pair_conv_supported(C, Rb.c2[0].k) &&
+                         Rb.c1[0].tc.hi && Rb.c2[0].tc.hi;
+      for (int c = 0; c < 3 && fused; ++c) {
+        float* dst = c < 2 ? pp[c] : GX;
+        ConvGemm q;
+        q.x = r; q.ldx = C; q.pre_slope = 0.1f; q.Cin = C; q.Cout = C; q.ntaps = Rb.c2[c].k; q.in_shift_step = 1;
+        q.tc_w = Rb.c2[c].tc.hi; q.tc_kpad = Rb.c2[c].tc.kpad; q.bias = Rb.c2[c].b;
+        q.res = r; q.ldr = C; q.y = dst; q.ldy = C; q.accumulate = (c == 2 && j > 0) ? 1 : 0;
+        q.in_off = S.off; q.out_off = S.off; q.B = S.B; q.M = S.maxT; q.M_out = S.maxT;
+        launch_tc_pair_conv(q, Rb.c1[c].tc.hi, Rb.c1[c].b, Rb.c1[c].tc.kpad, dils[c], m.tc_err, m.stream);
+        r = dst;
+      }
+      for (int c = 0; c < 3 && !fused; ++c) {
         ConvOpt a; a.dil = dils[c]; a.pre_slope = 0.1f;
         if (h16) { a.act = ACT_LRELU; a.act_slope = 0.1f; a.y16 = GA16; }
         run_conv(m, Rb.c1[c], r, C, GA, C, S, a);
