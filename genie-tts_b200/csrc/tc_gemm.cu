@@ -149,7 +149,11 @@ tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
 
-  const uint32_t idesc = (1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  // one MMA covers at most 256 columns: the 512-wide tile (split-fp16 linears: halves the number of CTAs that
+  // re-convert the same A rows) issues two per k-step into adjacent TMEM column ranges
+  const int n_a = n_mma > 256 ? 256 : n_mma, n_b = n_mma - n_a;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(n_a >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t idesc_b = (1u << 4) | ((uint32_t)(n_b >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
   const int Ktot = p.ntaps * p.Cin;
   const int KB = p.tc_kpad / BK;
   const float* __restrict__ xg = p.x + (long long)in0 * p.ldx;
@@ -274,6 +278,11 @@ tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
         umma_f16(tmem, da, db, idesc, (uint32_t)((it_k | j) != 0));
         if (SPLIT_A == 2) umma_f16(tmem, umma_desc(aA + A_BYTES + j * 32), db, idesc, 1u);
         if (W_LO) umma_f16(tmem, da, umma_desc(aW + W_BYTES + j * 32), idesc, 1u);
+        if (NT > 256 && n_b > 0) {
+          const uint64_t db2 = umma_desc(aW + 256 * 128 + j * 32);
+          umma_f16(tmem + 256u, da, db2, idesc_b, (uint32_t)((it_k | j) != 0));
+          if (SPLIT_A == 2) umma_f16(tmem + 256u, umma_desc(aA + A_BYTES + j * 32), db2, idesc_b, 1u);
+        }
       }
       // completion of everything issued so far -> frees this stage's buffers
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -341,6 +350,13 @@ void dispatch_nt(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   // hi/lo-split activations: every N tile re-converts the same A rows, so the wide tile wins although only one
   // CTA fits per SM (measured at 24 200 rows: K=2048 N=512 293 -> 226 us, K=512 N=1536 221 -> 214 us)
   static const int nt_env = [] { const char* e = getenv("GENIE_TC_NT_SPLIT"); return e ? atoi(e) : 256; }();
+  if constexpr (SPLIT_A == 2 && W_LO == 0) {
+    // 512-wide tile (one CTA per SM, all 512 TMEM columns): N = 1536 / 2048 of the T2S linears
+    static const int wide_env = [] { const char* e = getenv("GENIE_TC_NT512"); return e ? atoi(e) : 1; }();
+    // (N = 512 itself stays on the 256-wide tile: one CTA per 128 rows leaves 190 CTAs for 148 SMs at the bench
+    // size, 206 vs 190 us)
+    if (wide_env && p.tc_nt == 0 && p.Cout % 512 == 0 && p.Cout >= 1024 && p.ksplit == 1) { launch_tc<512, 2, 0>(p, err_flag, s); return; }
+  }
   if (SPLIT_A == 2 && !W_LO && nt_env == 256 && p.tc_nt == 0 && p.Cout > 128) { launch_tc<256, SPLIT_A, W_LO>(p, err_flag, s); return; }
   constexpr bool wide_ok = tc_min_blocks<256, SPLIT_A, W_LO>() == 2;
   constexpr bool mid_ok = tc_min_blocks<128, SPLIT_A, W_LO>() == 2;
