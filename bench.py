@@ -13,6 +13,8 @@ decode) over the batch.
   e2e   : same metric through the reference-facing call GENIE.tts_batch with HOST
           numpy buffers (H2D of phoneme ids, D2H of tokens and float32 audio inside
           the timed region)
+  --config {2,3,4} : BASELINE.json configs[1] (default, the headline), configs[2] (V2ProPlus English paragraph,
+          batch 64, KV up to ~1440) and configs[3] (V2 with 1024-d BERT rows, batch 256 per GPU)
   --impl reference : the reference's own CPU path (its ONNX graph files executed
           by oracle/onnx_interp.py over the restated host loop; falls back to the
           torch port if the graphs were not staged) on a bounded sample.
@@ -33,15 +35,30 @@ for _p in (ROOT, os.path.join(ROOT, "genie-tts_b200"), os.path.join(ROOT, "tests
         sys.path.insert(0, _p)
 
 METRIC = "audio-sec/sec"
-N_SENT = 100
-TOKENS = 90
-WORKLOAD = "GPT-SoVITS V2, 100 sentences x ~20 chars (Lr=60, Lt~U{40..60}, 132 prompt tokens, 90-token budget), 1 B200"
+# BASELINE.json configs[1..3] (0-based: configs[0] is the reference's own batch-1 CPU case -> --impl reference).
+# Synthetic inputs at the G2P / HuBERT / SV / RoBERTa output boundary, SURVEY.md §8d.
+CONFIGS = {
+    2: dict(version="v2", fixture_seed=0, sentences=100, tokens=90, Lr=60, Ts=264, n_audio=169600, Lt=(40, 60),
+            bert=False,
+            workload="configs[1]: GPT-SoVITS V2, 100 sentences x ~20 chars (Lr=60, Lt~U{40..60}, 132 prompt tokens, "
+                     "90-token budget, KV 242->332), 1 B200"),
+    3: dict(version="v2ProPlus", fixture_seed=1, sentences=64, tokens=500, Lr=300, Ts=1000, n_audio=640000,
+            Lt=(100, 140), bert=False,
+            workload="configs[2]: GPT-SoVITS V2ProPlus English paragraph, sentence-split: batch 64 x (Lt~U{100..140}, "
+                     "20 s reference = 300 ref phones + 500 prompt tokens, 500-step budget = the reference's loop "
+                     "bound, KV 900->1441 per utterance)"),
+    4: dict(version="v2", fixture_seed=0, sentences=256, tokens=90, Lr=60, Ts=264, n_audio=169600, Lt=(40, 60),
+            bert=True,
+            workload="configs[3]: GPT-SoVITS V2 Chinese shape: 256 sentences per GPU with N(0,1) 1024-d BERT rows for "
+                     "reference and target text (bert_proj GEMM in the encoder), 90-token budget"),
+}
+DTYPE = "f32 accumulate/activations; T2S GEMMs fp16 hi+lo split operands (tcgen05), fp32 KV; SoVITS convs single-pass fp16 operands (tcgen05)"
 # algorithmic work (measured on the reference graphs)
-GEN_GFLOP_PER_AUDIO_S = 8.26 + 16.52 + 8.26 + 4.13 + 2.06 + 1.36   # HiFi-GAN stages 0-4 + ups
-# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attention launch from the committed
-# `ncu --set full` capture (profiles/); None until that capture exists for the current kernel
-ATT_DRAM_BYTES_NCU = 104438016   # profiles/r01_v5_ncu_full_decode_attention.txt: 100.88 MB read + 3.56 MB written at
-                                 # kv_len ~ 245 per utterance (algorithmic 100.4 MB for that launch)
+GEN_GFLOP_PER_AUDIO_S = {"v2": 8.26 + 16.52 + 8.26 + 4.13 + 2.06 + 1.36,   # HiFi-GAN stages 0-4 + ups
+                         "v2ProPlus": 89.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of one decode_attention launch from the committed `ncu --set full`
+# capture of the CURRENT kernel (profiles/), with the algorithmic bytes of that same launch
+ATT_NCU = {"file": "profiles/r01_v5_ncu_full_decode_attention.txt", "dram_bytes": 104438016, "algorithmic_bytes": 100.4e6}
 
 
 def peaks():
@@ -53,12 +70,32 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
-def make_workload(n_sent, seed0=1234):
+def make_workload(cfg, n_sent=None, rank=0, seed0=1234):
+    """(prompt inputs, [text inputs]) of a config.  Every rank draws the SAME sentences (``rank`` is deliberately
+    unused): produced audio per step is then identical on every GPU and the 1/2/4/8 scaling curve measures the
+    machine, not the per-rank EOS-strip yield."""
     from synth import make_prompt_inputs, make_text_inputs
-    pr = make_prompt_inputs(seed=seed0, Lr=60, Ts=264, n_audio=169600)
+    n_sent = n_sent or cfg["sentences"]
+    v2pp = cfg["version"] == "v2ProPlus"
+    pr = make_prompt_inputs(seed=seed0, Lr=cfg["Lr"], Ts=cfg["Ts"], n_audio=cfg["n_audio"], bert=cfg["bert"], v2pp=v2pp)
     rng = np.random.default_rng(seed0 + 1)
-    texts = [make_text_inputs(seed=seed0 + 10 + i, Lt=int(rng.integers(40, 61))) for i in range(n_sent)]
-    return pr, texts
+    lo, hi = cfg["Lt"]
+    texts = [make_text_inputs(seed=seed0 + 10 + i, Lt=int(rng.integers(lo, hi + 1)), bert=cfg["bert"])
+             for i in range(n_sent)]
+    berts = [t["text_bert"] for t in texts] if cfg["bert"] else None
+    return pr, texts, berts
+
+
+def aggregate_over_ranks(times, units, world, device):
+    """Whole-job figures of an N-rank run: time = MAX over ranks (device-timed spans), units = SUM over ranks."""
+    import torch
+    import torch.distributed as dist
+    tt = torch.tensor(list(times), dtype=torch.float64, device=device)
+    uu = torch.tensor(list(units), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(uu, op=dist.ReduceOp.SUM)
+    return tt.tolist(), uu.tolist()
 
 
 class ClockSampler:
@@ -104,9 +141,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_step(pr, tx, sessions_or_port, kind, tokens):
+def cpu_reference_step(cfg, pr, tx, sessions_or_port, kind, tokens):
     """One sentence through the reference CPU path; returns audio seconds produced."""
     import torch
+    v2pp = cfg["version"] == "v2ProPlus"
     if kind == "reference":
         from oracle import ref_pipeline as R
         s = sessions_or_port
@@ -114,7 +152,12 @@ def cpu_reference_step(pr, tx, sessions_or_port, kind, tokens):
                          max_steps=tokens)
         sem = R.strip_eos(toks)
         sem = np.where(sem >= 1024, 0, sem)
-        audio = R.vocode(s, tx["text_seq"], sem, ref_audio_32k=pr["ref_audio"])
+        if v2pp:
+            if "ge" not in pr:
+                pr["ge"], pr["ge_advanced"] = R.prompt_global_emb(s, pr["ref_audio"], pr["sv_emb"])
+            audio = R.vocode(s, tx["text_seq"], sem, ge=pr["ge"], ge_advanced=pr["ge_advanced"])
+        else:
+            audio = R.vocode(s, tx["text_seq"], sem, ref_audio_32k=pr["ref_audio"])
     else:
         from oracle import gsv_port as P
         pm = sessions_or_port
@@ -123,16 +166,19 @@ def cpu_reference_step(pr, tx, sessions_or_port, kind, tokens):
                            noise_fn=lambda i: torch.randn(1025))
         sem = r.tokens.reshape(-1)
         sem = sem[sem < 1024]
-        audio = P.vits_decode(pm, tx["text_seq"], sem, P.ref_enc_v2(pm, pr["ref_audio"]), None,
-                              zp_noise=torch.randn(1, 192, 2 * len(sem)))
+        if v2pp:
+            ge, gea = P.prompt_encoder_v2pp(pm, pr["ref_audio"], pr["sv_emb"])
+        else:
+            ge, gea = P.ref_enc_v2(pm, pr["ref_audio"]), None
+        audio = P.vits_decode(pm, tx["text_seq"], sem, ge, gea, zp_noise=torch.randn(1, 192, 2 * len(sem)))
     return len(audio) / 32000.0
 
 
-def load_cpu_reference(model_dir):
+def load_cpu_reference(cfg, model_dir):
     import torch
     from fixture_models import have_templates
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    if have_templates("v2") and os.path.getsize(os.path.join(model_dir, "vits_fp32.onnx")) > 100000:
+    if have_templates(cfg["version"]) and os.path.getsize(os.path.join(model_dir, "vits_fp32.onnx")) > 100000:
         from oracle import ref_pipeline as R
         s = R.load_sessions(model_dir)
         R.set_sampler_mode(s, greedy=False)
@@ -141,29 +187,35 @@ def load_cpu_reference(model_dir):
     return P.PortModel(model_dir), "port"
 
 
-def run_reference_arm(args, model_dir, rank):
+def cpu_sample_tokens(cfg):
+    """Bounded CPU sample: the config's own token budget, capped so one sentence stays within ~20 s of CPU work."""
+    return min(cfg["tokens"], 90)
+
+
+def run_reference_arm(args, cfg, model_dir, rank):
     import torch
     if rank != 0:
         return
-    pr, texts = make_workload(4)
-    obj, kind = load_cpu_reference(model_dir)
+    pr, texts, _ = make_workload(cfg, 4)
+    obj, kind = load_cpu_reference(cfg, model_dir)
     cores = torch.get_num_threads()
-    sample = (f"1 sentence of the workload per step ({TOKENS}-token budget, batch 1: the reference path is "
+    tokens = cpu_sample_tokens(cfg)
+    sample = (f"1 sentence of the workload per step ({tokens}-token budget, batch 1: the reference path is "
               f"single-stream by construction), {'reference ONNX graphs on the torch-CPU interpreter' if kind == 'reference' else 'torch port'}"
               " (onnxruntime 1.22.1 unavailable offline)")
     for i in range(args.warmup):
-        cpu_reference_step(pr, texts[i % len(texts)], obj, kind, TOKENS)
+        cpu_reference_step(cfg, pr, texts[i % len(texts)], obj, kind, tokens)
     t0 = time.perf_counter()
     audio_s = 0.0
     for i in range(args.steps):
-        audio_s += cpu_reference_step(pr, texts[i % len(texts)], obj, kind, TOKENS)
+        audio_s += cpu_reference_step(cfg, pr, texts[i % len(texts)], obj, kind, tokens)
     dt = time.perf_counter() - t0
     v = audio_s / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": cfg["workload"], "sample": sample},
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -175,10 +227,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sentences", type=int, default=N_SENT)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json configs index + 1: 2 = headline (V2 JA 100 sentences), 3 = V2ProPlus EN "
+                         "paragraph batch 64 long KV, 4 = V2 ZH BERT batch 256 per GPU")
+    ap.add_argument("--sentences", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = CONFIGS[args.config]
+    TOKENS = cfg["tokens"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -186,15 +243,15 @@ def main():
     from conftest import fixture_dir
     # rank 0 writes the fixture once; other ranks wait on the marker
     if local_rank == 0:
-        model_dir = fixture_dir("v2", 0)
+        model_dir = fixture_dir(cfg["version"], cfg["fixture_seed"])
     else:
         from conftest import FIXTURE_ROOT
-        model_dir = os.path.join(FIXTURE_ROOT, "v2_seed0")
+        model_dir = os.path.join(FIXTURE_ROOT, f"{cfg['version']}_seed{cfg['fixture_seed']}")
         while not os.path.exists(os.path.join(model_dir, ".complete")):
             time.sleep(0.5)
 
     if args.impl == "reference":
-        run_reference_arm(args, model_dir, rank)
+        run_reference_arm(args, cfg, model_dir, rank)
         return
 
     import torch
@@ -213,8 +270,8 @@ def main():
         torch.cuda.synchronize()
 
     model = B200Model(model_dir, device=local_rank)
-    pr, texts = make_workload(args.sentences, seed0=1234 + 1000 * rank)
-    prompt = model.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"])   # untimed
+    pr, texts, berts = make_workload(cfg, args.sentences or cfg["sentences"], rank=rank)
+    prompt = model.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"], pr.get("sv_emb"))  # untimed
     B = len(texts)
     prompts = [prompt] * B
     seqs = [t["text_seq"].reshape(-1) for t in texts]
@@ -225,6 +282,7 @@ def main():
     # ---- device-resident leg
     dev = torch.device("cuda", local_rank)
     seq_dev = torch.from_numpy(np.concatenate(seqs)).to(dev)
+    bert_dev = torch.from_numpy(np.concatenate(berts, axis=0)).to(dev) if berts is not None else None
     y_ld = prompt.n_prompt_tokens + TOKENS + 2
     y_dev = torch.zeros((B, y_ld), dtype=torch.int64, device=dev)
     audio_dev = torch.zeros(B * TOKENS * 1280, dtype=torch.float32, device=dev)
@@ -234,7 +292,7 @@ def main():
 
     def step_device():
         w0 = time.perf_counter()
-        y_len, idx = model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev)
+        y_len, idx = model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev, text_bert_cat=bert_dev)
         w1 = time.perf_counter()
         t = model.last_timing()
         # host glue of the reference (Inference.py:41-44,108-109) on the small token matrix
@@ -255,7 +313,7 @@ def main():
         return float(alen.sum()) / 32000.0, t2
 
     def step_host():
-        auds = genie.tts_batch(model, prompts, seqs, None, sampling=sp)
+        auds = genie.tts_batch(model, prompts, seqs, berts, sampling=sp)
         return sum(len(a) for a in auds) / 32000.0, sum(a.nbytes for a in auds)
 
     for _ in range(args.warmup):
@@ -291,29 +349,24 @@ def main():
     barrier()
     dt_e = time.perf_counter() - t1
 
-    # ---- batch-1 first-audio latency (BASELINE.json metric part 3): one ~20-char sentence, host buffers,
-    # text front end excluded (untimed in the reference comparison too), 90-token budget
+    # ---- batch-1 first-audio latency (BASELINE.json metric part 3): one sentence of the config, host buffers,
+    # text front end excluded (untimed in the reference comparison too), the config's token budget
     lat = []
     for i in range(12):
         torch.cuda.synchronize()
         tl0 = time.perf_counter()
-        genie.tts_batch(model, [prompt], [seqs[i % B]], None, sampling=sp)
+        genie.tts_batch(model, [prompt], [seqs[i % B]], [berts[i % B]] if berts is not None else None, sampling=sp)
         lat.append(1000 * (time.perf_counter() - tl0))
     first_audio_ms = float(np.median(lat[2:]))
+    first_audio_p99 = float(np.max(lat[2:]))
     t_b1 = model.last_timing()          # stage events of the last batch-1 call
 
-    tt = torch.tensor([dt, dt_e], dtype=torch.float64, device=dev)
-    aa = torch.tensor([audio_s, e_audio], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(aa, op=dist.ReduceOp.SUM)
-    dt, dt_e = tt.tolist()
-    audio_s, e_audio = aa.tolist()
+    (dt, dt_e), (audio_s, e_audio) = aggregate_over_ranks([dt, dt_e], [audio_s, e_audio], world, dev)
 
     # ---- dominant kernel, timed live: decode_attention sits inside the step's CUDA graph, so the library
-    # replays it on the final KV cache (24 layers back to back, 2.8 GB >> L2) between CUDA events on its stream
+    # replays it on the final KV cache (24 layers back to back, GBs >> L2) between CUDA events on its stream
     model.set_option("time_attention", 20)
-    model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev)
+    model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev, text_bert_cat=bert_dev)
     t_att = model.last_timing()
     model.set_option("time_attention", 0)
 
@@ -322,50 +375,62 @@ def main():
         sm = {k: float(np.mean(v)) for k, v in stage_ms.items()}
         audio_per_step = audio_s / args.steps / world
         step_ms = 1000 * dt / args.steps
-        # (1) decode attention (HBM): algorithmic bytes = K and V rows of every cached token of one layer, fp32
+        S = np.asarray([cfg["Lr"] + len(q) + prompt.n_prompt_tokens for q in seqs], dtype=np.float64)   # prefill rows
+        # (1) decode attention (HBM): algorithmic bytes = K and V rows of every cached token of one layer, fp32.
+        # The replay runs on the FINAL cache (S + TOKENS rows per utterance): its bytes and its time belong together.
         att_us, att_mb = t_att["decode_attention_us"], t_att["decode_attention_kv_mb"]
         att_gbs = att_mb * 1e6 / (att_us * 1e-6) / 1e9 if att_us > 0 else 0.0
-        att_share = att_us * 1e-3 * 24 * TOKENS / step_ms
-        # (2) generator convs (tensor): BASELINE.md's 40.59 GFLOP per audio-second over the generator stage
+        # inside the step the cache grows linearly from S to S + TOKENS: the AVERAGE launch streams these bytes
+        kv_mb_avg = float((S + TOKENS / 2.0).sum()) * 2 * 512 * 4 / 1e6
+        att_us_avg = att_us * kv_mb_avg / att_mb if att_mb > 0 else 0.0     # time is linear in bytes
+        att_share = att_us_avg * 1e-3 * 24 * TOKENS / step_ms
+        # (2) generator convs (tensor): GFLOP per audio-second of the graph over the generator stage
         n_gen = max(1, last_t["generator_launches"])
-        gen_tf = GEN_GFLOP_PER_AUDIO_S * 1e9 * audio_per_step / (sm["generator"] * 1e-3) / 1e12
-        # (3) whole decode step (HBM): fp16 weights + fp32 KV read + KV append per step
-        kv_mb_step = att_mb * 24
+        gen_tf = GEN_GFLOP_PER_AUDIO_S[cfg["version"]] * 1e9 * audio_per_step / (sm["generator"] * 1e-3) / 1e12
+        # (3) whole decode step (HBM): fp16 weights + fp32 KV read of the AVERAGE step
+        kv_mb_step = kv_mb_avg * 24
         dec_gbs = (152.364 + kv_mb_step) * 1e6 / (sm["decode"] / TOKENS * 1e-3) / 1e9
         # (4) prefill (tensor): 150.99 MFLOP per position + 24*4*S^2*512 attention
-        S = np.asarray([60 + len(q) + 132 for q in seqs], dtype=np.float64)
         pre_tf = float((S * 150.99e6 + 24 * 4 * S * S * 512).sum()) / (sm["prefill"] * 1e-3) / 1e12
         narrow_gbs = (last_t.get("narrow_conv_mb", 0.0) * 1e6 / (last_t["narrow_conv_ms"] * 1e-3) / 1e9
                       if last_t.get("narrow_conv_ms") else 0.0)
         b1_ms_tok = t_b1["decode_ms"] / max(1, t_b1["steps"])
-        b1_T = 60 + len(seqs[11 % B]) + 132 + TOKENS / 2
+        b1_T = cfg["Lr"] + len(seqs[11 % B]) + prompt.n_prompt_tokens + TOKENS / 2
         b1_gbs = (152.364e6 + 98304.0 * b1_T) / (b1_ms_tok * 1e-3) / 1e9
+        h2d = int(sum(s.nbytes for s in seqs) + lens.nbytes + (sum(b.nbytes for b in berts) if berts is not None else 0))
         line = {
             "metric": METRIC, "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sentences_per_gpu": B, "tokens_per_sentence": TOKENS,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": cfg["workload"], "bench_config": args.config, "sentences_per_gpu": B,
+                       "tokens_per_sentence": TOKENS,
                        "sampling": "top_k=15 T=1.0 rep=1.35 Philox", "l2": "working set (KV cache, vocoder "
-                       "activations) >> 126 MB L2, no explicit flush", "parallelism": f"dp{world} by utterance"},
-            "e2e": {"value": e_audio / dt_e, "unit": "audio-s/s",
-                    "h2d_bytes_per_step": int(sum(s.nbytes for s in seqs) + lens.nbytes),
+                       "activations) >> 126 MB L2, no explicit flush",
+                       "parallelism": f"dp{world} by utterance, replicas only; every rank synthesises the same "
+                                      "sentences (yield-independent scaling)"},
+            # yield-independent companion of `value`: decode tokens x 40 ms (value counts the audio actually
+            # produced, i.e. after the reference's slicing quirks and EOS strip)
+            "token_audio_s_per_s": world * B * TOKENS * 0.04 * args.steps / dt,
+            "e2e": {"value": e_audio / dt_e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "t2s_tokens_per_s": world * B * TOKENS * args.steps / (np.sum(stage_ms["decode"]) * 1e-3) / 1.0
             if stage_ms["decode"] else None,
             "stage_ms": sm,
-            "first_audio_ms_p50_batch1": first_audio_ms,
+            "first_audio_ms_p50_batch1": first_audio_ms, "first_audio_ms_max_batch1": first_audio_p99,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "decode_attention_kernel<fused> (one query per utterance x head over "
                          "the fp32 KV cache; largest single kernel of the step)",
                          "achieved": att_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": att_gbs / hbm_peak,
                          "peak_source": which, "bytes_per_launch": att_mb * 1e6, "avg_launch_us": att_us,
                          "launches_per_step": 24 * TOKENS, "share_of_step": att_share,
-                         "timing": "replayed alone after the timed steps, 20 x 24 layers back to back, CUDA events "
-                                   "on the launching stream (inside the step it is a CUDA-graph node)",
-                         "traffic": ATT_DRAM_BYTES_NCU,
-                         "traffic_note": "ncu --set full capture of one launch at kv_len~245 (algorithmic 100.4 MB there; "
-                                         "the replay above runs at the final kv_len)"},
+                         "bytes_per_launch_step_average": kv_mb_avg * 1e6,
+                         "timing": "replayed alone after the timed steps on the FINAL KV cache, 20 x 24 layers back "
+                                   "to back, CUDA events on the launching stream (inside the step it is a CUDA-graph "
+                                   "node); share_of_step scales that time to the step-average KV length",
+                         "traffic": ATT_NCU["dram_bytes"],
+                         "traffic_note": f"{ATT_NCU['file']}: dram read+write of one launch whose algorithmic bytes "
+                                         f"are {ATT_NCU['algorithmic_bytes'] / 1e6:.1f} MB"},
             "rooflines": [
                 {"stage": "sovits generator convs (tc_conv_gemm / tc_halo_conv, tcgen05)", "bound": "tensor",
                  "achieved": gen_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gen_tf / tf_peak,
@@ -376,7 +441,8 @@ def main():
                 {"stage": "sovits generator narrow stages (C <= 32)", "bound": "hbm", "achieved": narrow_gbs,
                  "peak": hbm_peak, "unit": "GB/s", "frac": narrow_gbs / hbm_peak,
                  "ms": last_t.get("narrow_conv_ms"), "share_of_step": (last_t.get("narrow_conv_ms") or 0.0) / step_ms},
-                {"stage": "t2s decode step (all kernels, CUDA graph)", "bound": "hbm", "achieved": dec_gbs,
+                {"stage": "t2s decode step (all kernels, CUDA graph), bytes of the step-average KV length",
+                 "bound": "hbm", "achieved": dec_gbs,
                  "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "share_of_step": sm["decode"] / step_ms},
                 {"stage": "t2s prefill (tc_conv_gemm split-fp16 + attention)", "bound": "tensor", "achieved": pre_tf,
                  "peak": tf_peak, "unit": "TFLOP/s", "frac": pre_tf / tf_peak, "share_of_step": sm["prefill"] / step_ms},
@@ -388,12 +454,13 @@ def main():
             ],
         }
         if not args.no_cpu_baseline:
-            obj, kind = load_cpu_reference(model_dir)
+            obj, kind = load_cpu_reference(cfg, model_dir)
+            tokens = cpu_sample_tokens(cfg)
             tcpu = time.perf_counter()
-            a = cpu_reference_step(pr, texts[0], obj, kind, TOKENS)
+            a = cpu_reference_step(cfg, pr, texts[0], obj, kind, tokens)
             dcpu = time.perf_counter() - tcpu
             line["cpu_baseline"] = {"value": a / dcpu, "unit": "audio-s/s", "cores": torch.get_num_threads(),
-                                    "kind": kind, "sample": f"1 sentence ({TOKENS} tokens, batch 1), {dcpu:.1f} s of CPU work"}
+                                    "kind": kind, "sample": f"1 sentence ({tokens} tokens, batch 1), {dcpu:.1f} s of CPU work"}
         print(json.dumps(line))
     prompt.close()
     model.close()

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 
 namespace genie {
@@ -41,8 +43,33 @@ inline void check_launch(const char* what) {
 }
 
 // global kernel-launch counter (bench.py reports it as gpu_launches)
-extern unsigned long long g_launches;
-#define GENIE_LAUNCHED(name) do { ++::genie::g_launches; ::genie::check_launch(name); } while (0)
+extern std::atomic<unsigned long long> g_launches;
+// during stream capture nothing launches: the capturing thread points this at its own counter (kernels per replay)
+extern thread_local unsigned long long* t_capture_counter;
+#define GENIE_LAUNCHED(name)                                                         \
+  do {                                                                               \
+    if (::genie::t_capture_counter) ++*::genie::t_capture_counter; else ++::genie::g_launches; \
+    ::genie::check_launch(name);                                                     \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: one process may drive models
+// on several GPUs (ReplicaPool: one scheduler thread per GPU), so every launch site keeps one of these per kernel
+// instantiation and raises the limit on the CURRENT device the first time (or when a larger size is needed).
+struct DynSmemAttr {
+  static constexpr int MAX_DEV = 64;
+  std::atomic<size_t> set[MAX_DEV] = {};
+  std::mutex mu;
+  template <typename K> void ensure(K kernel, size_t smem) {
+    int dev = 0;
+    GENIE_CUDA(cudaGetDevice(&dev));
+    const bool tracked = dev >= 0 && dev < MAX_DEV;
+    if (tracked && smem <= set[dev].load(std::memory_order_acquire)) return;
+    std::lock_guard<std::mutex> lock(mu);
+    if (tracked && smem <= set[dev].load(std::memory_order_relaxed)) return;
+    GENIE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (tracked) set[dev].store(smem, std::memory_order_release);
+  }
+};
 
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch (decode step chain).  A kernel launched through launch_pdl may start while
@@ -52,8 +79,9 @@ extern unsigned long long g_launches;
 // loads of constant weights) overlaps the predecessor's tail.  Both are no-ops in a normal launch.
 // ---------------------------------------------------------------------------
 extern int g_pdl;          // GENIE_PDL=0 disables
-extern int g_pdl_now;      // cleared by the caller for launch sequences where it does not pay (batch <= 8 decode:
-                           // measured 58 -> 68 ms per 90 steps with it on)
+extern thread_local int g_pdl_now;   // cleared by the caller for launch sequences where it does not pay (batch <= 8
+                                    // decode: measured 58 -> 68 ms per 90 steps with it on); per host thread, as one
+                                    // scheduler thread per GPU may be issuing launch sequences at the same time
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

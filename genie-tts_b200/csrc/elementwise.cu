@@ -153,13 +153,15 @@ __global__ void decode_embed_kernel(float* out, const int* hist, int hist_ld, co
 __global__ void kv_scatter_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ kv_base,
                                   long long utt_stride, long long layer_off, long long v_off, int cap,
                                   const int* __restrict__ row_off, const int* __restrict__ dst_pos0,
-                                  const int* __restrict__ row2utt, int rows, const int* __restrict__ active) {
+                                  const int* __restrict__ row2utt, int rows, const int* __restrict__ active,
+                                  const int* __restrict__ slot_of) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over rows*1024/4 float4s
   if (i >= (long long)rows * 256) return;
   int r = (int)(i >> 8), c4 = (int)(i & 255);       // c4: float4 index within [K(512) | V(512)]
   int b = row2utt ? row2utt[r] : r;
   if (active && !active[b]) return;
   int pos = dst_pos0[b] + (row_off ? r - row_off[b] : 0);
+  if (slot_of) b = slot_of[b];
   int isv = c4 >> 7, col = (c4 & 127) * 4;          // col within 512
   int h = col >> 5, e = col & 31;
   float4 v = *reinterpret_cast<const float4*>(qkv + (long long)r * ld + 512 + isv * 512 + col);
@@ -168,15 +170,78 @@ __global__ void kv_scatter_kernel(const float* __restrict__ qkv, int ld, float* 
   *reinterpret_cast<float4*>(dst) = v;
 }
 
+__global__ void __launch_bounds__(256) prefill_bert_gather_kernel(float* __restrict__ bert, PrefillMeta pm,
+                                                                 const float* __restrict__ text_bert) {
+  const int r = blockIdx.x, b = pm.row2utt[r], i = r - pm.row_off[b];
+  if (i >= pm.lx[b]) return;                                   // audio row
+  const int lr = pm.lr[b];
+  const float* src = nullptr;
+  if (i < lr) { if (pm.ref_bert[b]) src = pm.ref_bert[b] + (long long)i * 1024; }
+  else if (text_bert) src = text_bert + (long long)(pm.txt_in_off[b] + i - lr) * 1024;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (src) v = *reinterpret_cast<const float4*>(src + threadIdx.x * 4);
+  *reinterpret_cast<float4*>(bert + (long long)(pm.txt_off[b] + i) * 1024 + threadIdx.x * 4) = v;
+}
+
+__global__ void __launch_bounds__(128) prefill_embed_kernel(float* __restrict__ x, PrefillMeta pm,
+                                                            const long long* __restrict__ text_seq,
+                                                            const float* __restrict__ proj,
+                                                            const float* __restrict__ proj_bias,
+                                                            const float* __restrict__ text_emb,
+                                                            const float* __restrict__ text_alpha, int text_vocab,
+                                                            const float* __restrict__ audio_emb,
+                                                            const float* __restrict__ audio_alpha,
+                                                            const float* __restrict__ div_term, int* err) {
+  const int r = blockIdx.x, b = pm.row2utt[r], i = r - pm.row_off[b];
+  const int lx = pm.lx[b];
+  float* out = x + (long long)r * 512;
+  for (int c = threadIdx.x; c < 512; c += 128) {
+    float v;
+    if (i < lx) {
+      const int lr = pm.lr[b];
+      long long id = i < lr ? pm.ref_seq[b][i] : text_seq[pm.txt_in_off[b] + i - lr];
+      if (id < 0 || id >= text_vocab) { if (err) *err = 2; id = 0; }
+      const float base = proj ? proj[(long long)(pm.txt_off[b] + i) * 512 + c] : proj_bias[c];
+      const float e = text_emb[id * 512 + c] + base;            // same association as the graph: (emb + bert) + PE
+      v = e + text_alpha[0] * pe_value(i + 1, c, div_term);
+    } else {
+      const int j = i - lx;
+      int tok = pm.prompt_tok[b][j];
+      if (tok < 0 || tok > 1024) { if (err) *err = 2; tok = 0; }
+      v = audio_emb[(long long)tok * 512 + c] + audio_alpha[0] * pe_value(j + 1, c, div_term);
+    }
+    out[c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(128) slot_init_kernel(const SlotInit* __restrict__ init,
+                                                        const int* const* __restrict__ prompt_tok, int* hist,
+                                                        int hist_ld, int* hist_len, int* kv_len, int* active,
+                                                        int* stop_step, SlotParams* params) {
+  const SlotInit in = init[blockIdx.x];
+  int* row = hist + (long long)in.slot * hist_ld;
+  const int* src = prompt_tok[blockIdx.x];
+  for (int i = threadIdx.x; i < hist_ld; i += 128) row[i] = i < in.hist_len ? src[i] : 0;
+  if (threadIdx.x == 0) {
+    hist_len[in.slot] = in.hist_len; kv_len[in.slot] = in.kv_len; active[in.slot] = 1; stop_step[in.slot] = -1;
+    params[in.slot] = in.p;
+  }
+}
+
 // ---- VITS helpers -------------------------------------------------------------
 __global__ void gather_rows_kernel(float* out, int ldo, const float* table, int C, const long long* idx,
-                                   int rows, int repeat) {
+                                   int rows, int repeat, int table_rows, int* err) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)rows * repeat * C) return;
   int c = (int)(i % C);
   long long ro = i / C;
   int r = (int)(ro / repeat);
-  out[ro * ldo + c] = table[idx[r] * C + c];
+  long long id = idx[r];
+  if (table_rows > 0 && (id < 0 || id >= table_rows)) {   // never read outside the table: flag (-> error) and clamp
+    if (err) *err = 2;
+    id = 0;
+  }
+  out[ro * ldo + c] = table[id * C + c];
 }
 
 __global__ void gated_act_kernel(const float* x, int ldx, float* y, int ldy, int H, int rows) {
@@ -390,16 +455,38 @@ void launch_decode_embed(float* out, const int* hist, int hist_ld, const int* hi
 }
 void launch_kv_scatter(const float* qkv, int ld, float* kv_base, long long utt_stride, long long layer_off,
                        long long v_off, int cap, const int* row_off, const int* dst_pos0, const int* row2utt,
-                       int rows, const int* active, cudaStream_t s) {
+                       int rows, const int* active, cudaStream_t s, const int* slot_of) {
   if (rows <= 0) return;
   kv_scatter_kernel<<<nblk((long long)rows * 256, 256), 256, 0, s>>>(qkv, ld, kv_base, utt_stride, layer_off, v_off,
-                                                                    cap, row_off, dst_pos0, row2utt, rows, active);
+                                                                    cap, row_off, dst_pos0, row2utt, rows, active,
+                                                                    slot_of);
   GENIE_LAUNCHED("kv_scatter");
 }
-void launch_gather_rows(float* out, int ldo, const float* table, int C, const long long* idx, int rows, int repeat,
-                        cudaStream_t s) {
+void launch_prefill_bert_gather(float* bert, const PrefillMeta& pm, const float* text_bert, int rows, cudaStream_t s) {
   if (rows <= 0) return;
-  gather_rows_kernel<<<nblk((long long)rows * repeat * C, 256), 256, 0, s>>>(out, ldo, table, C, idx, rows, repeat);
+  prefill_bert_gather_kernel<<<rows, 256, 0, s>>>(bert, pm, text_bert);
+  GENIE_LAUNCHED("prefill_bert_gather");
+}
+void launch_prefill_embed(float* x, const PrefillMeta& pm, const long long* text_seq, const float* proj,
+                          const float* proj_bias, const float* text_emb, const float* text_alpha, int text_vocab,
+                          const float* audio_emb, const float* audio_alpha, const float* div_term, int rows,
+                          int* err, cudaStream_t s) {
+  if (rows <= 0) return;
+  prefill_embed_kernel<<<rows, 128, 0, s>>>(x, pm, text_seq, proj, proj_bias, text_emb, text_alpha, text_vocab,
+                                            audio_emb, audio_alpha, div_term, err);
+  GENIE_LAUNCHED("prefill_embed");
+}
+void launch_slot_init(const SlotInit* init, int n, const int* const* prompt_tok, int* hist, int hist_ld, int* hist_len,
+                      int* kv_len, int* active, int* stop_step, SlotParams* params, cudaStream_t s) {
+  if (n <= 0) return;
+  slot_init_kernel<<<n, 128, 0, s>>>(init, prompt_tok, hist, hist_ld, hist_len, kv_len, active, stop_step, params);
+  GENIE_LAUNCHED("slot_init");
+}
+void launch_gather_rows(float* out, int ldo, const float* table, int C, const long long* idx, int rows, int repeat,
+                        cudaStream_t s, int table_rows, int* err) {
+  if (rows <= 0) return;
+  gather_rows_kernel<<<nblk((long long)rows * repeat * C, 256), 256, 0, s>>>(out, ldo, table, C, idx, rows, repeat,
+                                                                            table_rows, err);
   GENIE_LAUNCHED("gather_rows");
 }
 void launch_gated_act(const float* x, int ldx, float* y, int ldy, int H, int rows, cudaStream_t s) {

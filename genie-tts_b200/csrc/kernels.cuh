@@ -4,6 +4,17 @@
 
 namespace genie {
 
+// Per-slot decode parameters, resident in device memory: the captured decode-step graph reads them from here, so
+// it depends on neither a request's sampling configuration nor its seed (defaults = the constants baked into the
+// reference graphs, stage#[1780-1790]; top_p is an extension the graphs do not have, 1.0 = off).
+struct SlotParams {
+  int top_k; int greedy; int honour_stop;
+  int hist_max;                 // decoding stops once the history (prompt + generated) holds this many tokens
+  float temperature, penalty, top_p;
+  int utt;                      // Philox key part: index of the utterance within its admission call
+  unsigned long long seed;
+};
+
 
 // QKV split-K partials [nsplit][B][1536] (+ bias) -> q, append k/v at kv_len[b], attend over kv_len[b] + 1 tokens
 void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
@@ -28,9 +39,35 @@ void launch_decode_embed(float* out, const int* hist, int hist_ld, const int* hi
 
 // scatter K,V columns of qkv rows into the head-major cache:
 //   cache[b][layer][kv][h][pos][32], pos = dst_pos0[b] + (row - row_off[b])
+//   slot_of (optional): cache slab of utterance b is slot_of[b] instead of b
 void launch_kv_scatter(const float* qkv, int ld, float* kv_base, long long utt_stride, long long layer_off,
                        long long v_off, int cap, const int* row_off, const int* dst_pos0, const int* row2utt,
-                       int rows, const int* active, cudaStream_t s);
+                       int rows, const int* active, cudaStream_t s, const int* slot_of = nullptr);
+
+// ---- prefill input assembly for a ragged batch of newly admitted utterances (one launch each instead of
+// per-utterance copies): rows of utterance b are [row_off[b], row_off[b+1]) = Lr ref phones, Lt text phones
+// (together lx[b] text rows), Ly prompt tokens
+struct PrefillMeta {
+  const int* row2utt;            // [R]
+  const int* row_off;            // [n+1]
+  const int* txt_off;            // [n+1] offsets in text-row space (sum of lx)
+  const int* txt_in_off;         // [n]   offset of the utterance's text_seq / text_bert rows in the call's input
+  const int* lr; const int* lx;  // [n]
+  const long long* const* ref_seq;   // [n] device pointers (prompt)
+  const float* const* ref_bert;      // [n] device pointers or null
+  const int* const* prompt_tok;      // [n] device pointers
+};
+// bert[txt_off[b] + i, :] = ref_bert / text_bert row or zeros   (t2s_encoder: Concat(ref_bert, text_bert))
+void launch_prefill_bert_gather(float* bert, const PrefillMeta& pm, const float* text_bert, int rows, cudaStream_t s);
+// x[r, :] = Emb_text[id] + proj[txt row] (or bias) + alpha_t PE(i+1)  |  Emb_audio[tok] + alpha_a PE(j+1)
+void launch_prefill_embed(float* x, const PrefillMeta& pm, const long long* text_seq, const float* proj,
+                          const float* proj_bias, const float* text_emb, const float* text_alpha, int text_vocab,
+                          const float* audio_emb, const float* audio_alpha, const float* div_term, int rows,
+                          int* err, cudaStream_t s);
+// per-slot state of newly admitted utterances: history row (prompt tokens, rest zero), lengths, flags, parameters
+struct SlotInit { int slot, kv_len, hist_len, pad; SlotParams p; };
+void launch_slot_init(const SlotInit* init, int n, const int* const* prompt_tok, int* hist, int hist_ld, int* hist_len,
+                      int* kv_len, int* active, int* stop_step, SlotParams* params, cudaStream_t s);
 
 // decode-step single-shot tcgen05 GEMM (tc_small_gemm.cu): raw split-K partials of
 // act_in(sum_s x_s + a_bias) . W^T for rows <= 128, K multiple of 256
@@ -65,29 +102,32 @@ struct PersistentStep {
   int B = 1, nch = 1; float scale = 1.f;
 };
 int persistent_step_chunks(int B, int grid);
+bool persistent_step_fits(int B, int grid);
 void launch_t2s_step_persistent(const PersistentStep& a, int grid, cudaStream_t s);
 
 struct SamplerArgs {
-  const float* logits;     // [B, ld]
+  const float* logits;     // [B, ld], row b
   int ld;
-  int* hist;               // [B, hist_ld] token history (prompt + generated)
+  int* hist;               // [slots, hist_ld] token history (prompt + generated)
   int hist_ld;
-  int* hist_len;           // [B]
-  int* kv_len;             // [B] incremented when advance_kv
-  int* active;             // [B] cleared on stop (when honour_stop)
-  int* stop_step;          // [B] step index at which stop fired (or -1)
+  int* hist_len;           // [slots]
+  int* kv_len;             // [slots] incremented when advance_kv
+  int* active;             // [slots] cleared on stop (when honour_stop) or when the budget hist_max is reached
+  int* stop_step;          // [slots] history length at which the stop flag fired (or -1)
+  const SlotParams* params;   // [slots]
+  const int* slot_map;     // row b -> slot (prefill of newly admitted utterances); null = identity (decode)
   int B;
-  int utt_base;            // index of row 0 in the whole batch (Philox key): a split batch samples like the whole one
-  int top_k; float temperature; float penalty;
-  int greedy; unsigned long long seed; int step;
-  int honour_stop; int advance_kv; int check_stop;
-  float* dbg_noise;        // optional [B,1025] externally supplied noise (tests)
+  int advance_kv; int check_stop;
+  const float* dbg_noise;  // optional [B,1025] externally supplied noise (tests)
+  int dbg_no_append;       // tests: write the token to dbg_tokens[b] instead of appending to the history
+  int* dbg_tokens; int* dbg_stop;
 };
 void launch_sampler(const SamplerArgs& a, cudaStream_t s);
 
 // ---- VITS helpers (channels-last fp32)
+// out[r*repeat + j, :] = table[idx[r], :]; table_rows > 0: ids outside [0, table_rows) set *err = 2 and read row 0
 void launch_gather_rows(float* out, int ldo, const float* table, int C, const long long* idx, int rows, int repeat,
-                        cudaStream_t s);   // out[r*repeat + j, :] = table[idx[r], :]
+                        cudaStream_t s, int table_rows = 0, int* err = nullptr);
 void launch_gated_act(const float* x, int ldx, float* y, int ldy, int H, int rows, cudaStream_t s);  // tanh(a)*sigmoid(b)
 void launch_glu_residual(const float* y2, int ld2, float* x, int ldx, int H, int rows, cudaStream_t s); // x += a*sigmoid(b)
 void launch_flip_channels(const float* x, float* y, int C, int rows, cudaStream_t s);

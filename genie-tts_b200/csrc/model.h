@@ -5,6 +5,7 @@
 #include "../../include/genie_b200.h"
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -75,19 +76,25 @@ struct Workspace {
   unsigned long long generation = 0;   // bumped whenever any buffer moves (invalidates captured graphs)
 };
 
-struct Model {
+// Device allocations holding a model's weights.  Shared (ref-counted) by the model handle and every execution
+// context cloned from it (genie_context_create): the weights are freed when the last of them is destroyed.
+struct WeightOwner {
   int device = 0;
-  cudaStream_t stream = nullptr;
-  // the decode-step graph runs the batch as up to 4 independent branches (contiguous utterance ranges) on
-  // their own streams: every decode kernel is latency-bound, so the branches overlap
-  cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
-  int decode_split_min = 64;          // batches >= this are split; decode_branches = number of branches
-  int decode_branches = 2;
+  unsigned long long uid = 0;          // identity of the weight set (prompts remember it; never reused)
+  std::vector<void*> owned;
+  ~WeightOwner() { cudaSetDevice(device); for (void* p : owned) cudaFree(p); }
+};
+
+// Everything that is immutable after genie_model_finalize: plain pointers into the WeightOwner's allocations and
+// architecture constants.  Copyable: a context is a copy of this plus its own execution state.
+struct ModelWeights {
+  int device = 0;
   bool finalized = false, v2pp = false;
+  std::shared_ptr<WeightOwner> owner;
   std::unordered_map<std::string, RawTensor> raw[4];
-  std::vector<void*> owned;           // device allocations owned by the model
   size_t weight_bytes = 0;
+  int text_vocab = 732;               // rows of the phoneme embedding tables (input-id validation)
+  int vits_text_vocab = 732;
 
   // constants
   float* div_term = nullptr;          // [256]
@@ -117,35 +124,52 @@ struct Model {
   MelStyle ref_enc;                   // V2: vits ref_enc.*; V2ProPlus: prompt_encoder ref_enc.*
   Linear sv_emb, ge_to512; const float* prelu = nullptr;
   float* dft = nullptr;               // [1408, 2048]
+  // persistent decode step (batch <= skinny_max_rows): per-layer pointer table
+  void* step_layers_dev = nullptr; int num_sms = 0;
+};
+
+struct Model : ModelWeights {
+  // ---- execution state: one per handle (a context cloned from a model has its own)
+  cudaStream_t stream = nullptr;
+  bool stream_owned = true;           // false: bound to a caller-owned stream (genie_set_stream / genie_context_create)
+  // the decode-step graph runs the batch as up to 4 independent branches (contiguous utterance ranges) on
+  // their own streams: every decode kernel is latency-bound, so the branches overlap
+  cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
+  int decode_split_min = 64;          // batches >= this are split; decode_branches = number of branches
+  int decode_branches = 2;
+  std::vector<void*> ctx_owned;       // device allocations of this handle (error flag, barrier words)
+  std::mutex mu;                      // entry points of one handle are serialised (one scheduler thread per GPU
+                                      // is the intended use; a second thread waits instead of corrupting state)
 
   Workspace ws;
-  // decode-step CUDA graph cache
-  cudaGraphExec_t step_graph = nullptr; int step_graph_B = 0; unsigned long long step_graph_gen = 0;
-  int step_graph_cap = 0; int step_graph_flags = 0; int step_graph_hist_ld = 0;
-  unsigned long long step_graph_seed = 0; float step_graph_temp = 0.f, step_graph_pen = 0.f;
-  unsigned long long step_graph_launches = 0;   // kernels per replay (counted at capture)
+  unsigned long long options_gen = 0; // bumped by genie_set_option for anything baked into a captured graph
   int use_graph = 1;
   // tcgen05 path: 0 = exact SIMT everywhere; T2S always runs x_hi+x_lo against fp16-exact weights;
   // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo
   int use_tc = 1, tc_vits = 1, tc_min_rows = 9, skinny_max_rows = 8;
   int fuse_pairs = 1;                  // narrow resblock pairs as one kernel (tc_pair_conv.cu)
-  int* tc_err = nullptr;
-  // persistent decode step (batch <= skinny_max_rows): per-layer pointer table, barrier words, grid size
-  void* step_layers_dev = nullptr; unsigned* step_sync = nullptr; int num_sms = 0;
+  int* tc_err = nullptr;               // device flag: 1 = tcgen05 mbarrier timeout, 2 = input id out of range
+  unsigned* step_sync = nullptr;       // persistent step: [0] barrier counter, [1] barrier-timeout flag
   int persistent_step = 4;             // largest batch that takes the persistent step (0 = off, <= 8)
+  int persistent_ok = -1;              // -1 unknown, 0 the device cannot hold the grid co-resident, 1 ok
   // debug
   bool record_logits = false, keep = false;
   std::vector<float> logits_host;
   std::map<std::string, std::vector<float>> kept;
   float timing[12] = {0};      // [8] decode-attention us / launch, [9] its KV MB / launch (time_attention option)
-  std::shared_ptr<void> t2s_session;   // batch between t2s_prefill and t2s_read (t2s.cu)
+  std::shared_ptr<void> t2s_session;   // slot pool of the T2S stage (t2s.cu): batch in flight / continuous batching
+  std::shared_ptr<void> t2s_graphs;    // captured decode steps (t2s.cu)
   int time_attention = 0;      // > 0: after t2s_generate replay the fused decode attention this many times per layer
 
+  Model() = default;
+  Model(const Model&) = delete; Model& operator=(const Model&) = delete;
   ~Model();
 };
 
 struct Prompt {
-  Model* model = nullptr;
+  int device = 0;
+  unsigned long long model_uid = 0;   // WeightOwner::uid of the model it was built for (contexts share it)
   int Lr = 0, Ly = 0, ge_dim = 0;
   bool has_bert = false;
   long long* ref_seq = nullptr;       // device int64 [Lr]
@@ -157,7 +181,8 @@ struct Prompt {
   float* flow_cond = nullptr;         // device [4][1536]
   float* dec_cond = nullptr;          // device [C0]
   std::vector<void*> owned;
-  ~Prompt() { for (void* p : owned) cudaFree(p); }
+  // never touches the model: a prompt may outlive it (the handle's owner decides the order)
+  ~Prompt() { if (!owned.empty()) cudaSetDevice(device); for (void* p : owned) cudaFree(p); }
 };
 
 // weights.cu
@@ -166,7 +191,8 @@ void model_finalize(Model& m);
 void prompt_build(Model& m, Prompt& p, const int64_t* ref_seq, int Lr, const float* ref_bert, const float* ssl, int Ts,
                   const float* ref_audio, int n_audio, const float* sv_emb, const float* ge_in, int ge_dim,
                   const float* ge_adv_in);
-struct SamplingCfg { int top_k; float temperature, penalty; int greedy; unsigned long long seed; int max_steps, fixed_steps; };
+struct SamplingCfg { int top_k; float temperature, penalty, top_p; int greedy; unsigned long long seed; int max_steps, fixed_steps; };
+// legacy batch API: one batch admitted at once into a pool sized for it
 void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
                  const float* text_bert, const SamplingCfg& cfg, int io_dev);
 int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_active, int* steps_done);
@@ -174,6 +200,15 @@ void t2s_read(Model& m, int io_dev, int64_t* y, int y_ld, int* y_len, int* idx);
 int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
                  const float* text_bert, const SamplingCfg& cfg, const volatile int* cancel, int io_dev,
                  int64_t* y, int y_ld, int* y_len, int* idx);
+// continuous batching: a pool of decode slots with fixed per-slot KV capacity
+void t2s_pool_create(Model& m, int n_slots, int kv_cap, int max_prompt_tokens, int max_steps);
+void t2s_pool_admit(Model& m, int n, const int* slots, Prompt* const* prompts, const int64_t* text_seq,
+                    const int* text_len, const float* text_bert, const SamplingCfg* cfgs);
+int t2s_pool_step(Model& m, int n_steps, int* n_active);
+void t2s_pool_poll(Model& m, int* state, int* n_generated, int n);
+void t2s_pool_read(Model& m, int slot, int64_t* y, int y_cap, int* y_len, int* idx);
+void t2s_pool_release(Model& m, int slot);
+void t2s_pool_info(Model& m, int* n_slots, int* kv_cap, int* hist_ld);
 void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
                  const int64_t* sem, const int* sem_len, const float* zp_noise, unsigned long long seed,
                  float noise_scale, int io_dev, float* audio, int* audio_len);

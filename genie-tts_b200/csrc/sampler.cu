@@ -49,14 +49,17 @@ __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
   pdl_wait();      // logits come from the predecessor GEMM
   __shared__ float raw[V];
   __shared__ float lg[V];
+  __shared__ float pr[V];
   __shared__ unsigned char taken[V];
   __shared__ ArgVal sh_av[8];
   __shared__ float sh_f[8];
   const int b = blockIdx.x, tid = threadIdx.x;
-  if (a.active && !a.active[b]) return;
+  const int slot = a.slot_map ? a.slot_map[b] : b;
+  if (a.active && !a.active[slot]) return;
+  const SlotParams P = a.params[slot];
   const float* lrow = a.logits + (long long)b * a.ld;
-  int* hist = a.hist + (long long)b * a.hist_ld;
-  const int n = a.hist_len[b];
+  int* hist = a.hist + (long long)slot * a.hist_ld;
+  const int n = a.hist_len[slot];
 
   for (int i = tid; i < V; i += 256) { float v = lrow[i]; raw[i] = v; lg[i] = v; taken[i] = 0; }
   __syncthreads();
@@ -69,14 +72,38 @@ __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
   for (int i = tid; i < n; i += 256) {
     int t = hist[i];
     float s = raw[t];
-    lg[t] = (s < 0.f) ? s * a.penalty : s / a.penalty;
+    lg[t] = (s < 0.f) ? s * P.penalty : s / P.penalty;
   }
   __syncthreads();
-  for (int i = tid; i < V; i += 256) lg[i] = lg[i] / a.temperature;
+  // top-p (extension; absent from the reference graphs, off at 1.0): in descending order of the penalised logits
+  // drop every token whose inclusive cumulative probability exceeds top_p, except the first
+  if (P.top_p > 0.f && P.top_p < 1.f) {
+    loc.v = -CUDART_INF_F; loc.i = V;
+    for (int i = tid; i < V; i += 256) { ArgVal c; c.v = lg[i]; c.i = i; loc = better(loc, c); }
+    const ArgVal top = block_argmax(loc, sh_av);
+    float part = 0.f;
+    for (int i = tid; i < V; i += 256) { float e = expf(lg[i] - top.v); pr[i] = e; part += e; }
+    const float denom = block_sum(part, sh_f);
+    __syncthreads();
+    for (int i = tid; i < V; i += 256) {
+      const float li = lg[i];
+      float cum = 0.f;
+      for (int j = 0; j < V; ++j) {
+        const float lj = lg[j];
+        if (lj > li || (lj == li && j <= i)) cum += pr[j];
+      }
+      taken[i] = (cum / denom > P.top_p && i != top.i) ? 2 : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < V; i += 256) if (taken[i]) { lg[i] = -CUDART_INF_F; taken[i] = 0; }
+    __syncthreads();
+  }
+  for (int i = tid; i < V; i += 256) lg[i] = lg[i] / P.temperature;
   __syncthreads();
   // k-th largest value counting duplicates: peel the maximum top_k times
   float kth = 0.f;
-  for (int r = 0; r < a.top_k; ++r) {
+  const int top_k = P.top_k < 1 ? 1 : (P.top_k > V ? V : P.top_k);
+  for (int r = 0; r < top_k; ++r) {
     loc.v = -CUDART_INF_F; loc.i = V;
     for (int i = tid; i < V; i += 256)
       if (!taken[i]) { ArgVal c; c.v = lg[i]; c.i = i; loc = better(loc, c); }
@@ -98,26 +125,30 @@ __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
   // token = argmax(probs / noise), first index on ties (ArgMax select_last_index=0)
   loc.v = -CUDART_INF_F; loc.i = V;
   for (int i = tid; i < V; i += 256) {
-    float pr = lg[i] / denom;
+    float p = lg[i] / denom;
     float q = 1.f;
-    if (!a.greedy) q = a.dbg_noise ? a.dbg_noise[(long long)b * V + i]
-                                   : philox_normal(a.seed, (uint32_t)(b + a.utt_base), (uint32_t)n, (uint32_t)i);
-    ArgVal c; c.v = pr / q; c.i = i;
+    if (!P.greedy) q = a.dbg_noise ? a.dbg_noise[(long long)b * V + i]
+                                   : philox_normal(P.seed, (uint32_t)P.utt, (uint32_t)n, (uint32_t)i);
+    ArgVal c; c.v = p / q; c.i = i;
     loc = better(loc, c);
   }
   const ArgVal tokv = block_argmax(loc, sh_av);
   if (tid == 0) {
     const int tok = tokv.i;
-    hist[n] = tok;
-    a.hist_len[b] = n + 1;
-    if (a.advance_kv) a.kv_len[b] += 1;
-    if (a.check_stop) {
-      const bool stop = (raw_best.i == EOS) || (tok == EOS);
-      if (stop && a.stop_step[b] < 0) {
-        a.stop_step[b] = n;   // history length before this token (graph-replay safe step id)
-        if (a.honour_stop) a.active[b] = 0;
-      }
+    const bool stop = (raw_best.i == EOS) || (tok == EOS);
+    if (a.dbg_no_append) {
+      a.dbg_tokens[b] = tok;
+      if (a.dbg_stop) a.dbg_stop[b] = stop ? 1 : 0;
+      return;
     }
+    hist[n] = tok;
+    a.hist_len[slot] = n + 1;
+    if (a.advance_kv) a.kv_len[slot] += 1;
+    if (a.check_stop && stop && a.stop_step[slot] < 0) {
+      a.stop_step[slot] = n;   // history length before this token (graph-replay safe step id)
+      if (P.honour_stop) a.active[slot] = 0;
+    }
+    if (n + 1 >= P.hist_max) a.active[slot] = 0;   // loop bound (Inference.py:95) / fixed token budget
   }
 }
 
@@ -125,7 +156,7 @@ __global__ void __launch_bounds__(256) sampler_kernel(SamplerArgs a) {
 
 void launch_sampler(const SamplerArgs& a, cudaStream_t s) {
   if (a.B <= 0) return;
-  GENIE_CHECK(a.top_k >= 1 && a.top_k <= V, "sampler: bad top_k");
+  GENIE_CHECK(a.params != nullptr, "sampler: no per-slot parameters");
   launch_pdl(sampler_kernel, dim3(a.B), dim3(256), 0, s, a);
   GENIE_LAUNCHED("sampler");
 }

@@ -1,7 +1,13 @@
-// T2S GPT stage: text encode (t2s_encoder#[49-83]) -> prefill
-// (t2s_first_stage_decoder) -> decode loop (t2s_stage_decoder x <=500,
-// reference src/genie_tts/Core/Inference.py:76-106) for a ragged batch of
-// independent utterances.  KV cache: fp32, head-major, appended in place.
+// T2S GPT stage: text encode (t2s_encoder#[49-83]) -> prefill (t2s_first_stage_decoder) -> decode loop
+// (t2s_stage_decoder x <=500, reference src/genie_tts/Core/Inference.py:76-106) for independent utterances.
+//
+// The stage is organised as a POOL OF DECODE SLOTS.  A slot owns a KV slab (fp32, head-major, appended in place),
+// a token-history row and its decode parameters (SlotParams, in device memory).  Utterances are ADMITTED into free
+// slots (the admission runs their prefill as one ragged batch and writes K/V straight into the slot slabs), every
+// decode step advances all active slots at once (one CUDA-graph replay over the first `rows` slots; stopped / free
+// slots exit early in every kernel), finished slots are read and released.  The batch API of the reference-facing
+// path (genie_t2s_prefill / decode_steps / read / generate) is the special case "pool sized for this batch, all
+// utterances admitted at once"; the continuous-batching server admits and releases slots while others decode.
 #include "model.h"
 #include <algorithm>
 #include <cmath>
@@ -12,21 +18,6 @@ namespace {
 
 constexpr int D = 512, NL = 24, H = 16, V = 1025;
 
-struct Batch {
-  int B = 0;
-  std::vector<int> Lr, Lt, Ly, Lx, S, row_off, txt_off;
-  int rows = 0, txt_rows = 0, maxS = 0, cap = 0, hist_ld = 0;
-};
-
-__global__ void fill_rows_kernel(float* x, const float* bias, int rows) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)rows * 512) return;
-  x[i] = bias ? bias[i & 511] : 0.f;
-}
-__global__ void init_hist_kernel(int* hist, int hist_ld, const int* const* prompt_ptrs, const int* ly, int B) {
-  int b = blockIdx.x;
-  for (int i = threadIdx.x; i < ly[b]; i += blockDim.x) hist[(long long)b * hist_ld + i] = prompt_ptrs[b][i];
-}
 __global__ void hist_to_i64_kernel(const int* hist, int hist_ld, const int* hist_len, long long* y, int y_ld, int B) {
   int b = blockIdx.x;
   int n = hist_len[b];
@@ -35,23 +26,40 @@ __global__ void hist_to_i64_kernel(const int* hist, int hist_ld, const int* hist
 }
 
 struct StepBufs {
+  unsigned long long key = 0;   // mix of the buffer addresses below (what a captured step bakes)
   float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part, *part2, *ppart;
   int *hist, *hist_len, *kv_len, *active, *stop_step;
+  const SlotParams* params;
   float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld; long long part_stride;
-  int utt_base;   // first utterance of this branch within the batch
 };
 
-// State of one batch between genie_t2s_prefill and genie_t2s_read: everything the decode loop and the result
-// read-out need.  The buffers live in the model's workspace, so a model has one live session at a time.
+struct SlotHost { int in_use = 0, Ly = 0, S = 0, max_steps = 0, honour = 1; };
+
+// captured decode steps, keyed by everything the graph bakes: row count, slab geometry, buffer addresses
+// (workspace generation) and the path-selection options
+struct StepGraph {
+  int rows = 0, cap = 0, hist_ld = 0; unsigned long long gen = 0, opt = 0;
+  cudaGraphExec_t exec = nullptr; unsigned long long launches = 0; unsigned long long last_use = 0;
+};
+struct GraphCache {
+  std::vector<StepGraph> e; unsigned long long tick = 0;
+  ~GraphCache() { for (auto& g : e) if (g.exec) cudaGraphExecDestroy(g.exec); }
+};
+
+// The slot pool of one model handle.  Buffers live in the handle's workspace (grow-only, named), so a handle has
+// one pool at a time: creating a new one (any batch-API prefill does) drops the previous one.
 struct T2SSession {
-  Batch bt; SamplingCfg cfg{}; int B = 0, max_steps = 0;
-  float* LOGITS = nullptr; int* HIST = nullptr; long long* Y64 = nullptr;
+  int n_slots = 0, cap = 0, hist_ld = 0;
+  bool pool_mode = false;
+  float* LOGITS = nullptr; float* LOGITS_PRE = nullptr; int* HIST = nullptr; long long* Y64 = nullptr;
   int *d_histlen = nullptr, *d_kvlen = nullptr, *d_active = nullptr, *d_stop = nullptr;
+  SlotParams* d_params = nullptr;
   StepBufs w{};
-  bool can_graph = false;
-  int steps_done = 0;
+  std::vector<SlotHost> slots;
+  // batch API bookkeeping
+  int B = 0, max_steps = 0, steps_done = 0, fixed = 0;
   bool all_stopped = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;                       // prefill
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;                       // last admission (prefill)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> decode_spans;  // one pair per decode_steps call
   ~T2SSession() {
     if (ev0) cudaEventDestroy(ev0);
@@ -61,43 +69,39 @@ struct T2SSession {
 };
 
 T2SSession& session_of(Model& m) {
-  GENIE_CHECK(m.t2s_session != nullptr, "no T2S batch in flight: call genie_t2s_prefill first");
+  GENIE_CHECK(m.t2s_session != nullptr, "no T2S batch in flight: call genie_t2s_prefill / genie_t2s_pool_create first");
   return *static_cast<T2SSession*>(m.t2s_session.get());
 }
+GraphCache& graphs_of(Model& m) {
+  if (!m.t2s_graphs) m.t2s_graphs = std::make_shared<GraphCache>();
+  return *static_cast<GraphCache*>(m.t2s_graphs.get());
+}
 
-void record_step_logits(Model& m, const T2SSession& S) {
+void record_logits_rows(Model& m, const float* dev, int rows) {
   if (!m.record_logits) return;
   std::vector<float>& rec = m.logits_host;
   const size_t o = rec.size();
-  rec.resize(o + (size_t)S.B * V);
-  GENIE_CUDA(cudaMemcpyAsync(rec.data() + o, S.LOGITS, (size_t)S.B * V * 4, cudaMemcpyDeviceToHost, m.stream));
+  rec.resize(o + (size_t)rows * V);
+  GENIE_CUDA(cudaMemcpyAsync(rec.data() + o, dev, (size_t)rows * V * 4, cudaMemcpyDeviceToHost, m.stream));
   GENIE_CUDA(cudaStreamSynchronize(m.stream));
 }
 
-// pointer table / barrier words of the persistent step (allocated outside any stream capture)
+// barrier words of the persistent step (per handle; allocated outside any stream capture) and the residency check
 void ensure_persistent_step(Model& m) {
-  if (!m.step_layers_dev) {
-    std::vector<StepLayerPtrs> hl(NL);
-    for (int l = 0; l < NL; ++l) {
-      const T2SLayer& L = m.layers[l];
-      hl[l] = StepLayerPtrs{reinterpret_cast<const __half*>(L.qkv.w), reinterpret_cast<const __half*>(L.out.w),
-                            reinterpret_cast<const __half*>(L.ff1.w), reinterpret_cast<const __half*>(L.ff2.w),
-                            L.qkv.b, L.out.b, L.ff1.b, L.ff2.b, L.ln1_g, L.ln1_b, L.ln2_g, L.ln2_b};
-    }
-    StepLayerPtrs* d = nullptr;
-    GENIE_CUDA(cudaMalloc(&d, sizeof(StepLayerPtrs) * NL));
-    GENIE_CUDA(cudaMemcpy(d, hl.data(), sizeof(StepLayerPtrs) * NL, cudaMemcpyHostToDevice));
-    m.owned.push_back(d);
-    m.step_layers_dev = d;
+  if (!m.step_sync) {
     GENIE_CUDA(cudaMalloc(&m.step_sync, 2 * sizeof(unsigned)));
     GENIE_CUDA(cudaMemset(m.step_sync, 0, 2 * sizeof(unsigned)));
-    m.owned.push_back(m.step_sync);
-    GENIE_CUDA(cudaDeviceGetAttribute(&m.num_sms, cudaDevAttrMultiProcessorCount, m.device));
+    m.ctx_owned.push_back(m.step_sync);
+  }
+  if (m.persistent_ok < 0) {
+    // one CTA per SM must be co-resident for the device-wide barrier; the launch itself is cooperative
+    // (t2s_persistent.cu), this check only decides whether the path is offered at all on this device
+    m.persistent_ok = persistent_step_fits(8, m.num_sms) ? 1 : 0;
   }
 }
 
 // one decode step for every active utterance (stage#[12-1821])
-void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
+void decode_step(Model& m, const StepBufs& w, int B) {
   cudaStream_t s = m.stream;
   struct PdlScope { int prev; explicit PdlScope(int on) : prev(g_pdl_now) { g_pdl_now = on; } ~PdlScope() { g_pdl_now = prev; } };
   const PdlScope pdl_scope(B > m.skinny_max_rows ? 1 : 0);
@@ -105,7 +109,8 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   const float scale = 1.0f / std::sqrt(32.0f);
   // measured (90 steps): batch 1 / 2 / 4 / 8 = 37 / 43 / 53 / 77 ms persistent vs 58 / - / 60 / 70 ms kernel chain
   const bool persistent = m.persistent_step && B <= m.persistent_step && B <= m.skinny_max_rows && m.layers[0].qkv.w_f16 &&
-                          m.predict.w_f16 && w.ppart != nullptr && m.step_layers_dev != nullptr;
+                          m.predict.w_f16 && w.ppart != nullptr && m.step_layers_dev != nullptr && m.step_sync != nullptr &&
+                          m.persistent_ok == 1;
   if (persistent) {
     // batch <= 8: all 24 layers + logits in one resident kernel (t2s_persistent.cu)
     PersistentStep a;
@@ -176,52 +181,116 @@ void decode_step(Model& m, const StepBufs& w, int B, const SamplingCfg& cfg) {
   if (!persistent) run_linear(m, m.predict, w.h, D, w.logits, V, B);
   SamplerArgs a{};
   a.logits = w.logits; a.ld = V; a.hist = w.hist; a.hist_ld = w.hist_ld; a.hist_len = w.hist_len;
-  a.kv_len = w.kv_len; a.active = w.active; a.stop_step = w.stop_step; a.B = B; a.utt_base = w.utt_base;
-  a.top_k = cfg.top_k; a.temperature = cfg.temperature; a.penalty = cfg.penalty; a.greedy = cfg.greedy;
-  a.seed = cfg.seed; a.step = 0; a.honour_stop = cfg.fixed_steps > 0 ? 0 : 1; a.advance_kv = 1; a.check_stop = 1;
-  a.dbg_noise = nullptr;
+  a.kv_len = w.kv_len; a.active = w.active; a.stop_step = w.stop_step; a.params = w.params; a.slot_map = nullptr;
+  a.B = B; a.advance_kv = 1; a.check_stop = 1;
   launch_sampler(a, s);
 }
 
-}  // namespace
 
-// encoder + first-stage graph for a batch: embeddings, 24 prefill layers into the KV cache, first sampled token;
-// leaves the decode-step buffers and graph ready (Inference.py:76-93)
-void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len_in,
-                 const float* text_bert, const SamplingCfg& cfg, int io_dev) {
+SlotParams slot_params(const SamplingCfg& c, int Ly, int utt) {
+  SlotParams p{};
+  p.top_k = c.top_k; p.greedy = c.greedy; p.honour_stop = c.fixed_steps > 0 ? 0 : 1;
+  const int steps = c.fixed_steps > 0 ? c.fixed_steps : c.max_steps;
+  p.hist_max = Ly + 1 + steps;
+  p.temperature = c.temperature; p.penalty = c.penalty; p.top_p = c.top_p; p.utt = utt; p.seed = c.seed;
+  return p;
+}
+
+// (re)build the pool of a handle: per-slot state, KV slabs and decode-step buffers for n_slots slots of kv_cap tokens
+T2SSession& pool_build(Model& m, int n_slots, int kv_cap, int hist_ld, bool pool_mode) {
   GENIE_CHECK(m.finalized, "model not finalized");
-  GENIE_CHECK(B > 0, "empty batch");
+  GENIE_CHECK(n_slots > 0 && kv_cap > 0 && hist_ld > 0, "bad pool geometry");
+  GENIE_CUDA(cudaSetDevice(m.device));
+  m.t2s_session.reset();
+  std::shared_ptr<T2SSession> sp = std::make_shared<T2SSession>();
+  T2SSession& S = *sp;
+  S.n_slots = n_slots; S.cap = (kv_cap + 15) / 16 * 16; S.hist_ld = hist_ld; S.pool_mode = pool_mode;
+  S.slots.assign(n_slots, SlotHost{});
+  Workspace& ws = m.ws;
+  const int B = n_slots;
+  S.LOGITS = ws.get<float>("t2s.logits", (size_t)B * V);
+  S.HIST = ws.get<int>("t2s.hist", (size_t)B * hist_ld);
+  S.Y64 = ws.get<long long>("t2s.y64", (size_t)B * hist_ld);
+  S.d_histlen = ws.get<int>("t2s.slot.histlen", B); S.d_kvlen = ws.get<int>("t2s.slot.kvlen", B);
+  S.d_active = ws.get<int>("t2s.slot.active", B); S.d_stop = ws.get<int>("t2s.slot.stop", B);
+  S.d_params = ws.get<SlotParams>("t2s.slot.params", B);
+  // KV cache [slot][layer][K|V][H][cap][32] fp32
+  const long long head_sz = (long long)S.cap * 32, v_off = H * head_sz, layer_stride = 2 * v_off,
+                  utt_stride = NL * layer_stride;
+  StepBufs& w = S.w;
+  w = StepBufs{};
+  w.kv = ws.get<float>("t2s.kv", (size_t)B * utt_stride);
+  w.h = ws.get<float>("t2s.step.h", (size_t)B * D); w.qkv = ws.get<float>("t2s.step.qkv", (size_t)B * 3 * D);
+  w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
+  w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
+  w.part = ws.get<float>("t2s.step.part", (size_t)8 * B * D);
+  w.part2 = ws.get<float>("t2s.step.part2", (size_t)8 * B * D);
+  w.ppart = ws.get<float>("t2s.step.ppart", (size_t)std::max(B, 8) * 16 * 8 * 36);
+  w.part_stride = (long long)B * D;
+  w.logits = S.LOGITS; w.hist = S.HIST; w.hist_len = S.d_histlen; w.kv_len = S.d_kvlen; w.active = S.d_active;
+  w.stop_step = S.d_stop; w.params = S.d_params;
+  w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off; w.cap = S.cap; w.hist_ld = hist_ld;
+  {
+    const void* ptrs[] = {w.h, w.qkv, w.att, w.tmp, w.h1, w.ff, w.logits, w.part, w.part2, w.ppart, w.hist, w.hist_len,
+                          w.kv_len, w.active, w.stop_step, w.params, w.kv};
+    unsigned long long k = 1469598103934665603ull;
+    for (const void* q : ptrs) { k ^= (unsigned long long)reinterpret_cast<uintptr_t>(q); k *= 1099511628211ull; }
+    w.key = k;
+  }
+  cudaStream_t s = m.stream;
+  // free slots must read as inactive; rows of free slots flow through the GEMMs, so start them finite
+  GENIE_CUDA(cudaMemsetAsync(S.d_active, 0, B * sizeof(int), s));
+  GENIE_CUDA(cudaMemsetAsync(S.d_histlen, 0, B * sizeof(int), s));
+  GENIE_CUDA(cudaMemsetAsync(S.d_kvlen, 0, B * sizeof(int), s));
+  if (pool_mode) {
+    GENIE_CUDA(cudaMemsetAsync(w.h, 0, (size_t)B * D * 4, s));
+    GENIE_CUDA(cudaMemsetAsync(w.att, 0, (size_t)B * D * 4, s));
+    GENIE_CUDA(cudaMemsetAsync(w.h1, 0, (size_t)B * D * 4, s));
+    GENIE_CUDA(cudaMemsetAsync(w.part, 0, (size_t)8 * B * D * 4, s));
+    GENIE_CUDA(cudaMemsetAsync(w.part2, 0, (size_t)8 * B * D * 4, s));
+  }
+  if (m.persistent_step > 0) ensure_persistent_step(m);
+  m.t2s_session = sp;
+  return S;
+}
+
+// Admission = encoder + first-stage graph (Inference.py:76-93) for n new utterances as one ragged batch: embeddings,
+// 24 prefill layers writing K/V into the slots' slabs, first sampled token appended to the slots' histories.
+void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* prompts, const int64_t* text_seq,
+           const int* text_len, const float* text_bert, const SamplingCfg* cfgs, int n_cfg, int io_dev) {
+  GENIE_CHECK(n > 0, "empty batch");
   cudaStream_t s = m.stream;
   GENIE_CUDA(cudaSetDevice(m.device));
-  const int max_steps = cfg.fixed_steps > 0 ? cfg.fixed_steps : cfg.max_steps;
-  m.t2s_session.reset();
-  std::shared_ptr<T2SSession> sess_ptr = std::make_shared<T2SSession>();
-  T2SSession& S = *sess_ptr;
-  S.cfg = cfg; S.B = B; S.max_steps = max_steps;
-
-  // ---- text lengths (device-resident payload: lengths are still host metadata)
-  std::vector<int> text_len(text_len_in, text_len_in + B);
-  Batch& bt = S.bt; bt.B = B;
-  bt.row_off.push_back(0); bt.txt_off.push_back(0);
+  // ---- geometry
+  std::vector<int> Lr(n), Lt(n), Ly(n), Lx(n), Sx(n), slot(n), row_off(n + 1, 0), txt_off(n + 1, 0), txt_in_off(n + 1, 0);
   bool any_bert = text_bert != nullptr;
-  for (int b = 0; b < B; ++b) {
+  int maxS = 0;
+  for (int b = 0; b < n; ++b) {
     Prompt* p = prompts[b];
-    GENIE_CHECK(p && p->model == &m, "prompt does not belong to this model");
+    const SamplingCfg& c = cfgs[n_cfg == 1 ? 0 : b];
+    GENIE_CHECK(p && p->model_uid == m.owner->uid, "prompt does not belong to this model");
     GENIE_CHECK(text_len[b] > 0, "empty text_seq");
-    bt.Lr.push_back(p->Lr); bt.Lt.push_back(text_len[b]); bt.Ly.push_back(p->Ly);
-    bt.Lx.push_back(p->Lr + text_len[b]); bt.S.push_back(p->Lr + text_len[b] + p->Ly);
-    bt.row_off.push_back(bt.row_off.back() + bt.S.back());
-    bt.txt_off.push_back(bt.txt_off.back() + bt.Lx.back());
-    bt.maxS = std::max(bt.maxS, bt.S.back());
+    const int steps = c.fixed_steps > 0 ? c.fixed_steps : c.max_steps;
+    slot[b] = slots_in ? slots_in[b] : b;
+    GENIE_CHECK(slot[b] >= 0 && slot[b] < S.n_slots, "slot index out of range");
+    GENIE_CHECK(!S.slots[slot[b]].in_use, "slot " + std::to_string(slot[b]) + " is still in use");
+    Lr[b] = p->Lr; Lt[b] = text_len[b]; Ly[b] = p->Ly; Lx[b] = Lr[b] + Lt[b]; Sx[b] = Lx[b] + Ly[b];
+    GENIE_CHECK(Sx[b] + steps + 1 <= S.cap, "utterance needs " + std::to_string(Sx[b] + steps + 1) +
+                                                " KV rows, the pool's slots hold " + std::to_string(S.cap));
+    GENIE_CHECK(Ly[b] + steps + 2 <= S.hist_ld, "utterance needs a longer token history than the pool was built for");
+    row_off[b + 1] = row_off[b] + Sx[b]; txt_off[b + 1] = txt_off[b] + Lx[b]; txt_in_off[b + 1] = txt_in_off[b] + Lt[b];
+    maxS = std::max(maxS, Sx[b]);
     any_bert = any_bert || p->has_bert;
   }
-  bt.rows = bt.row_off.back(); bt.txt_rows = bt.txt_off.back();
-  bt.cap = ((bt.maxS + max_steps + 1 + 15) / 16) * 16;
-  int maxLy = *std::max_element(bt.Ly.begin(), bt.Ly.end());
-  bt.hist_ld = maxLy + max_steps + 2;
+  for (int b = 0; b < n; ++b)
+    for (int c = 0; c < b; ++c) GENIE_CHECK(slot[b] != slot[c], "slot listed twice in one admission");
+  const int R = row_off[n], txt_rows = txt_off[n], n_text_in = txt_in_off[n];
+  if (!io_dev)
+    for (int i = 0; i < n_text_in; ++i)
+      GENIE_CHECK(text_seq[i] >= 0 && text_seq[i] < m.text_vocab, "text_seq id out of range (phoneme table has " +
+                                                                      std::to_string(m.text_vocab) + " rows)");
 
   Workspace& ws = m.ws;
-  const int R = bt.rows;
   float* X = ws.get<float>("t2s.x", (size_t)R * D);
   float* QKV = ws.get<float>("t2s.qkv", (size_t)R * 3 * D);
   float* ATT = ws.get<float>("t2s.att", (size_t)R * D);
@@ -233,112 +302,94 @@ void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   static const bool ffn16_env = [] { const char* e = getenv("GENIE_FFN16"); return !(e && e[0] == '0'); }();
   const bool ffn16 = ffn16_env && m.use_tc && R >= m.tc_min_rows && R > m.skinny_max_rows && m.layers[0].ff1.tc.hi &&
                      m.layers[0].ff2.tc.hi && !m.layers[0].ff2.tc.lo;
-  float* XT = ws.get<float>("t2s.xtext", (size_t)bt.txt_rows * D);
-  float* BERT = any_bert ? ws.get<float>("t2s.bert", (size_t)bt.txt_rows * 1024) : nullptr;
-  long long* SEQ = ws.get<long long>("t2s.seq", bt.txt_rows);
-  int* IMETA = ws.get<int>("t2s.imeta", (size_t)R * 2 + bt.txt_rows + 8 * (B + 1));
-  float* LAST = ws.get<float>("t2s.last", (size_t)B * D);
-  float* LOGITS = ws.get<float>("t2s.logits", (size_t)B * V);
-  long long* LASTIDX = ws.get<long long>("t2s.lastidx", B);
-  const int** PPTR = ws.get<const int*>("t2s.pptr", B);
-  int* HIST = ws.get<int>("t2s.hist", (size_t)B * bt.hist_ld);
-  long long* Y64 = ws.get<long long>("t2s.y64", (size_t)B * bt.hist_ld);
-  // KV cache [B][layer][K|V][H][cap][32] fp32
-  const long long head_sz = (long long)bt.cap * 32, v_off = H * head_sz, layer_stride = 2 * v_off,
-                  utt_stride = NL * layer_stride;
-  float* KV = ws.get<float>("t2s.kv", (size_t)B * utt_stride);
+  float* XT = any_bert ? ws.get<float>("t2s.xtext", (size_t)txt_rows * D) : nullptr;
+  float* BERT = any_bert ? ws.get<float>("t2s.bert", (size_t)txt_rows * 1024) : nullptr;
+  long long* SEQ_IN = io_dev ? nullptr : ws.get<long long>("t2s.seq_in", n_text_in);
+  float* BERT_IN = (text_bert && !io_dev) ? ws.get<float>("t2s.bert_in", (size_t)n_text_in * 1024) : nullptr;
+  float* LAST = ws.get<float>("t2s.last", (size_t)n * D);
+  float* LOGITS_PRE = ws.get<float>("t2s.logits_pre", (size_t)n * V);
+  long long* LASTIDX = ws.get<long long>("t2s.lastidx", n);
+  // one int block + one pointer block + the slot-init records per admission
+  //   ints: row_off[n+1] | txt_off[n+1] | txt_in_off[n+1] | lr[n] | lx[n] | slot[n] | zero[n] | row2utt[R]
+  const size_t n_int = (size_t)3 * (n + 1) + 4 * n + R;
+  int* IMETA = ws.get<int>("t2s.imeta", n_int);
+  const void** PMETA = ws.get<const void*>("t2s.pmeta", (size_t)3 * n);
+  SlotInit* SINIT = ws.get<SlotInit>("t2s.sinit", n);
 
-  // ---- host-built index metadata, one upload
-  //   txt_pos[txt_rows] | row2utt[R] | aud_pos[R] (per audio row; text rows unused) | per-utt arrays
-  std::vector<int> meta((size_t)R * 2 + bt.txt_rows + 8 * (B + 1), 0);
-  // per-utterance state first: its device addresses (baked into the decode-step graph) then
-  // depend only on the buffer base and B, not on this call's row counts
-  int* h_row_off = meta.data();                 // [B+1]
-  int* h_lx = h_row_off + (B + 1);              // [B]
-  int* h_zero = h_lx + (B + 1);                 // [B] zeros (dst_pos0 for prefill scatter)
-  int* h_kvlen = h_zero + (B + 1);              // [B]
-  int* h_histlen = h_kvlen + (B + 1);           // [B]
-  int* h_active = h_histlen + (B + 1);          // [B]
-  int* h_stop = h_active + (B + 1);             // [B]
-  int* h_ly = h_stop + (B + 1);                 // [B]
-  int* h_txt_pos = h_ly + (B + 1);
-  int* h_row2utt = h_txt_pos + bt.txt_rows;
-  int* h_aud_tok_pos = h_row2utt + R;           // position (1-based) of audio rows
-  for (int b = 0; b < B; ++b) {
-    for (int i = 0; i < bt.Lx[b]; ++i) h_txt_pos[bt.txt_off[b] + i] = i + 1;
-    for (int i = 0; i < bt.S[b]; ++i) h_row2utt[bt.row_off[b] + i] = b;
-    for (int i = 0; i < bt.Ly[b]; ++i) h_aud_tok_pos[bt.row_off[b] + bt.Lx[b] + i] = i + 1;
-    h_row_off[b] = bt.row_off[b]; h_lx[b] = bt.Lx[b]; h_kvlen[b] = bt.S[b]; h_histlen[b] = bt.Ly[b];
-    h_active[b] = 1; h_stop[b] = -1; h_ly[b] = bt.Ly[b];
+  std::vector<int> meta(n_int, 0);
+  int* h_row_off = meta.data(); int* h_txt_off = h_row_off + (n + 1); int* h_txt_in = h_txt_off + (n + 1);
+  int* h_lr = h_txt_in + (n + 1); int* h_lx = h_lr + n; int* h_slot = h_lx + n; int* h_zero = h_slot + n;
+  int* h_row2utt = h_zero + n;
+  std::vector<const void*> pmeta((size_t)3 * n);
+  std::vector<SlotInit> sinit(n);
+  std::vector<long long> li(n);
+  for (int b = 0; b < n; ++b) {
+    h_row_off[b] = row_off[b]; h_txt_off[b] = txt_off[b]; h_txt_in[b] = txt_in_off[b];
+    h_lr[b] = Lr[b]; h_lx[b] = Lx[b]; h_slot[b] = slot[b];
+    for (int i = 0; i < Sx[b]; ++i) h_row2utt[row_off[b] + i] = b;
+    pmeta[b] = prompts[b]->ref_seq; pmeta[n + b] = prompts[b]->ref_bert; pmeta[2 * n + b] = prompts[b]->prompts;
+    const SamplingCfg& c = cfgs[n_cfg == 1 ? 0 : b];
+    sinit[b] = SlotInit{slot[b], Sx[b], Ly[b], 0, slot_params(c, Ly[b], b)};
+    li[b] = row_off[b + 1] - 1;
   }
-  h_row_off[B] = R;
-  GENIE_CUDA(cudaMemcpyAsync(IMETA, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-  int* d_row_off = IMETA; int* d_lx = d_row_off + (B + 1); int* d_zero = d_lx + (B + 1);
-  int* d_kvlen = d_zero + (B + 1); int* d_histlen = d_kvlen + (B + 1); int* d_active = d_histlen + (B + 1);
-  int* d_stop = d_active + (B + 1); int* d_ly = d_stop + (B + 1);
-  int* d_txt_pos = d_ly + (B + 1); int* d_row2utt = d_txt_pos + bt.txt_rows; int* d_aud_pos = d_row2utt + R;
-
-  GENIE_CUDA(cudaEventCreate(&S.ev0)); GENIE_CUDA(cudaEventCreate(&S.ev1));
-  cudaEvent_t ev0 = S.ev0, ev1 = S.ev1;
-  GENIE_CUDA(cudaEventRecord(ev0, s));
-
-  // ---- K1: x = Emb_text[ref||text] + bert_proj(bert) + alpha*PE(1..Lx)   (t2s_encoder#[49-83])
-  const cudaMemcpyKind in_kind = io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  {
-    long long toff = 0;
-    for (int b = 0; b < B; ++b) {
-      Prompt* p = prompts[b];
-      GENIE_CUDA(cudaMemcpyAsync(SEQ + bt.txt_off[b], p->ref_seq, p->Lr * sizeof(long long), cudaMemcpyDeviceToDevice, s));
-      GENIE_CUDA(cudaMemcpyAsync(SEQ + bt.txt_off[b] + p->Lr, text_seq + toff, text_len[b] * sizeof(long long), in_kind, s));
-      if (any_bert) {
-        float* dst = BERT + (long long)bt.txt_off[b] * 1024;
-        if (p->has_bert) GENIE_CUDA(cudaMemcpyAsync(dst, p->ref_bert, (size_t)p->Lr * 1024 * 4, cudaMemcpyDeviceToDevice, s));
-        else GENIE_CUDA(cudaMemsetAsync(dst, 0, (size_t)p->Lr * 1024 * 4, s));
-        dst += (long long)p->Lr * 1024;
-        if (text_bert) GENIE_CUDA(cudaMemcpyAsync(dst, text_bert + toff * 1024, (size_t)text_len[b] * 1024 * 4, in_kind, s));
-        else GENIE_CUDA(cudaMemsetAsync(dst, 0, (size_t)text_len[b] * 1024 * 4, s));
-      }
-      toff += text_len[b];
-    }
+  h_row_off[n] = R; h_txt_off[n] = txt_rows; h_txt_in[n] = n_text_in;
+  GENIE_CUDA(cudaMemcpyAsync(IMETA, meta.data(), n_int * sizeof(int), cudaMemcpyHostToDevice, s));
+  GENIE_CUDA(cudaMemcpyAsync(PMETA, pmeta.data(), pmeta.size() * sizeof(void*), cudaMemcpyHostToDevice, s));
+  GENIE_CUDA(cudaMemcpyAsync(SINIT, sinit.data(), sinit.size() * sizeof(SlotInit), cudaMemcpyHostToDevice, s));
+  GENIE_CUDA(cudaMemcpyAsync(LASTIDX, li.data(), n * sizeof(long long), cudaMemcpyHostToDevice, s));
+  const long long* d_text = reinterpret_cast<const long long*>(text_seq);
+  if (!io_dev) {
+    GENIE_CUDA(cudaMemcpyAsync(SEQ_IN, text_seq, (size_t)n_text_in * 8, cudaMemcpyHostToDevice, s));
+    d_text = SEQ_IN;
   }
+  const float* d_text_bert = text_bert;
+  if (text_bert && !io_dev) {
+    GENIE_CUDA(cudaMemcpyAsync(BERT_IN, text_bert, (size_t)n_text_in * 1024 * 4, cudaMemcpyHostToDevice, s));
+    d_text_bert = BERT_IN;
+  }
+  // the host vectors above are pageable: the copies are staged by the runtime before the call returns
+  int* d_row_off = IMETA; int* d_txt_off = d_row_off + (n + 1); int* d_txt_in = d_txt_off + (n + 1);
+  int* d_lr = d_txt_in + (n + 1); int* d_lx = d_lr + n; int* d_slot = d_lx + n; int* d_zero = d_slot + n;
+  int* d_row2utt = d_zero + n;
+  PrefillMeta pm{};
+  pm.row2utt = d_row2utt; pm.row_off = d_row_off; pm.txt_off = d_txt_off; pm.txt_in_off = d_txt_in; pm.lr = d_lr; pm.lx = d_lx;
+  pm.ref_seq = reinterpret_cast<const long long* const*>(PMETA);
+  pm.ref_bert = reinterpret_cast<const float* const*>(PMETA + n);
+  pm.prompt_tok = reinterpret_cast<const int* const*>(PMETA + 2 * n);
+
+  if (!S.ev0) { GENIE_CUDA(cudaEventCreate(&S.ev0)); GENIE_CUDA(cudaEventCreate(&S.ev1)); }
+  GENIE_CUDA(cudaEventRecord(S.ev0, s));
+
+  // ---- K1 + K3: xy = [Emb_text[ref||text] + bert_proj(bert) + alpha PE(1..Lx)  ||  Emb_audio[prompts] + alpha PE(1..Ly)]
+  // (t2s_encoder#[49-83], first_stage#[5-25]); bert features are zeros for ja/en (GetPhonesAndBert.py:60,80), where
+  // bert_proj reduces to its bias
   if (any_bert) {
-    run_linear(m, m.bert_proj, BERT, 1024, XT, D, bt.txt_rows);
-  } else {
-    // bert features are zeros for ja/en (reference GetPhonesAndBert.py:60,80): bert_proj reduces to its bias
-    fill_rows_kernel<<<(unsigned)(((long long)bt.txt_rows * 512 + 255) / 256), 256, 0, s>>>(XT, m.bert_proj.b, bt.txt_rows);
-    GENIE_LAUNCHED("fill_rows");
+    launch_prefill_bert_gather(BERT, pm, d_text_bert, R, s);
+    run_linear(m, m.bert_proj, BERT, 1024, XT, D, txt_rows);
   }
-  launch_text_embed_pe(XT, SEQ, d_txt_pos, m.text_emb, m.text_alpha, m.div_term, bt.txt_rows, s);
-  keep_tensor(m, "x", XT, (long long)bt.txt_rows * D);
-
-  // ---- K3: xy = [x || Emb_audio[prompts] + alpha*PE(1..Ly)]  (first_stage#[5-25])
-  {
-    std::vector<const int*> pp(B);
-    for (int b = 0; b < B; ++b) pp[b] = prompts[b]->prompts;
-    GENIE_CUDA(cudaMemcpyAsync(PPTR, pp.data(), B * sizeof(int*), cudaMemcpyHostToDevice, s));
-    GENIE_CUDA(cudaMemsetAsync(HIST, 0, (size_t)B * bt.hist_ld * sizeof(int), s));
-    init_hist_kernel<<<B, 128, 0, s>>>(HIST, bt.hist_ld, PPTR, d_ly, B);
-    GENIE_LAUNCHED("init_hist");
-    for (int b = 0; b < B; ++b) {
-      GENIE_CUDA(cudaMemcpyAsync(X + (long long)bt.row_off[b] * D, XT + (long long)bt.txt_off[b] * D,
-                                 (size_t)bt.Lx[b] * D * 4, cudaMemcpyDeviceToDevice, s));
-      float* dst = X + (long long)(bt.row_off[b] + bt.Lx[b]) * D;
-      launch_audio_embed_pe(dst, prompts[b]->prompts, d_aud_pos + bt.row_off[b] + bt.Lx[b], m.audio_emb,
-                            m.audio_alpha, m.div_term, bt.Ly[b], s);
-    }
+  launch_prefill_embed(X, pm, d_text, XT, m.bert_proj.b, m.text_emb, m.text_alpha, m.text_vocab, m.audio_emb,
+                       m.audio_alpha, m.div_term, R, m.tc_err, s);
+  launch_slot_init(SINIT, n, pm.prompt_tok, S.HIST, S.hist_ld, S.d_histlen, S.d_kvlen, S.d_active, S.d_stop, S.d_params, s);
+  if (m.keep) {   // debug: the encoder graph's output x = the text rows
+    float* XK = ws.get<float>("t2s.xkeep", (size_t)txt_rows * D);
+    for (int b = 0; b < n; ++b)
+      GENIE_CUDA(cudaMemcpyAsync(XK + (size_t)txt_off[b] * D, X + (size_t)row_off[b] * D, (size_t)Lx[b] * D * 4,
+                                 cudaMemcpyDeviceToDevice, s));
+    keep_tensor(m, "x", XK, (long long)txt_rows * D);
   }
 
-  // ---- K4: 24 prefill layers over all rows of all utterances
+  // ---- K4: 24 prefill layers over all rows of all admitted utterances
+  const StepBufs& w = S.w;
   const float scale = 1.0f / std::sqrt(32.0f);
   float* Hcur = X;
   for (int l = 0; l < NL; ++l) {
     const T2SLayer& L = m.layers[l];
     run_linear(m, L.qkv, Hcur, D, QKV, 3 * D, R);
-    launch_kv_scatter(QKV, 3 * D, KV, utt_stride, l * layer_stride, v_off, bt.cap, d_row_off, d_zero, d_row2utt, R,
-                      nullptr, s);
+    launch_kv_scatter(QKV, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, S.cap, d_row_off, d_zero, d_row2utt, R,
+                      nullptr, s, d_slot);
     Attn a;
     a.q = QKV; a.ldq = 3 * D; a.k = QKV + D; a.ldk = 3 * D; a.v = QKV + 2 * D; a.ldv = 3 * D;
-    a.o = ATT; a.ldo = D; a.q_off = d_row_off; a.kv_off = d_row_off; a.B = B; a.H = H; a.d = 32; a.max_q = bt.maxS;
+    a.o = ATT; a.ldo = D; a.q_off = d_row_off; a.kv_off = d_row_off; a.B = n; a.H = H; a.d = 32; a.max_q = maxS;
     a.scale = scale; a.mask_mode = 1; a.lx = d_lx;
     launch_attention(a, s);
     run_linear(m, L.out, ATT, D, TMP, D, R, ACT_NONE, Hcur, D);
@@ -361,119 +412,180 @@ void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       keep_tensor(m, "h0", X, (long long)R * D);
     }
   }
-  // logits for the last row of each utterance (first_stage#[1785-1788])
-  {
-    std::vector<long long> li(B);
-    for (int b = 0; b < B; ++b) li[b] = bt.row_off[b + 1] - 1;
-    GENIE_CUDA(cudaMemcpyAsync(LASTIDX, li.data(), B * sizeof(long long), cudaMemcpyHostToDevice, s));
-    launch_gather_rows(LAST, D, X, D, LASTIDX, B, 1, s);
-    run_linear(m, m.predict, LAST, D, LOGITS, V, B);
-  }
-  S.LOGITS = LOGITS; S.HIST = HIST; S.Y64 = Y64;
-  S.d_histlen = d_histlen; S.d_kvlen = d_kvlen; S.d_active = d_active; S.d_stop = d_stop;
-  m.logits_host.clear();
-  record_step_logits(m, S);
+  // logits for the last row of each utterance (first_stage#[1785-1788]) and the first sampled token (#[1789-1820];
+  // the first-stage graph has no stop output)
+  launch_gather_rows(LAST, D, X, D, LASTIDX, n, 1, s);
+  run_linear(m, m.predict, LAST, D, LOGITS_PRE, V, n);
+  S.LOGITS_PRE = LOGITS_PRE;
+  record_logits_rows(m, LOGITS_PRE, n);
   {
     SamplerArgs a{};
-    a.logits = LOGITS; a.ld = V; a.hist = HIST; a.hist_ld = bt.hist_ld; a.hist_len = d_histlen; a.kv_len = d_kvlen;
-    a.active = d_active; a.stop_step = d_stop; a.B = B; a.top_k = cfg.top_k; a.temperature = cfg.temperature;
-    a.penalty = cfg.penalty; a.greedy = cfg.greedy; a.seed = cfg.seed; a.honour_stop = 0; a.advance_kv = 0;
-    a.check_stop = 0;   // the first-stage graph has no stop output
+    a.logits = LOGITS_PRE; a.ld = V; a.hist = S.HIST; a.hist_ld = S.hist_ld; a.hist_len = S.d_histlen; a.kv_len = S.d_kvlen;
+    a.active = S.d_active; a.stop_step = S.d_stop; a.params = S.d_params; a.slot_map = d_slot; a.B = n;
+    a.advance_kv = 0; a.check_stop = 0;
     launch_sampler(a, s);
   }
-  GENIE_CUDA(cudaEventRecord(ev1, s));
+  GENIE_CUDA(cudaEventRecord(S.ev1, s));
+  for (int b = 0; b < n; ++b) {
+    const SamplingCfg& c = cfgs[n_cfg == 1 ? 0 : b];
+    SlotHost& h = S.slots[slot[b]];
+    h.in_use = 1; h.Ly = Ly[b]; h.S = Sx[b]; h.honour = c.fixed_steps > 0 ? 0 : 1;
+    h.max_steps = c.fixed_steps > 0 ? c.fixed_steps : c.max_steps;
+  }
+}
 
-  // ---- decode-step buffers and graph (Inference.py:95-106 runs in t2s_decode_steps)
-  StepBufs& w = S.w;
-  w = StepBufs{};
-  w.h = ws.get<float>("t2s.step.h", (size_t)B * D); w.qkv = ws.get<float>("t2s.step.qkv", (size_t)B * 3 * D);
-  w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
-  w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
-  w.part = ws.get<float>("t2s.step.part", (size_t)8 * B * D);
-  w.part2 = ws.get<float>("t2s.step.part2", (size_t)8 * B * D);
-  w.ppart = ws.get<float>("t2s.step.ppart", (size_t)B * 16 * 8 * 36);
-  w.part_stride = (long long)B * D;
-  w.logits = LOGITS; w.hist = HIST; w.hist_len = d_histlen; w.kv_len = d_kvlen; w.active = d_active;
-  w.stop_step = d_stop; w.kv = KV; w.utt_stride = utt_stride; w.layer_stride = layer_stride; w.v_off = v_off;
-  w.cap = bt.cap; w.hist_ld = bt.hist_ld;
-
-  if (m.persistent_step && B <= m.persistent_step) ensure_persistent_step(m);
-  // the graph bakes pointers and scalar args; re-capture when any of them changes
-  const int flags = (cfg.greedy ? 1 : 0) | (cfg.fixed_steps > 0 ? 2 : 0) | (m.use_tc ? 4 : 0) | (cfg.top_k << 4) |
-                    (m.tc_min_rows << 16);
-  const bool can_graph = m.use_graph && !m.record_logits && !g_sync_debug;
-  S.can_graph = can_graph;
-  if (can_graph) {
-    bool stale = !m.step_graph || m.step_graph_B != B || m.step_graph_gen != ws.generation ||
-                 m.step_graph_cap != bt.cap || m.step_graph_flags != flags || m.step_graph_hist_ld != bt.hist_ld;
-    // seed / temperature / penalty are baked too: fold them into staleness via a cheap hash
-    if (m.step_graph_seed != cfg.seed || m.step_graph_temp != cfg.temperature || m.step_graph_pen != cfg.penalty)
-      stale = true;
-    if (stale) {
-      if (m.step_graph) { cudaGraphExecDestroy(m.step_graph); m.step_graph = nullptr; }
-      cudaGraph_t g = nullptr;
-      unsigned long long launches_before = g_launches;
-      GENIE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+// the captured decode step over the first `rows` slots (captured on first use, then replayed)
+StepGraph& step_graph(Model& m, T2SSession& S, int rows) {
+  GraphCache& gc = graphs_of(m);
+  const unsigned long long opt = m.options_gen;
+  for (auto& g : gc.e)
+    if (g.rows == rows && g.cap == S.cap && g.hist_ld == S.hist_ld && g.gen == S.w.key && g.opt == opt) {
+      g.last_use = ++gc.tick;
+      return g;
+    }
+  // drop entries whose buffers have moved or whose options changed, keep the cache small
+  for (size_t i = 0; i < gc.e.size();) {
+    if (gc.e[i].gen != S.w.key || gc.e[i].opt != opt) {
+      cudaGraphExecDestroy(gc.e[i].exec);
+      gc.e.erase(gc.e.begin() + i);
+    } else ++i;
+  }
+  if (gc.e.size() >= 12) {
+    size_t old = 0;
+    for (size_t i = 1; i < gc.e.size(); ++i) if (gc.e[i].last_use < gc.e[old].last_use) old = i;
+    cudaGraphExecDestroy(gc.e[old].exec);
+    gc.e.erase(gc.e.begin() + old);
+  }
+  cudaStream_t s = m.stream;
+  const StepBufs& w = S.w;
+  const int B = rows;
+  cudaGraph_t g = nullptr;
+  unsigned long long captured = 0;
+  GENIE_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  t_capture_counter = &captured;
+  try {
+    int nb = (B >= m.decode_split_min && m.stream2) ? m.decode_branches : 1;
+    if (nb > 1 && (B + nb - 1) / nb > 128) nb = (B + 127) / 128;   // keep every branch on the <= 128-row GEMM
+    if (nb > 4) nb = 4;
+    while (nb > 1 && B / nb < 16) --nb;              // every branch stays on the tensor-core path
+    if (nb > 1) {
+      // independent slot ranges as parallel graph branches: every decode kernel is latency-bound
+      // (or, the attention, bandwidth-bound with few resources), so the branches overlap
+      cudaStream_t bs[4] = {s, m.stream2, m.stream3, m.stream4};
+      cudaEvent_t bj[4] = {nullptr, m.ev_join, m.ev_join3, m.ev_join4};
+      GENIE_CUDA(cudaEventRecord(m.ev_fork, s));
+      cudaStream_t keep = m.stream;
       try {
-        int nb = (B >= m.decode_split_min && m.stream2) ? m.decode_branches : 1;
-        if (nb > 1 && (B + nb - 1) / nb > 128) nb = (B + 127) / 128;   // keep every branch on the <= 128-row GEMM
-        if (nb > 4) nb = 4;
-        while (nb > 1 && B / nb < 16) --nb;              // every branch stays on the tensor-core path
-        if (nb > 1) {
-          // independent utterance ranges as parallel graph branches: every decode kernel is latency-bound
-          // (or, the attention, bandwidth-bound with few resources), so the branches overlap
-          cudaStream_t bs[4] = {s, m.stream2, m.stream3, m.stream4};
-          cudaEvent_t bj[4] = {nullptr, m.ev_join, m.ev_join3, m.ev_join4};
-          GENIE_CUDA(cudaEventRecord(m.ev_fork, s));
-          cudaStream_t keep = m.stream;
-          try {
-            for (int k = 0; k < nb; ++k) {
-              const int b0 = (int)((long long)B * k / nb), b1 = (int)((long long)B * (k + 1) / nb);
-              StepBufs w2 = w;
-              w2.h += (size_t)b0 * D; w2.qkv += (size_t)b0 * 3 * D; w2.att += (size_t)b0 * D; w2.tmp += (size_t)b0 * D;
-              w2.h1 += (size_t)b0 * D; w2.ff += (size_t)b0 * 4 * D; w2.logits += (size_t)b0 * V;
-              // private slice of the partial-sum buffers ([split][rows][N] views with N changing per use must
-              // not overlap between branches that run in different phases): 8 * rows * D floats per branch
-              w2.part += (size_t)8 * b0 * D; w2.part2 += (size_t)8 * b0 * D; w2.part_stride = (long long)(b1 - b0) * D;
-              w2.hist += (size_t)b0 * w.hist_ld;
-              w2.hist_len += b0; w2.kv_len += b0; w2.active += b0; w2.stop_step += b0;
-              w2.kv += (size_t)b0 * w.utt_stride; w2.utt_base = b0;
-              if (k > 0) GENIE_CUDA(cudaStreamWaitEvent(bs[k], m.ev_fork, 0));
-              m.stream = bs[k];
-              decode_step(m, w2, b1 - b0, cfg);
-              if (k > 0) GENIE_CUDA(cudaEventRecord(bj[k], bs[k]));
-            }
-          } catch (...) { m.stream = keep; throw; }
-          m.stream = keep;
-          for (int k = 1; k < nb; ++k) GENIE_CUDA(cudaStreamWaitEvent(s, bj[k], 0));
-        } else {
-          decode_step(m, w, B, cfg);
+        for (int k = 0; k < nb; ++k) {
+          const int b0 = (int)((long long)B * k / nb), b1 = (int)((long long)B * (k + 1) / nb);
+          StepBufs w2 = w;
+          w2.h += (size_t)b0 * D; w2.qkv += (size_t)b0 * 3 * D; w2.att += (size_t)b0 * D; w2.tmp += (size_t)b0 * D;
+          w2.h1 += (size_t)b0 * D; w2.ff += (size_t)b0 * 4 * D; w2.logits += (size_t)b0 * V;
+          // private slice of the partial-sum buffers ([split][rows][N] views with N changing per use must
+          // not overlap between branches that run in different phases): 8 * rows * D floats per branch
+          w2.part += (size_t)8 * b0 * D; w2.part2 += (size_t)8 * b0 * D; w2.part_stride = (long long)(b1 - b0) * D;
+          w2.hist += (size_t)b0 * w.hist_ld;
+          w2.hist_len += b0; w2.kv_len += b0; w2.active += b0; w2.stop_step += b0; w2.params += b0;
+          w2.kv += (size_t)b0 * w.utt_stride;
+          if (k > 0) GENIE_CUDA(cudaStreamWaitEvent(bs[k], m.ev_fork, 0));
+          m.stream = bs[k];
+          decode_step(m, w2, b1 - b0);
+          if (k > 0) GENIE_CUDA(cudaEventRecord(bj[k], bs[k]));
         }
-      } catch (...) {
-        cudaStreamEndCapture(s, &g);
-        if (g) cudaGraphDestroy(g);
-        throw;
-      }
-      GENIE_CUDA(cudaStreamEndCapture(s, &g));
-      m.step_graph_launches = g_launches - launches_before;
-      g_launches = launches_before;            // capture does not launch
-      GENIE_CUDA(cudaGraphInstantiate(&m.step_graph, g, 0));
-      cudaGraphDestroy(g);
-      m.step_graph_B = B; m.step_graph_gen = ws.generation; m.step_graph_cap = bt.cap; m.step_graph_flags = flags; m.step_graph_hist_ld = bt.hist_ld;
-      m.step_graph_seed = cfg.seed; m.step_graph_temp = cfg.temperature; m.step_graph_pen = cfg.penalty;
+      } catch (...) { m.stream = keep; throw; }
+      m.stream = keep;
+      for (int k = 1; k < nb; ++k) GENIE_CUDA(cudaStreamWaitEvent(s, bj[k], 0));
+    } else {
+      StepBufs w1 = w;
+      w1.part_stride = (long long)B * D;
+      decode_step(m, w1, B);
+    }
+  } catch (...) {
+    t_capture_counter = nullptr;
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  t_capture_counter = nullptr;
+  GENIE_CUDA(cudaStreamEndCapture(s, &g));
+  StepGraph e;
+  e.rows = rows; e.cap = S.cap; e.hist_ld = S.hist_ld; e.gen = S.w.key; e.opt = opt; e.launches = captured;
+  cudaError_t ie = cudaGraphInstantiate(&e.exec, g, 0);
+  cudaGraphDestroy(g);
+  GENIE_CUDA(ie);
+  e.last_use = ++gc.tick;
+  gc.e.push_back(e);
+  return gc.e.back();
+}
+
+// one decode step over the first `rows` slots
+void run_step(Model& m, T2SSession& S, int rows) {
+  const bool can_graph = m.use_graph && !m.record_logits && !g_sync_debug;
+  if (can_graph) {
+    StepGraph& g = step_graph(m, S, rows);
+    GENIE_CUDA(cudaGraphLaunch(g.exec, m.stream));
+    g_launches += g.launches;
+  } else {
+    StepBufs w1 = S.w;
+    w1.part_stride = (long long)rows * D;
+    decode_step(m, w1, rows);
+  }
+  record_logits_rows(m, S.LOGITS, rows);
+}
+
+void check_step_errors(Model& m) {
+  check_tc_error(m);
+  if (m.step_sync) {
+    unsigned flag[2] = {0, 0};
+    GENIE_CUDA(cudaMemcpy(flag, m.step_sync, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag[1]) {
+      cudaMemset(m.step_sync, 0, sizeof(flag));
+      GENIE_CHECK(false, "persistent decode step: device-wide barrier timed out");
     }
   }
-  m.t2s_session = sess_ptr;
+}
+
+int slot_idx(const SlotHost& h, int hist_len, int stop_step) {
+  // the reference's loop variable at exit (Inference.py:95-106): index of the step whose stop flag fired, else the
+  // last index run
+  const int steps_run = hist_len - h.Ly - 1;
+  int idx = (!h.honour || stop_step < 0) ? steps_run - 1 : stop_step - (h.Ly + 1);
+  return idx < 0 ? 0 : idx;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch API (reference-facing path: Inference.py:63-109 for B utterances at once)
+// ---------------------------------------------------------------------------------------------------------------
+void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
+                 const float* text_bert, const SamplingCfg& cfg, int io_dev) {
+  GENIE_CHECK(m.finalized, "model not finalized");
+  GENIE_CHECK(B > 0, "empty batch");
+  const int max_steps = cfg.fixed_steps > 0 ? cfg.fixed_steps : cfg.max_steps;
+  int maxS = 0, maxLy = 0;
+  for (int b = 0; b < B; ++b) {
+    GENIE_CHECK(prompts[b] != nullptr, "null prompt");
+    GENIE_CHECK(text_len[b] > 0, "empty text_seq");
+    maxS = std::max(maxS, prompts[b]->Lr + text_len[b] + prompts[b]->Ly);
+    maxLy = std::max(maxLy, prompts[b]->Ly);
+  }
+  T2SSession& S = pool_build(m, B, maxS + max_steps + 1, maxLy + max_steps + 2, false);
+  S.B = B; S.max_steps = max_steps; S.fixed = cfg.fixed_steps > 0;
+  m.logits_host.clear();
+  admit(m, S, B, nullptr, prompts, text_seq, text_len, text_bert, &cfg, 1, io_dev);
+  // capture (or find) the decode graph now: the first decode_steps call then only replays
+  if (m.use_graph && !m.record_logits && !g_sync_debug) step_graph(m, S, B);
 }
 
 // up to n_steps more decode steps for the batch in flight (stage graph + sampler per step, Inference.py:95-106);
 // returns GENIE_CANCELLED (2) when the host flag fired, 0 otherwise
 int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_active_out, int* steps_done_out) {
   T2SSession& S = session_of(m);
+  GENIE_CHECK(!S.pool_mode, "this handle runs a slot pool: use genie_t2s_pool_step");
   cudaStream_t s = m.stream;
   GENIE_CUDA(cudaSetDevice(m.device));
   const int B = S.B;
-  const SamplingCfg& cfg = S.cfg;
   int rc = 0;
   std::vector<int> h_act(B, 1);
   const int poll_every = 8;
@@ -483,15 +595,9 @@ int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_a
   GENIE_CUDA(cudaEventRecord(ea, s));
   for (int k = 0; k < n_steps && S.steps_done < S.max_steps && !S.all_stopped; ++k) {
     if (cancel && *cancel) { rc = 2 /* GENIE_CANCELLED */; break; }
-    if (S.can_graph) {
-      GENIE_CUDA(cudaGraphLaunch(m.step_graph, s));
-      g_launches += m.step_graph_launches;
-    } else {
-      decode_step(m, S.w, B, cfg);
-    }
+    run_step(m, S, B);
     ++S.steps_done;
-    record_step_logits(m, S);
-    if (cfg.fixed_steps <= 0 && (S.steps_done % poll_every == 0 || m.record_logits)) {
+    if (!S.fixed && (S.steps_done % poll_every == 0 || m.record_logits)) {
       GENIE_CUDA(cudaMemcpyAsync(h_act.data(), S.d_active, B * sizeof(int), cudaMemcpyDeviceToHost, s));
       GENIE_CUDA(cudaStreamSynchronize(s));
       bool any = false;
@@ -502,7 +608,7 @@ int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_a
   GENIE_CUDA(cudaEventRecord(eb, s));
   if (n_active_out) {
     int n = 0;
-    if (cfg.fixed_steps > 0) n = S.steps_done < S.max_steps ? B : 0;
+    if (S.fixed) n = S.steps_done < S.max_steps ? B : 0;
     else if (!S.all_stopped && S.steps_done < S.max_steps) {
       GENIE_CUDA(cudaMemcpyAsync(h_act.data(), S.d_active, B * sizeof(int), cudaMemcpyDeviceToHost, s));
       GENIE_CUDA(cudaStreamSynchronize(s));
@@ -518,54 +624,39 @@ int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_a
 // tokens generated so far (prompt tokens + generated, per utterance) and the reference's loop index
 void t2s_read(Model& m, int io_dev, int64_t* y_out, int y_ld, int* y_len_out, int* idx_out) {
   T2SSession& S = session_of(m);
+  GENIE_CHECK(!S.pool_mode, "this handle runs a slot pool: use genie_t2s_pool_read");
   cudaStream_t s = m.stream;
   GENIE_CUDA(cudaSetDevice(m.device));
   const int B = S.B;
-  const Batch& bt = S.bt;
-  const SamplingCfg& cfg = S.cfg;
   const StepBufs& w = S.w;
-  const int steps_done = S.steps_done;
-  GENIE_CHECK(y_ld >= bt.hist_ld || y_out == nullptr, "y_ld too small: need >= " + std::to_string(bt.hist_ld));
+  GENIE_CHECK(y_ld >= S.hist_ld || y_out == nullptr, "y_ld too small: need >= " + std::to_string(S.hist_ld));
 
-  // ---- results
   std::vector<int> h_len(B), h_stopv(B), h_kvlen_final(B);
   GENIE_CUDA(cudaMemcpyAsync(h_len.data(), S.d_histlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
   GENIE_CUDA(cudaMemcpyAsync(h_kvlen_final.data(), S.d_kvlen, B * sizeof(int), cudaMemcpyDeviceToHost, s));
   GENIE_CUDA(cudaMemcpyAsync(h_stopv.data(), S.d_stop, B * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (y_out) {
-    hist_to_i64_kernel<<<B, 256, 0, s>>>(S.HIST, bt.hist_ld, S.d_histlen, S.Y64, bt.hist_ld, B);
+    hist_to_i64_kernel<<<B, 256, 0, s>>>(S.HIST, S.hist_ld, S.d_histlen, S.Y64, S.hist_ld, B);
     GENIE_LAUNCHED("hist_to_i64");
-    GENIE_CUDA(cudaMemcpy2DAsync(y_out, (size_t)y_ld * 8, S.Y64, (size_t)bt.hist_ld * 8, (size_t)bt.hist_ld * 8, B,
+    GENIE_CUDA(cudaMemcpy2DAsync(y_out, (size_t)y_ld * 8, S.Y64, (size_t)S.hist_ld * 8, (size_t)S.hist_ld * 8, B,
                                  io_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
   }
   GENIE_CUDA(cudaStreamSynchronize(s));
-  check_tc_error(m);
-  if (m.step_sync) {
-    unsigned flag[2] = {0, 0};
-    GENIE_CUDA(cudaMemcpy(flag, m.step_sync, sizeof(flag), cudaMemcpyDeviceToHost));
-    if (flag[1]) {
-      cudaMemset(m.step_sync, 0, sizeof(flag));
-      GENIE_CHECK(false, "persistent decode step: device-wide barrier timed out");
-    }
-  }
+  check_step_errors(m);
   for (int b = 0; b < B; ++b) {
-    // reference loop variable at exit: index of the step whose stop flag fired, else last index
-    int idx;
-    if (cfg.fixed_steps > 0 || h_stopv[b] < 0) idx = steps_done - 1;
-    else idx = h_stopv[b] - (bt.Ly[b] + 1);     // stop_step stores the history length before that step's token
     if (y_len_out) y_len_out[b] = h_len[b];
-    if (idx_out) idx_out[b] = idx < 0 ? 0 : idx;
+    if (idx_out) idx_out[b] = slot_idx(S.slots[b], h_len[b], h_stopv[b]);
   }
   // measurement aid (bench.py roofline): the dominant decode kernel sits inside a CUDA graph, so it is
-  // replayed here on the final cache state, all layers back to back (2.8 GB of KV >> L2), between events
-  if (m.time_attention > 0 && B > m.skinny_max_rows && B <= 128) {
+  // replayed here on the final cache state, all layers back to back (GBs of KV >> L2), between events
+  if (m.time_attention > 0 && B > m.skinny_max_rows) {
     cudaEvent_t ea, eb;
     cudaEventCreate(&ea); cudaEventCreate(&eb);
     const float scale = 1.0f / std::sqrt(32.0f);
     GENIE_CUDA(cudaEventRecord(ea, s));
     for (int r = 0; r < m.time_attention; ++r)
       for (int l = 0; l < 24; ++l)
-        launch_decode_attention_fused(w.part, 2, w.part_stride * 3, m.layers[l].qkv.b, w.att, w.kv, w.utt_stride,
+        launch_decode_attention_fused(w.part, 2, (long long)B * D * 3, m.layers[l].qkv.b, w.att, w.kv, w.utt_stride,
                                       l * w.layer_stride, w.v_off, w.kv_len, nullptr, B, w.cap, scale, s);
     GENIE_CUDA(cudaEventRecord(eb, s));
     GENIE_CUDA(cudaEventSynchronize(eb));
@@ -584,7 +675,7 @@ void t2s_read(Model& m, int io_dev, int64_t* y_out, int y_ld, int* y_len_out, in
     cudaEventElapsedTime(&t, e.first, e.second);
     t12 += t;
   }
-  m.timing[0] = t01; m.timing[1] = t12; m.timing[2] = t01 + t12; m.timing[3] = (float)steps_done;
+  m.timing[0] = t01; m.timing[1] = t12; m.timing[2] = t01 + t12; m.timing[3] = (float)S.steps_done;
 }
 
 // Inference.py:63-106 in one call: prefill, decode to the stop condition / budget, read the tokens
@@ -596,6 +687,109 @@ int t2s_generate(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   const int rc = t2s_decode_steps(m, max_steps, cancel, nullptr, nullptr);
   t2s_read(m, io_dev, y_out, y_ld, y_len_out, idx_out);
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// continuous batching (SURVEY 8f-1 / BASELINE config 5): slots admitted and released while others decode
+// ---------------------------------------------------------------------------------------------------------------
+void t2s_pool_create(Model& m, int n_slots, int kv_cap, int max_prompt_tokens, int max_steps) {
+  GENIE_CHECK(n_slots >= 1 && n_slots <= 1024, "pool: n_slots must be 1..1024");
+  GENIE_CHECK(max_steps >= 1 && max_prompt_tokens >= 1, "pool: bad limits");
+  pool_build(m, n_slots, kv_cap, max_prompt_tokens + max_steps + 2, true);
+  GENIE_CUDA(cudaStreamSynchronize(m.stream));
+}
+
+void t2s_pool_admit(Model& m, int n, const int* slots, Prompt* const* prompts, const int64_t* text_seq,
+                    const int* text_len, const float* text_bert, const SamplingCfg* cfgs) {
+  T2SSession& S = session_of(m);
+  GENIE_CHECK(S.pool_mode, "no slot pool on this handle: call genie_t2s_pool_create first");
+  GENIE_CHECK(slots != nullptr, "null slots");
+  admit(m, S, n, slots, prompts, text_seq, text_len, text_bert, cfgs, n, 0);
+}
+
+// up to n_steps decode steps over every active slot; stops early once no slot is active.  The step graph covers
+// the slots [0, rows) with rows = the smallest bucket holding the highest slot in use (free slots exit early)
+int t2s_pool_step(Model& m, int n_steps, int* n_active_out) {
+  T2SSession& S = session_of(m);
+  GENIE_CHECK(S.pool_mode, "no slot pool on this handle");
+  GENIE_CUDA(cudaSetDevice(m.device));
+  cudaStream_t s = m.stream;
+  int hi = -1;
+  for (int i = 0; i < S.n_slots; ++i) if (S.slots[i].in_use) hi = i;
+  int n_act = 0;
+  if (hi >= 0) {
+    static const int buckets[] = {1, 2, 4, 8, 16, 32, 64, 96, 128, 192, 256, 384, 512, 768, 1024};
+    int rows = S.n_slots;
+    for (int bkt : buckets) if (bkt >= hi + 1) { rows = std::min(bkt, S.n_slots); break; }
+    std::vector<int> h_act(rows, 0);
+    for (int k = 0; k < n_steps; ++k) {
+      run_step(m, S, rows);
+      if ((k & 7) == 7 || k + 1 == n_steps) {
+        GENIE_CUDA(cudaMemcpyAsync(h_act.data(), S.d_active, rows * sizeof(int), cudaMemcpyDeviceToHost, s));
+        GENIE_CUDA(cudaStreamSynchronize(s));
+        n_act = 0;
+        for (int b = 0; b < rows; ++b) n_act += h_act[b] ? 1 : 0;
+        if (n_act == 0) break;
+      }
+    }
+    check_step_errors(m);
+  }
+  if (n_active_out) *n_active_out = n_act;
+  return 0;
+}
+
+// state[i]: 0 free, 1 decoding, 2 finished (stopped or budget used; read + release it); n_generated[i] = tokens
+// generated so far (first-stage token included)
+void t2s_pool_poll(Model& m, int* state, int* n_generated, int n) {
+  T2SSession& S = session_of(m);
+  GENIE_CHECK(S.pool_mode, "no slot pool on this handle");
+  GENIE_CHECK(n >= S.n_slots, "poll: arrays shorter than the pool");
+  GENIE_CUDA(cudaSetDevice(m.device));
+  std::vector<int> act(S.n_slots), len(S.n_slots);
+  GENIE_CUDA(cudaMemcpyAsync(act.data(), S.d_active, S.n_slots * sizeof(int), cudaMemcpyDeviceToHost, m.stream));
+  GENIE_CUDA(cudaMemcpyAsync(len.data(), S.d_histlen, S.n_slots * sizeof(int), cudaMemcpyDeviceToHost, m.stream));
+  GENIE_CUDA(cudaStreamSynchronize(m.stream));
+  for (int i = 0; i < S.n_slots; ++i) {
+    const SlotHost& h = S.slots[i];
+    if (state) state[i] = !h.in_use ? 0 : (act[i] ? 1 : 2);
+    if (n_generated) n_generated[i] = h.in_use ? len[i] - h.Ly : 0;
+  }
+}
+
+void t2s_pool_read(Model& m, int slot, int64_t* y, int y_cap, int* y_len, int* idx) {
+  T2SSession& S = session_of(m);
+  GENIE_CHECK(S.pool_mode, "no slot pool on this handle");
+  GENIE_CHECK(slot >= 0 && slot < S.n_slots && S.slots[slot].in_use, "read: slot not in use");
+  GENIE_CUDA(cudaSetDevice(m.device));
+  int len = 0, stop = -1;
+  std::vector<int> row(S.hist_ld);
+  GENIE_CUDA(cudaMemcpyAsync(&len, S.d_histlen + slot, sizeof(int), cudaMemcpyDeviceToHost, m.stream));
+  GENIE_CUDA(cudaMemcpyAsync(&stop, S.d_stop + slot, sizeof(int), cudaMemcpyDeviceToHost, m.stream));
+  GENIE_CUDA(cudaMemcpyAsync(row.data(), S.HIST + (size_t)slot * S.hist_ld, S.hist_ld * sizeof(int),
+                             cudaMemcpyDeviceToHost, m.stream));
+  GENIE_CUDA(cudaStreamSynchronize(m.stream));
+  GENIE_CHECK(y == nullptr || y_cap >= len, "read: y too short, need " + std::to_string(len));
+  if (y) for (int i = 0; i < len; ++i) y[i] = row[i];
+  if (y_len) *y_len = len;
+  if (idx) *idx = slot_idx(S.slots[slot], len, stop);
+}
+
+void t2s_pool_release(Model& m, int slot) {
+  T2SSession& S = session_of(m);
+  GENIE_CHECK(S.pool_mode, "no slot pool on this handle");
+  GENIE_CHECK(slot >= 0 && slot < S.n_slots, "release: slot index out of range");
+  GENIE_CUDA(cudaSetDevice(m.device));
+  if (S.slots[slot].in_use) {   // a slot released while still decoding (cancelled request) stops here
+    GENIE_CUDA(cudaMemsetAsync(S.d_active + slot, 0, sizeof(int), m.stream));
+    S.slots[slot] = SlotHost{};
+  }
+}
+
+void t2s_pool_info(Model& m, int* n_slots, int* kv_cap, int* hist_ld) {
+  T2SSession& S = session_of(m);
+  if (n_slots) *n_slots = S.n_slots;
+  if (kv_cap) *kv_cap = S.cap;
+  if (hist_ld) *hist_ld = S.hist_ld;
 }
 
 }  // namespace genie

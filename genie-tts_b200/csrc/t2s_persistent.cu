@@ -436,16 +436,33 @@ __global__ void __launch_bounds__(NTHR, 1) t2s_step_persistent_kernel(Persistent
   }
 }
 
+// Cooperative launch: the driver either makes all `grid` CTAs co-resident (what the device-wide barrier needs)
+// or fails the launch with cudaErrorCooperativeLaunchTooLarge — never a silent partial residency that would turn
+// every barrier into a 4M-iteration spin.  Kernel nodes keep the attribute under stream capture.
 template <int BR>
 void launch_br(const PersistentStep& a, int grid, cudaStream_t s) {
   constexpr size_t smem = (size_t)BR * FF * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(t2s_step_persistent_kernel<BR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    configured = true;
-  }
-  t2s_step_persistent_kernel<BR><<<grid, NTHR, smem, s>>>(a);
+  static DynSmemAttr attr;
+  attr.ensure(t2s_step_persistent_kernel<BR>, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  GENIE_CUDA(cudaLaunchKernelEx(&cfg, t2s_step_persistent_kernel<BR>, a));
+}
+
+template <int BR>
+int max_resident_ctas() {
+  constexpr size_t smem = (size_t)BR * FF * sizeof(float);
+  static DynSmemAttr attr;
+  attr.ensure(t2s_step_persistent_kernel<BR>, smem);
+  int per_sm = 0, dev = 0, sms = 0;
+  GENIE_CUDA(cudaGetDevice(&dev));
+  GENIE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  GENIE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, t2s_step_persistent_kernel<BR>, NTHR, smem));
+  return per_sm * sms;
 }
 
 }  // namespace
@@ -453,6 +470,14 @@ void launch_br(const PersistentStep& a, int grid, cudaStream_t s) {
 int persistent_step_chunks(int B, int grid) {
   int n = grid / (B * NH);
   return n < 1 ? 1 : (n > 8 ? 8 : n);
+}
+
+// can `grid` CTAs of the batch-B instantiation be resident at once on the current device (an otherwise idle one)?
+bool persistent_step_fits(int B, int grid) {
+  if (B < 1 || B > 8) return false;
+  const int cap = B == 1 ? max_resident_ctas<1>() : B == 2 ? max_resident_ctas<2>() : B <= 4 ? max_resident_ctas<4>()
+                                                                                             : max_resident_ctas<8>();
+  return cap >= grid;
 }
 
 void launch_t2s_step_persistent(const PersistentStep& a, int grid, cudaStream_t s) {

@@ -331,12 +331,8 @@ tc_conv_gemm_kernel(ConvGemm p, int* err_flag) {
 template <int NT, int SPLIT_A, int W_LO>
 void launch_tc(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   constexpr size_t smem = tc_smem_bytes<NT, SPLIT_A, W_LO>();
-  static bool configured = false;
-  if (!configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_conv_gemm_kernel<NT, SPLIT_A, W_LO>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static DynSmemAttr attr;
+  attr.ensure(tc_conv_gemm_kernel<NT, SPLIT_A, W_LO>, smem);
   const int nq = p.M + p.q_extra;
   dim3 grid((nq + BM - 1) / BM, ((p.Cout + NT - 1) / NT) * p.ksplit, p.B);
   tc_conv_gemm_kernel<NT, SPLIT_A, W_LO><<<grid, tc_threads<NT, SPLIT_A, W_LO>(), smem, s>>>(p, err_flag);

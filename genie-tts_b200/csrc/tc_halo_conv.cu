@@ -533,11 +533,8 @@ bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t 
   if (smem < EPI_BYTES) smem = EPI_BYTES;
   smem += 1024;
   if (smem > 200 * 1024) return false;
-  static size_t configured = 0;
-  if (smem > configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_halo_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  attr.ensure(tc_halo_bulk_kernel, smem);
   const int nq = p.M + p.q_extra;
   dim3 grid((nq + 127) / 128, p.Cout / BNT, p.B);
   tc_halo_bulk_kernel<<<grid, BTHR, smem, s>>>(p, g, err_flag);
@@ -567,12 +564,8 @@ bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   if (smem < EPI_BYTES) smem = EPI_BYTES;
   smem += 1024;
   if (smem > 200 * 1024) return false;
-  static size_t configured = 0;
-  if (smem > configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_halo_conv_kernel<NT, MT, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  attr.ensure(tc_halo_conv_kernel<NT, MT, ROWB>, smem);
   const int nq = p.M + p.q_extra;
   dim3 grid((nq + MT * 128 - 1) / (MT * 128), (p.Cout + NT - 1) / NT, p.B);
   tc_halo_conv_kernel<NT, MT, ROWB><<<grid, NTHR, smem, s>>>(p, g, err_flag);

@@ -258,11 +258,8 @@ void launch_pair(const ConvGemm& p, const __half* w1, const float* bias1, int kp
   g.i_bytes = up((size_t)(ROWS + IPAD) * 2 * C);
   g.w_bytes = up((size_t)g.k * C * 2 * C);
   const size_t smem = (size_t)g.x_bytes + g.i_bytes + g.w_bytes + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_pair_conv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  attr.ensure(tc_pair_conv_kernel<C>, smem);
   dim3 grid((p.M + g.T - 1) / g.T, 1, p.B);
   tc_pair_conv_kernel<C><<<grid, NTHR, smem, s>>>(p, w1, bias1, kpad1, g, err_flag);
   GENIE_LAUNCHED("tc_pair_conv");

@@ -219,11 +219,8 @@ __global__ void __launch_bounds__(THR) tc_small_gemm_kernel(SmallGemm p, int* er
 template <int NT, int THR>
 void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
   constexpr size_t smem = 2 * NKB * (THR == 256 ? 8192 : 16384) + (size_t)NKB * NT * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    GENIE_CUDA(cudaFuncSetAttribute(tc_small_gemm_kernel<NT, THR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static DynSmemAttr attr;
+  attr.ensure(tc_small_gemm_kernel<NT, THR>, smem);
   launch_pdl(tc_small_gemm_kernel<NT, THR>, dim3((p.N + NT - 1) / NT, p.K / KS), dim3(THR), smem, s, p, err_flag);
   GENIE_LAUNCHED("tc_small_gemm");
 }

@@ -173,7 +173,10 @@ void prompt_build(Model& m, Prompt& p, const int64_t* ref_seq, int Lr, const flo
   GENIE_CUDA(cudaSetDevice(m.device));
   cudaStream_t s = m.stream;
   Workspace& ws = m.ws;
-  p.model = &m; p.Lr = Lr;
+  p.device = m.device; p.model_uid = m.owner->uid; p.Lr = Lr;
+  for (int i = 0; i < Lr; ++i)
+    GENIE_CHECK(ref_seq[i] >= 0 && ref_seq[i] < m.text_vocab, "prompt: ref_seq id out of range (phoneme table has " +
+                                                                  std::to_string(m.text_vocab) + " rows)");
   p.ref_seq = dev_alloc<long long>(p.owned, Lr);
   GENIE_CUDA(cudaMemcpyAsync(p.ref_seq, ref_seq, Lr * sizeof(long long), cudaMemcpyHostToDevice, s));
   if (ref_bert) {
@@ -270,12 +273,17 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   int* o2 = hoff.data(); int* oL = o2 + (B + 1); int* oTok = oL + (B + 1);
   int maxT2 = 0, maxL = 0, nsem = 0, ntext = 0;
   for (int b = 0; b < B; ++b) {
-    GENIE_CHECK(prompts[b] && prompts[b]->model == &m, "prompt does not belong to this model");
+    GENIE_CHECK(prompts[b] && prompts[b]->model_uid == m.owner->uid, "prompt does not belong to this model");
     GENIE_CHECK(sem_len[b] > 0 && text_len[b] > 0, "vits: empty utterance");
     o2[b + 1] = o2[b] + 2 * sem_len[b]; oL[b + 1] = oL[b] + text_len[b]; oTok[b + 1] = oTok[b] + sem_len[b];
     maxT2 = std::max(maxT2, 2 * sem_len[b]); maxL = std::max(maxL, text_len[b]);
   }
   const int R2 = o2[B]; const int RL = oL[B]; nsem = oTok[B]; ntext = RL;
+  if (!io_dev) {   // host-resident ids are validated here; device-resident ones are clamped + flagged by the gather
+    for (int i = 0; i < nsem; ++i) GENIE_CHECK(sem[i] >= 0 && sem[i] < 1024, "vits: semantic id out of range [0, 1024)");
+    for (int i = 0; i < ntext; ++i)
+      GENIE_CHECK(text_seq[i] >= 0 && text_seq[i] < m.vits_text_vocab, "vits: text_seq id out of range");
+  }
   for (int st = 1; st <= 5; ++st)
     for (int b = 0; b <= B; ++b) hoff[(size_t)(2 + st) * (B + 1) + b] = o2[b] * mult[st];
   std::vector<int> r2u(R2);
@@ -317,11 +325,11 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   float* bff = ws.get<float>("v.ff", RM * 768);
 
   // ---- K9: codebook dequant + x2 nearest upsample (vits#[273-292]); ssl_proj
-  launch_gather_rows(Q768, 768, m.codebook, 768, SEM, nsem, 2, s);
+  launch_gather_rows(Q768, 768, m.codebook, 768, SEM, nsem, 2, s, 1024, m.tc_err);
   run_conv(m, m.ssl_proj, Q768, 768, Y, 192, s2);
   // ---- K10: encoder_ssl (3), text embedding + encoder_text (6)
   run_vits_encoder(m, m.enc_ssl, 3, Y, s2, bq, bk, bv, batt, btmp, bff);
-  launch_gather_rows(TX, 192, m.vits_text_emb, 192, TXT, ntext, 1, s);
+  launch_gather_rows(TX, 192, m.vits_text_emb, 192, TXT, ntext, 1, s, m.vits_text_vocab, m.tc_err);
   run_vits_encoder(m, m.enc_text, 6, TX, sL, bq, bk, bv, batt, btmp, bff);
   // ---- K11: MRTE (vits#[4891-4964])
   {

@@ -9,14 +9,17 @@
 
 namespace genie {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
+thread_local unsigned long long* t_capture_counter = nullptr;
 int g_sync_debug = []() { const char* e = getenv("GENIE_SYNC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
-int g_pdl_now = 1;
+thread_local int g_pdl_now = 1;
 int g_pdl = []() { const char* e = getenv("GENIE_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
 
 Model::~Model() {
-  if (step_graph) cudaGraphExecDestroy(step_graph);
-  for (void* p : owned) cudaFree(p);
+  cudaSetDevice(device);
+  t2s_session.reset();                 // events of the slot pool and the captured steps before the streams go
+  t2s_graphs.reset();
+  for (void* p : ctx_owned) cudaFree(p);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
   if (stream2) cudaStreamDestroy(stream2);
@@ -24,7 +27,8 @@ Model::~Model() {
   if (stream4) cudaStreamDestroy(stream4);
   if (ev_join3) cudaEventDestroy(ev_join3);
   if (ev_join4) cudaEventDestroy(ev_join4);
-  if (stream) cudaStreamDestroy(stream);
+  if (stream && stream_owned) cudaStreamDestroy(stream);
+  // the weights (owner) are released with the last handle that shares them
 }
 
 namespace {
@@ -100,7 +104,7 @@ struct Finalizer {
   float* f32(int g, const std::string& name, float scale = 1.f) {
     const RawTensor& t = raw(g, name);
     if (!t.f16 && scale == 1.f) return reinterpret_cast<float*>(t.d);
-    float* d = dev_alloc<float>(m.owned, t.numel);
+    float* d = dev_alloc<float>(m.owner->owned, t.numel);
     m.weight_bytes += t.numel * 4;
     to_f32_kernel<<<(unsigned)((t.numel + 255) / 256), 256, 0, s>>>(t.d, t.f16, d, t.numel, scale);
     GENIE_LAUNCHED("to_f32");
@@ -122,7 +126,7 @@ struct Finalizer {
     GENIE_CHECK(v.dims.size() == 3, "conv weight must be 3-D: " + prefix);
     Conv c;
     c.Cout = (int)v.dims[0]; c.Cin = (int)v.dims[1]; c.k = (int)v.dims[2];
-    float* out = dev_alloc<float>(m.owned, v.numel);
+    float* out = dev_alloc<float>(m.owner->owned, v.numel);
     m.weight_bytes += v.numel * 4;
     const RawTensor* gt = wn ? &raw(g, prefix + ".weight_g") : nullptr;
     prep_weight_kernel<<<c.Cout, 256, 0, s>>>(v.d, v.f16, gt ? gt->d : nullptr, gt ? gt->f16 : 0, c.Cout, c.Cin, c.k,
@@ -138,7 +142,7 @@ struct Finalizer {
     ConvT c;
     c.Cin = (int)v.dims[0]; c.Cout = (int)v.dims[1]; c.k = (int)v.dims[2];
     c.stride = stride; c.pad = (c.k - stride) / 2;
-    float* out = dev_alloc<float>(m.owned, v.numel);
+    float* out = dev_alloc<float>(m.owner->owned, v.numel);
     m.weight_bytes += v.numel * 4;
     prep_weight_kernel<<<c.Cin, 256, 0, s>>>(v.d, v.f16, gt.d, gt.f16, c.Cin, c.Cout, c.k, scale, out, 1);
     GENIE_LAUNCHED("prep_weight");
@@ -179,14 +183,14 @@ struct Finalizer {
     TcW t;
     t.kpad = ((ntaps * Cin + 63) / 64) * 64;
     const long long n = (long long)Cout * t.kpad;
-    __half* hi = dev_alloc<__half>(m.owned, n);
-    __half* lo = dev_alloc<__half>(m.owned, n);
+    __half* hi = dev_alloc<__half>(m.owner->owned, n);
+    __half* lo = dev_alloc<__half>(m.owner->owned, n);
     m.weight_bytes += n * 4;
     pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(w, co_stride, tap_stride, ntaps, Cin, Cout, t.kpad, hi, lo);
     GENIE_LAUNCHED("pack_tc");
     t.hi = hi; t.lo = lo;
     if (tap_stride == Cin && co_stride == (long long)ntaps * Cin && pretile_w128_supported(Cin, Cout, ntaps)) {
-      __half* tiles = dev_alloc<__half>(m.owned, n);
+      __half* tiles = dev_alloc<__half>(m.owner->owned, n);
       m.weight_bytes += n * 2;
       launch_pretile_w128(hi, Cout, t.kpad, Cin, ntaps, tiles, s);
       t.tiles = tiles;
@@ -202,7 +206,7 @@ struct Finalizer {
     }
     if (c.k == c.stride && c.pad == 0 && c.Cin % 4 == 0) {
       c.tc_fused = pack(c.w, c.Cin, 0, 1, c.Cin, c.Cout * c.k);
-      float* bf = dev_alloc<float>(m.owned, (size_t)c.Cout * c.k);
+      float* bf = dev_alloc<float>(m.owner->owned, (size_t)c.Cout * c.k);
       for (int r = 0; r < c.k; ++r) {
         if (c.b) GENIE_CUDA(cudaMemcpyAsync(bf + (size_t)r * c.Cout, c.b, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, s));
         else GENIE_CUDA(cudaMemsetAsync(bf + (size_t)r * c.Cout, 0, (size_t)c.Cout * 4, s));
@@ -239,7 +243,7 @@ struct Finalizer {
       for (int j = 0; j < 3; ++j)
         for (int c = 0; c < 3; ++c) { pack_conv(m.res[i * 3 + j].c1[c]); pack_conv(m.res[i * 3 + j].c2[c]); }
     }
-    m.tc_err = dev_alloc<int>(m.owned, 1);
+    m.tc_err = dev_alloc<int>(m.ctx_owned, 1);
     GENIE_CUDA(cudaMemsetAsync(m.tc_err, 0, sizeof(int), s));
   }
 
@@ -249,6 +253,7 @@ struct Finalizer {
     GENIE_CHECK(m.div_term != nullptr, "genie_model_set_constants must be called before finalize");
     // ---- T2S
     m.text_emb = f32(E, "encoder.ar_text_embedding.word_embeddings.weight");
+    m.text_vocab = (int)raw(E, "encoder.ar_text_embedding.word_embeddings.weight").dims[0];
     m.text_alpha = f32(E, "encoder.ar_text_position.alpha");
     m.bert_proj = linear(E, "encoder.bert_proj.weight", "encoder.bert_proj.bias", false);
     m.audio_emb = f32(T, "ar_audio_embedding.word_embeddings.weight");
@@ -264,11 +269,25 @@ struct Finalizer {
       L.ln1_g = f32(T, p + "norm1.weight"); L.ln1_b = f32(T, p + "norm1.bias");
       L.ln2_g = f32(T, p + "norm2.weight"); L.ln2_b = f32(T, p + "norm2.bias");
     }
+    // pointer table of the persistent decode step (t2s_persistent.cu): immutable, shared by every context
+    if (m.layers[0].qkv.w_f16 && m.predict.w_f16) {
+      std::vector<StepLayerPtrs> hl(24);
+      for (int l = 0; l < 24; ++l) {
+        const T2SLayer& L = m.layers[l];
+        hl[l] = StepLayerPtrs{reinterpret_cast<const __half*>(L.qkv.w), reinterpret_cast<const __half*>(L.out.w),
+                              reinterpret_cast<const __half*>(L.ff1.w), reinterpret_cast<const __half*>(L.ff2.w),
+                              L.qkv.b, L.out.b, L.ff1.b, L.ff2.b, L.ln1_g, L.ln1_b, L.ln2_g, L.ln2_b};
+      }
+      StepLayerPtrs* d = dev_alloc<StepLayerPtrs>(m.owner->owned, 24);
+      GENIE_CUDA(cudaMemcpy(d, hl.data(), sizeof(StepLayerPtrs) * 24, cudaMemcpyHostToDevice));
+      m.step_layers_dev = d;
+    }
+    GENIE_CUDA(cudaDeviceGetAttribute(&m.num_sms, cudaDevAttrMultiProcessorCount, m.device));
     // prompt-time VQ (t2s_encoder#[2-48])
     m.ssl_vq = conv(E, "vits.ssl_proj");
     m.codebook_enc = f32(E, "vits.quantizer.vq.layers.0._codebook.embed");
     {
-      float* sq = dev_alloc<float>(m.owned, 1024);
+      float* sq = dev_alloc<float>(m.owner->owned, 1024);
       launch_row_sqnorm(m.codebook_enc, 768, 768, 1024, sq, s);
       m.codebook_enc_sq = sq;
     }
@@ -276,6 +295,7 @@ struct Finalizer {
     const std::string q = "vq_model.";
     m.codebook = f32(V, q + "quantizer.vq.layers.0._codebook.embed");
     m.vits_text_emb = f32(V, q + "enc_p.text_embedding.weight");
+    m.vits_text_vocab = (int)raw(V, q + "enc_p.text_embedding.weight").dims[0];
     m.ssl_proj = conv(V, q + "enc_p.ssl_proj");
     m.enc_proj = conv(V, q + "enc_p.proj");
     enc_layers(m.enc_ssl, 3, q + "enc_p.encoder_ssl.");
@@ -326,7 +346,7 @@ struct Finalizer {
       m.ref_enc = mel_style(V, q + "ref_enc.");
     }
     pack_all();
-    m.dft = dev_alloc<float>(m.owned, 1408LL * 2048);
+    m.dft = dev_alloc<float>(m.owner->owned, 1408LL * 2048);
     launch_dft_matrix(m.dft, s);
     GENIE_CUDA(cudaStreamSynchronize(s));
     m.finalized = true;
@@ -371,6 +391,7 @@ void check_tc_error(Model& m) {
   GENIE_CUDA(cudaMemcpy(&h, m.tc_err, sizeof(int), cudaMemcpyDeviceToHost));
   if (h) {
     cudaMemset(m.tc_err, 0, sizeof(int));
+    if (h == 2) throw Error{"input id out of range (phoneme ids must be < the embedding rows, semantic ids < 1025)"};
     throw Error{"tcgen05 pipeline timed out waiting on an mbarrier (tc_gemm.cu)"};
   }
 }

@@ -10,6 +10,7 @@ them inside every encoder / vocoder call."""
 from __future__ import annotations
 
 import os
+import threading
 from typing import Callable, Dict, Optional
 
 import numpy as np
@@ -29,7 +30,9 @@ def set_feature_extractors(hubert=None, sv=None) -> None:
 
 class ReferenceAudio:
     _prompt_cache: Dict[str, "ReferenceAudio"] = LRUCacheDict(
-        capacity=int(os.getenv("Max_Cached_Reference_Audio", "10")))
+        capacity=int(os.getenv("Max_Cached_Reference_Audio", "10")),
+        on_evict=lambda k, inst: inst._drop_device_prompts())        # an evicted reference frees its HBM
+    _device_lock = threading.RLock()      # device prompts are built from request threads (server) and the worker
 
     def __new__(cls, prompt_wav: str, prompt_text: str, language: str):
         if prompt_wav in cls._prompt_cache:
@@ -88,9 +91,10 @@ class ReferenceAudio:
         self._drop_device_prompts()
 
     def _drop_device_prompts(self) -> None:
-        for p in getattr(self, "_device_prompts", {}).values():
-            p.close()
-        self._device_prompts = {}
+        with self._device_lock:
+            for p in getattr(self, "_device_prompts", {}).values():
+                p.close()
+            self._device_prompts = {}
 
     @classmethod
     def clear_cache(cls) -> None:
@@ -101,9 +105,15 @@ class ReferenceAudio:
     # -- device side -----------------------------------------------------------
     def device_prompt(self, model):
         """B200Prompt for ``model`` (built once per (reference audio, character))."""
+        with self._device_lock:
+            return self._device_prompt_locked(model)
+
+    def _device_prompt_locked(self, model):
         key = id(model)
+        for k in [k for k, q in self._device_prompts.items() if q.closed]:   # models closed / evicted since
+            del self._device_prompts[k]
         p = self._device_prompts.get(key)
-        if p is None or not p._h:
+        if p is None or p.closed or p.model is not model:
             sv = None
             if model.is_v2pp:
                 if self.sv_emb is None:

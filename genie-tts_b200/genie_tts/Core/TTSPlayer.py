@@ -150,7 +150,8 @@ class TTSPlayer:
 
     # -- public API --------------------------------------------------------------
     def start_session(self, play: bool = False, split: bool = False, save_path: Optional[str] = None,
-                      chunk_callback: Optional[Callable[[Optional[bytes]], None]] = None) -> None:
+                      chunk_callback: Optional[Callable[[Optional[bytes]], None]] = None, sampling=None) -> None:
+        """``sampling`` (extension): SamplingParams of this session; None = the reference's graph constants."""
         with self._api_lock:
             if self._worker is None or not self._worker.is_alive():
                 self._worker = threading.Thread(target=self._tts_worker_loop, daemon=True)
@@ -159,6 +160,11 @@ class TTSPlayer:
                 self._playback_worker = threading.Thread(target=self._playback_worker_loop, daemon=True)
                 self._playback_worker.start()
             tts_client.stop_event.clear()
+            if sampling is not None:
+                tts_client.sampling = sampling
+            else:
+                from ..engine import SamplingParams
+                tts_client.sampling = SamplingParams()
             clear_queue(self._text_queue)
             clear_queue(self._audio_queue)
             self._tts_done_event.clear()

@@ -97,8 +97,20 @@ def _prep_save_path(save_path) -> Optional[str]:
     return save_path
 
 
+def _sampling(top_k, top_p, temperature, repetition_penalty, seed):
+    """Sampling knobs surfaced through the public API.  The reference bakes them into its
+    graphs as constants (top_k 15, temperature 1.0, repetition_penalty 1.35, no top-p: SURVEY K7) — ``None``
+    keeps exactly those; ``seed=None`` draws fresh noise per sentence like the unseeded graphs."""
+    from .engine import SamplingParams
+    return SamplingParams(top_k=int(top_k or 0), top_p=float(top_p) if top_p else 1.0,
+                          temperature=float(temperature or 0.0), repetition_penalty=float(repetition_penalty or 0.0),
+                          seed=seed)
+
+
 async def tts_async(character_name: str, text: str, play: bool = False, split_sentence: bool = False,
-                    save_path: Union[str, PathLike, None] = None) -> AsyncIterator[bytes]:
+                    save_path: Union[str, PathLike, None] = None, *, top_k: Optional[int] = None,
+                    top_p: Optional[float] = None, temperature: Optional[float] = None,
+                    repetition_penalty: Optional[float] = None, seed: Optional[int] = None) -> AsyncIterator[bytes]:
     if character_name not in _reference_audios:
         raise ValueError("Please call 'set_reference_audio' first to set the reference audio.")
     save_path = _prep_save_path(save_path)
@@ -106,7 +118,8 @@ async def tts_async(character_name: str, text: str, play: bool = False, split_se
     loop = asyncio.get_running_loop()
     _activate(character_name)
     tts_player.start_session(play=play, split=split_sentence, save_path=save_path,
-                             chunk_callback=lambda c: loop.call_soon_threadsafe(q.put_nowait, c))
+                             chunk_callback=lambda c: loop.call_soon_threadsafe(q.put_nowait, c),
+                             sampling=_sampling(top_k, top_p, temperature, repetition_penalty, seed))
     tts_player.feed(text)
     tts_player.end_session()
     while True:
@@ -117,13 +130,18 @@ async def tts_async(character_name: str, text: str, play: bool = False, split_se
 
 
 def tts(character_name: str, text: str, play: bool = False, split_sentence: bool = True,
-        save_path: Union[str, PathLike, None] = None) -> None:
+        save_path: Union[str, PathLike, None] = None, *, top_k: Optional[int] = None, top_p: Optional[float] = None,
+        temperature: Optional[float] = None, repetition_penalty: Optional[float] = None,
+        seed: Optional[int] = None) -> None:
+    """Reference signature (Internal.py:265-309) plus keyword-only sampling knobs, all defaulting to the
+    reference's graph constants."""
     if character_name not in _reference_audios:
         logger.error("Please call 'set_reference_audio' first to set the reference audio.")
         return
     save_path = _prep_save_path(save_path)
     _activate(character_name)
-    tts_player.start_session(play=play, split=split_sentence, save_path=save_path)
+    tts_player.start_session(play=play, split=split_sentence, save_path=save_path,
+                             sampling=_sampling(top_k, top_p, temperature, repetition_penalty, seed))
     tts_player.feed(text)
     tts_player.end_session()
     tts_player.wait_for_tts_completion()

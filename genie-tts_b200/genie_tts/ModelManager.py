@@ -63,11 +63,21 @@ class GSVModel:
 class ModelManager:
     def __init__(self, device: Optional[int] = None):
         cap = int(os.getenv("Max_Cached_Character_Models", "3"))
-        self.character_to_model: Dict[str, object] = LRUCacheDict(capacity=cap)
+        # an evicted character releases its HBM at once: the model closes its device prompts and itself (a cached
+        # ReferenceAudio rebuilds its device prompt on the next use, ``get`` reloads the weights lazily)
+        self.character_to_model: Dict[str, object] = LRUCacheDict(capacity=cap, on_evict=self._evicted)
         self.character_to_language: Dict[str, str] = {}
         self.character_model_paths: Dict[str, str] = {}
         self.device = int(os.getenv("GENIE_DEVICE", "0")) if device is None else device
         self.providers = ["B200ExecutionProvider"]     # the reference pins CPUExecutionProvider (:125)
+
+    @staticmethod
+    def _evicted(name: str, model) -> None:
+        logger.info(f"Character {name.capitalize()} evicted from the model cache.")
+        try:
+            model.close()
+        except Exception as e:                     # never let an eviction break the load that caused it
+            logger.error(f"Error while closing evicted character {name}: {e}")
 
     def load_character(self, character_name: str, model_dir: str, language: str) -> bool:
         name = character_name.lower()
@@ -80,11 +90,7 @@ class ModelManager:
         except Exception as e:                     # same contract as the reference: log + False
             logger.error(f"Error: Failed to load model directory '{model_dir}'.\nDetails: {e}")
             return False
-        evicted = [k for k in list(self.character_to_model.keys())]
-        self.character_to_model[name] = model
-        for k in evicted:                          # free HBM of whatever the LRU just dropped
-            if k not in self.character_to_model:
-                gc.collect()
+        self.character_to_model[name] = model      # may evict (and close) the least recently used character
         self.character_to_language[name] = language
         self.character_model_paths[name] = model_dir
         logger.info(f"Character {name.capitalize()} loaded successfully.\n- Model Path: {model_dir}\n"
@@ -120,7 +126,7 @@ class ModelManager:
         if name in self.character_to_model:
             model = self.character_to_model[name]
             del self.character_to_model[name]
-            model.close()
+            model.close()                          # waits for a call in flight, closes the model's device prompts
             gc.collect()
             logger.info(f"Character {name.capitalize()} removed successfully.")
 

@@ -1,8 +1,16 @@
-"""FastAPI front end (reference: src/genie_tts/Server.py:25-165): same routes and payloads;
-/tts streams raw s16 PCM @32 kHz, one chunk per sentence."""
+"""FastAPI front end: the reference's REST surface (src/genie_tts/Server.py:25-165 — same six routes, same JSON
+payloads, /tts streams raw s16 PCM @32 kHz, one chunk per sentence) on top of ``SynthesisService``.
+
+What is different from the reference is behind the routes: there is no global ``tts_player`` / ``context`` on the
+request path.  Every /tts is a ``RequestStream`` of per-sentence futures served by continuous batching on every GPU
+of the box, so concurrent requests neither wait for each other's sentences nor clear each other's queues (the
+reference's ``start_session`` does, Core/TTSPlayer.py:185-186)."""
 from __future__ import annotations
 
 import asyncio
+import logging
+import os
+import threading
 from typing import AsyncIterator, Optional
 
 import uvicorn
@@ -11,11 +19,30 @@ from fastapi.responses import StreamingResponse
 from pydantic import BaseModel
 
 from .Audio.ReferenceAudio import ReferenceAudio
-from .Core.TTSPlayer import tts_player
-from .Internal import _activate, _reference_audios, load_character, set_reference_audio, unload_character
-from .ModelManager import model_manager
+from .Internal import (_prep_save_path, _reference_audios, _sampling, check_onnx_model_dir, set_reference_audio)
+from .Service import RequestStream, SynthesisService
+from .Utils.Language import normalize_language
 
+logger = logging.getLogger(__name__)
 app = FastAPI()
+_service: Optional[SynthesisService] = None
+_service_lock = threading.Lock()
+
+
+def get_service() -> SynthesisService:
+    """One service per server process, created on first use (needs a GPU)."""
+    global _service
+    with _service_lock:
+        if _service is None:
+            _service = SynthesisService(n_slots=int(os.getenv("GENIE_SLOTS", "128")),
+                                        kv_capacity=int(os.getenv("GENIE_KV_CAPACITY", "1024")))
+        return _service
+
+
+def set_service(service: Optional[SynthesisService]) -> None:
+    global _service
+    with _service_lock:
+        _service = service
 
 
 class CharacterPayload(BaseModel):
@@ -40,12 +67,31 @@ class TTSPayload(BaseModel):
     text: str
     split_sentence: bool = False
     save_path: Optional[str] = None
+    # extension: sampling knobs, None = the reference's graph constants
+    top_k: Optional[int] = None
+    top_p: Optional[float] = None
+    temperature: Optional[float] = None
+    repetition_penalty: Optional[float] = None
+    seed: Optional[int] = None
+
+
+def _reference_of(name: str) -> Optional[ReferenceAudio]:
+    entry = _reference_audios.get(name)
+    if entry is None:
+        return None
+    if "reference" in entry:
+        return entry["reference"]           # type: ignore[return-value]
+    return ReferenceAudio(prompt_wav=entry["audio_path"], prompt_text=entry["audio_text"], language=entry["language"])
 
 
 @app.post("/load_character")
 def load_character_endpoint(payload: CharacterPayload):
     try:
-        load_character(payload.character_name, payload.onnx_model_dir, payload.language)
+        check_onnx_model_dir(payload.onnx_model_dir)
+        language = normalize_language(payload.language)
+        if language not in ("Japanese", "English", "Chinese", "Hybrid-Chinese-English"):
+            raise ValueError("Unknown language")
+        get_service().load_character(payload.character_name, payload.onnx_model_dir, language)
     except Exception as e:
         raise HTTPException(status_code=500, detail=str(e))
     return {"status": "success", "message": f"Character '{payload.character_name}' loaded."}
@@ -54,7 +100,7 @@ def load_character_endpoint(payload: CharacterPayload):
 @app.post("/unload_character")
 def unload_character_endpoint(payload: UnloadCharacterPayload):
     try:
-        unload_character(payload.character_name)
+        get_service().unload_character(payload.character_name)
     except Exception as e:
         raise HTTPException(status_code=500, detail=str(e))
     return {"status": "success", "message": f"Character '{payload.character_name}' unloaded."}
@@ -69,43 +115,51 @@ def set_reference_audio_endpoint(payload: ReferenceAudioPayload):
     return {"status": "success", "message": "Reference audio set."}
 
 
-def run_tts_in_background(character_name: str, text: str, split_sentence: bool, save_path: Optional[str],
-                          chunk_callback) -> None:
-    try:
-        _activate(character_name)
-        tts_player.start_session(play=False, split=split_sentence, save_path=save_path, chunk_callback=chunk_callback)
-        tts_player.feed(text)
-        tts_player.end_session()
-        tts_player.wait_for_tts_completion()
-    except Exception:
-        chunk_callback(None)
-        raise
-
-
-async def audio_stream_generator(queue: "asyncio.Queue") -> AsyncIterator[bytes]:
-    while True:
-        chunk = await queue.get()
-        if chunk is None:
-            return
+async def audio_stream_generator(stream: RequestStream) -> AsyncIterator[bytes]:
+    """Sentence futures -> PCM chunks, in text order, without blocking the event loop."""
+    from .Service import pcm16
+    saved = []
+    for fut in stream.futures:
+        try:
+            audio = await asyncio.wrap_future(fut)
+        except Exception as e:                      # reference: log, keep the stream alive (TTSPlayer.py:109-114)
+            logger.error(f"/tts: sentence failed: {e}")
+            continue
+        if audio is None or len(audio) == 0:
+            continue
+        chunk = pcm16(audio)
+        if stream.save_path:
+            saved.append(chunk)
         yield chunk
+    if stream.save_path and saved:
+        stream._saved = saved
+        stream.finish()
 
 
 @app.post("/tts")
 async def tts_endpoint(payload: TTSPayload):
-    if payload.character_name not in _reference_audios:
+    svc = get_service()
+    ref = _reference_of(payload.character_name)
+    if ref is None:
         raise HTTPException(status_code=404, detail="Character not found or reference audio not set.")
-    if model_manager.get(payload.character_name) is None:
+    svc.set_reference(payload.character_name, ref)
+    try:
+        sp = None
+        if any(v is not None for v in (payload.top_k, payload.top_p, payload.temperature,
+                                       payload.repetition_penalty, payload.seed)):
+            sp = _sampling(payload.top_k, payload.top_p, payload.temperature, payload.repetition_penalty, payload.seed)
+        loop = asyncio.get_running_loop()
+        # phonemisation + dispatch happen off the event loop (G2P is host work of unbounded cost)
+        stream = await loop.run_in_executor(None, lambda: svc.submit(
+            payload.character_name, payload.text, payload.split_sentence, _prep_save_path(payload.save_path), sp))
+    except KeyError:
         raise HTTPException(status_code=404, detail="Character not loaded.")
-    loop = asyncio.get_running_loop()
-    q: "asyncio.Queue" = asyncio.Queue()
-    loop.run_in_executor(None, run_tts_in_background, payload.character_name, payload.text, payload.split_sentence,
-                         payload.save_path, lambda c: loop.call_soon_threadsafe(q.put_nowait, c))
-    return StreamingResponse(audio_stream_generator(q), media_type="audio/wav")
+    return StreamingResponse(audio_stream_generator(stream), media_type="audio/wav")
 
 
 @app.post("/stop")
 def stop_endpoint():
-    tts_player.stop()
+    get_service().stop_all()
     return {"status": "success", "message": "TTS stopped."}
 
 
@@ -115,5 +169,13 @@ def clear_reference_audio_cache_endpoint():
     return {"status": "success", "message": "Reference audio cache cleared."}
 
 
+@app.get("/stats")
+def stats_endpoint():
+    """Extension: per-replica scheduler counters (batches, requests, latency percentiles)."""
+    return get_service().stats()
+
+
 def start_server(host: str = "127.0.0.1", port: int = 8000, workers: int = 1):
+    # one process drives every GPU of the box (one scheduler thread per GPU and character); `workers` > 1 would
+    # duplicate the weights per worker process, exactly as the reference's uvicorn workers do (Server.py:165)
     uvicorn.run(app, host=host, port=port, workers=workers)

@@ -6,9 +6,10 @@ from collections import OrderedDict
 class LRUCacheDict(OrderedDict):
     """Dict with a capacity: reads refresh recency, inserts evict the least recently used."""
 
-    def __init__(self, capacity: int):
+    def __init__(self, capacity: int, on_evict=None):
         super().__init__()
         self.capacity = max(1, int(capacity))
+        self.on_evict = on_evict          # called with (key, value) for entries the capacity pushes out
 
     def __getitem__(self, key):
         val = OrderedDict.__getitem__(self, key)
@@ -19,7 +20,9 @@ class LRUCacheDict(OrderedDict):
         OrderedDict.__setitem__(self, key, value)
         self.move_to_end(key)
         while len(self) > self.capacity:
-            self.popitem(last=False)
+            k, v = self.popitem(last=False)
+            if self.on_evict is not None:
+                self.on_evict(k, v)
 
 
 def clear_queue(q: "queue.Queue") -> None:

@@ -23,7 +23,8 @@ class GenieNativeError(RuntimeError):
 
 class Sampling(C.Structure):
     _fields_ = [("top_k", C.c_int), ("temperature", C.c_float), ("repetition_penalty", C.c_float),
-                ("greedy", C.c_int), ("seed", C.c_ulonglong), ("max_steps", C.c_int), ("fixed_steps", C.c_int)]
+                ("greedy", C.c_int), ("seed", C.c_ulonglong), ("max_steps", C.c_int), ("fixed_steps", C.c_int),
+                ("top_p", C.c_float)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -43,6 +44,8 @@ SIGNATURES = {
     "genie_model_finalize": (C.c_int, [_P]),
     "genie_model_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "genie_model_destroy": (None, [_P]),
+    "genie_context_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "genie_set_stream": (C.c_int, [_P, _P]),
     "genie_prompt_create": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, C.POINTER(_P)]),
     "genie_prompt_create_with_ge": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, C.POINTER(_P)]),
     "genie_prompt_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -53,12 +56,20 @@ SIGNATURES = {
     "genie_t2s_prefill": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P, _P, _P, C.POINTER(Sampling), C.c_int]),
     "genie_t2s_decode_steps": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "genie_t2s_read": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
+    "genie_t2s_pool_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "genie_t2s_pool_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "genie_t2s_admit": (C.c_int, [_P, C.c_int, _P, C.POINTER(_P), _P, _P, _P, _P]),
+    "genie_t2s_pool_step": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "genie_t2s_pool_poll": (C.c_int, [_P, _P, _P, C.c_int]),
+    "genie_t2s_pool_read": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "genie_t2s_release": (C.c_int, [_P, C.c_int]),
     "genie_vits_decode": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_ulonglong, C.c_float,
                                     C.c_int, _P, _P]),
     "genie_debug_record_logits": (C.c_int, [_P, C.c_int]),
     "genie_debug_read_logits": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "genie_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_longlong, C.POINTER(C.c_longlong)]),
     "genie_debug_keep": (C.c_int, [_P, C.c_int]),
+    "genie_debug_sample": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.POINTER(Sampling), _P, C.c_int, _P, _P]),
     "genie_debug_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "genie_profiler_range": (C.c_int, [C.c_int]),

@@ -11,6 +11,8 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import threading
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -48,19 +50,28 @@ def _f32(a) -> np.ndarray:
 @dataclass
 class SamplingParams:
     """Defaults (<=0) fall back to the graph constants: top_k 15, temperature 1.0,
-    repetition_penalty 1.35 (t2s_stage_decoder#[1780-1790]).  ``greedy`` is the
-    test-only switch that makes token sequences comparable with the oracle."""
+    repetition_penalty 1.35 (t2s_stage_decoder#[1780-1790]).  ``top_p`` is an extension (the reference graphs have
+    no top-p node); 1.0 = off.  ``greedy`` is the test-only switch that makes token sequences comparable with the
+    oracle.  ``seed=None`` draws a fresh 64-bit seed per call — the reference's RandomNormalLike nodes are unseeded,
+    so successive sentences must not share a noise stream; pass an int for reproducible output."""
     top_k: int = 0
     temperature: float = 0.0
     repetition_penalty: float = 0.0
     greedy: bool = False
-    seed: int = 0
+    seed: Optional[int] = None
     max_steps: int = 500
     fixed_steps: int = 0
+    top_p: float = 1.0
 
-    def to_c(self) -> N.Sampling:
+    def resolved_seed(self) -> int:
+        if self.seed is None:
+            return int.from_bytes(os.urandom(8), "little")
+        return self.seed & 0xFFFFFFFFFFFFFFFF
+
+    def to_c(self, seed: Optional[int] = None) -> N.Sampling:
         return N.Sampling(self.top_k, self.temperature, self.repetition_penalty, int(self.greedy),
-                          self.seed & 0xFFFFFFFFFFFFFFFF, self.max_steps, self.fixed_steps)
+                          self.resolved_seed() if seed is None else seed, self.max_steps, self.fixed_steps,
+                          float(self.top_p))
 
 
 class _PinnedPool:
@@ -115,6 +126,10 @@ class B200Model:
         self.device = device
         self.is_v2pp = tabs.is_v2pp
         self._h = C.c_void_p(0)
+        self._prompts: "weakref.WeakSet[B200Prompt]" = weakref.WeakSet()   # closed with the model
+        self._contexts: "weakref.WeakSet[B200Model]" = weakref.WeakSet()
+        self._pool = None
+        self.lock = threading.RLock()           # callers that share a handle between threads (server workers)
         L = N.lib()
         N.check(L.genie_model_create(device, C.byref(self._h)))
         try:
@@ -141,10 +156,40 @@ class B200Model:
             raise
 
     # -- lifecycle -----------------------------------------------------------
+    @property
+    def closed(self) -> bool:
+        return not self._h
+
     def close(self) -> None:
-        if self._h:
-            N.lib().genie_model_destroy(self._h)
-            self._h = C.c_void_p(0)
+        """Releases the handle and everything built on it: contexts and device prompts are closed FIRST, so that no
+        live ``B200Prompt`` keeps HBM of an evicted character and none outlives its model by accident (the C side
+        tolerates either order; this is about releasing memory when the LRU evicts a character)."""
+        with self.lock:
+            for c in list(self._contexts):
+                c.close()
+            for p in list(self._prompts):
+                p.close()
+            if self._h:
+                N.lib().genie_model_destroy(self._h)
+                self._h = C.c_void_p(0)
+
+    def create_context(self, cuda_stream: Optional[int] = None) -> "B200Model":
+        """A second independent execution context on the same weights (own stream / workspace / slot pool /
+        graphs): e.g. a continuous-batching scheduler plus a latency-critical batch-1 caller on one GPU.
+        ``cuda_stream``: a caller-owned ``cudaStream_t`` (as int, e.g. ``torch.cuda.Stream().cuda_stream``)."""
+        ctx = object.__new__(B200Model)
+        ctx.model_dir, ctx.device, ctx.is_v2pp, ctx.constants = self.model_dir, self.device, self.is_v2pp, self.constants
+        ctx._h = C.c_void_p(0)
+        ctx._prompts = self._prompts              # prompts are valid on every handle of the model
+        ctx._contexts = weakref.WeakSet()
+        ctx._pool = None
+        ctx.lock = threading.RLock()
+        N.check(N.lib().genie_context_create(self._h, C.c_void_p(cuda_stream or 0), C.byref(ctx._h)))
+        self._contexts.add(ctx)
+        return ctx
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        N.check(N.lib().genie_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
     def __del__(self):
         try:
@@ -234,10 +279,61 @@ class B200Model:
         N.check(N.lib().genie_t2s_read(self._h, 0, _ptr(y), y_ld, _ptr(y_len), _ptr(idx)))
         return [y[b, :y_len[b]].copy() for b in range(B)], [int(i) for i in idx]
 
+    # -- continuous batching: the T2S stage as a pool of decode slots ---------------------------------
+    def pool_create(self, n_slots: int, kv_capacity: int, max_prompt_tokens: int, max_steps: int = 500) -> None:
+        N.check(N.lib().genie_t2s_pool_create(self._h, n_slots, kv_capacity, max_prompt_tokens, max_steps))
+        self._pool = (n_slots, max_prompt_tokens + max_steps + 2)
+
+    def pool_admit(self, slots: Sequence[int], prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
+                   text_berts: Optional[Sequence[Optional[np.ndarray]]] = None,
+                   samplings: Optional[Sequence[SamplingParams]] = None) -> None:
+        """Prefill ``len(slots)`` requests into free slots while the other slots keep their state."""
+        n = len(slots)
+        seqs = [_i64(t) for t in text_seqs]
+        lens = np.asarray([len(t) for t in seqs], dtype=np.int32)
+        cat = np.concatenate(seqs)
+        bert = None
+        if text_berts is not None and any(b is not None and np.any(b) for b in text_berts):
+            bert = np.concatenate([_f32(b) if b is not None else np.zeros((len(s), 1024), np.float32)
+                                   for b, s in zip(text_berts, seqs)], axis=0)
+        sl = np.asarray(slots, dtype=np.int32)
+        hs = (C.c_void_p * n)(*[p._h for p in prompts])
+        sps = None
+        if samplings is not None:
+            sps = (N.Sampling * n)(*[(sp or SamplingParams()).to_c() for sp in samplings])
+        N.check(N.lib().genie_t2s_admit(self._h, n, _ptr(sl), hs, _ptr(cat), _ptr(lens), _ptr(bert),
+                                        C.cast(sps, C.c_void_p) if sps is not None else None))
+
+    def pool_step(self, n_steps: int) -> int:
+        """Up to ``n_steps`` decode steps over all active slots; returns the number still decoding."""
+        n_active = C.c_int(0)
+        N.check(N.lib().genie_t2s_pool_step(self._h, int(n_steps), C.byref(n_active)))
+        return n_active.value
+
+    def pool_poll(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(state[n_slots]: 0 free / 1 decoding / 2 finished, tokens generated so far per slot)."""
+        n = self._pool[0]
+        state = np.zeros(n, dtype=np.int32)
+        gen = np.zeros(n, dtype=np.int32)
+        N.check(N.lib().genie_t2s_pool_poll(self._h, _ptr(state), _ptr(gen), n))
+        return state, gen
+
+    def pool_read(self, slot: int) -> Tuple[np.ndarray, int]:
+        y = np.zeros(self._pool[1], dtype=np.int64)
+        y_len, idx = C.c_int(0), C.c_int(0)
+        N.check(N.lib().genie_t2s_pool_read(self._h, int(slot), _ptr(y), len(y), C.byref(y_len), C.byref(idx)))
+        return y[:y_len.value].copy(), idx.value
+
+    def pool_release(self, slot: int) -> None:
+        N.check(N.lib().genie_t2s_release(self._h, int(slot)))
+
     # -- SoVITS -----------------------------------------------------------------
     def vits_decode(self, prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
                     semantic: Sequence[np.ndarray], zp_noise: Optional[Sequence[np.ndarray]] = None,
-                    seed: int = 0, noise_scale: float = -1.0) -> List[np.ndarray]:
+                    seed: Optional[int] = None, noise_scale: float = -1.0) -> List[np.ndarray]:
+        """``seed=None``: fresh z_p noise per call, as the reference's unseeded RandomNormalLike (vits#[6490])."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
         B = len(prompts)
         seqs = [_i64(t) for t in text_seqs]
         sems = [_i64(t) for t in semantic]
@@ -266,17 +362,20 @@ class B200Model:
         return out
 
     # -- device-resident payload variants (bench `value` leg: inputs/outputs stay in HBM) ------
-    def t2s_generate_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sampling: SamplingParams, y_out):
-        """text_seq_cat: int64 CUDA tensor (concat); y_out: int64 CUDA tensor [B, y_ld].  Lengths and the
-        small per-utterance results (y_len, idx) are host metadata."""
+    def t2s_generate_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sampling: SamplingParams, y_out,
+                            text_bert_cat=None):
+        """text_seq_cat: int64 CUDA tensor (concat); text_bert_cat: optional f32 CUDA tensor [sum len, 1024];
+        y_out: int64 CUDA tensor [B, y_ld].  Lengths and the small per-utterance results (y_len, idx) are host
+        metadata."""
         B = len(prompts)
         lens = np.ascontiguousarray(text_lens, dtype=np.int32)
         y_len = np.zeros(B, dtype=np.int32)
         idx = np.zeros(B, dtype=np.int32)
         hs = (C.c_void_p * B)(*[p._h for p in prompts])
         csp = sampling.to_c()
-        N.check(N.lib().genie_t2s_generate(self._h, hs, B, _ptr(text_seq_cat), _ptr(lens), None, C.byref(csp), None,
-                                           1, _ptr(y_out), int(y_out.shape[1]), _ptr(y_len), _ptr(idx)))
+        N.check(N.lib().genie_t2s_generate(self._h, hs, B, _ptr(text_seq_cat), _ptr(lens), _ptr(text_bert_cat),
+                                           C.byref(csp), None, 1, _ptr(y_out), int(y_out.shape[1]), _ptr(y_len),
+                                           _ptr(idx)))
         return y_len, idx
 
     def vits_decode_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sem_cat, sem_lens: np.ndarray,
@@ -303,6 +402,22 @@ class B200Model:
 
     def keep(self, enable: bool) -> None:
         N.check(N.lib().genie_debug_keep(self._h, int(enable)))
+
+    def debug_sample(self, logits: np.ndarray, hist: np.ndarray, hist_len: np.ndarray, sampling: SamplingParams,
+                     noise: Optional[np.ndarray] = None, n_draws: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+        """The sampler kernel on host-supplied logits [rows,1025] and histories [rows,ld]; returns
+        (tokens [rows,n_draws], stop flags [rows,n_draws]).  ``noise`` [n_draws,rows,1025] replaces Philox."""
+        lg = _f32(logits).reshape(-1, 1025)
+        rows = lg.shape[0]
+        h = np.ascontiguousarray(hist, dtype=np.int64).reshape(rows, -1)
+        hl = np.ascontiguousarray(hist_len, dtype=np.int32).reshape(rows)
+        nz = _f32(noise).reshape(n_draws, rows, 1025) if noise is not None else None
+        tok = np.zeros((rows, n_draws), dtype=np.int64)
+        stop = np.zeros((rows, n_draws), dtype=np.int32)
+        csp = sampling.to_c()
+        N.check(N.lib().genie_debug_sample(self._h, _ptr(lg), rows, _ptr(h), h.shape[1], _ptr(hl), C.byref(csp),
+                                           _ptr(nz), n_draws, _ptr(tok), _ptr(stop)))
+        return tok, stop
 
     def read_kept(self, what: str) -> np.ndarray:
         n = C.c_longlong(0)
@@ -344,6 +459,11 @@ class B200Prompt:
         n, gd, lr = C.c_int(0), C.c_int(0), C.c_int(0)
         N.check(L.genie_prompt_info(self._h, C.byref(n), C.byref(gd), C.byref(lr)))
         self.n_prompt_tokens, self.ge_dim, self.ref_len = n.value, gd.value, lr.value
+        model._prompts.add(self)                 # the model closes its prompts before it closes itself
+
+    @property
+    def closed(self) -> bool:
+        return not self._h
 
     def read(self):
         pr = np.zeros(self.n_prompt_tokens, dtype=np.int64)

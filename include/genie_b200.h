@@ -14,8 +14,14 @@
  * pointers unless the `io_on_device` argument of the call is 1, in which case
  * the in/out payload pointers are device pointers on the model's GPU (used by
  * bench.py's HBM-resident `value` leg).  All integer token ids are int64 to
- * match the reference's numpy feeds.  One model handle belongs to one GPU and
- * must be driven by one thread at a time.
+ * match the reference's numpy feeds.  One handle belongs to one GPU; calls on one
+ * handle are serialised by the library (a second thread waits), calls on different
+ * handles — including contexts cloned from one model — run concurrently.
+ *
+ * Streams: every handle issues its work on ONE main CUDA stream (cuBLAS-style
+ * binding rather than a stream argument on every call): the library's own by
+ * default, or a caller-owned cudaStream_t given to genie_context_create /
+ * genie_set_stream.  Calls return after their results are complete on that stream.
  */
 #ifndef GENIE_B200_H
 #define GENIE_B200_H
@@ -61,7 +67,18 @@ int genie_model_set_constants(genie_model* m, const float* pe_div_term_256, int 
  * prompt-encoder tensors (ModelManager.py:287-293). */
 int genie_model_finalize(genie_model* m);
 int genie_model_info(const genie_model* m, int* is_v2pp, long long* weight_bytes, long long* workspace_bytes);
+/* Destroys the handle.  Weights are reference-counted: they are freed when the model AND every context cloned
+ * from it are gone.  Prompts never dereference the model, so they may be destroyed before or after it. */
 void genie_model_destroy(genie_model* m);
+
+/* ---- execution contexts: a second (third, ...) independent handle onto the SAME weights, with its own stream,
+ * workspace, T2S slot pool and captured graphs — ">1 session per model" (one scheduler thread per GPU
+ * plus e.g. a latency-critical batch-1 caller beside it).  cuda_stream: a caller-owned cudaStream_t the context
+ * issues its work on, or NULL for a library-owned stream.  Every entry point taking a genie_model* accepts a
+ * context; prompts built through any handle of a model are valid for all of them.  Free with genie_model_destroy. */
+int genie_context_create(genie_model* model, void* cuda_stream, genie_model** out);
+/* re-bind a handle's main stream (NULL: back to a library-owned stream); drops captured graphs */
+int genie_set_stream(genie_model* m, void* cuda_stream);
 
 /* ---- prompt: replaces the per-reference-audio work the reference redoes in every call:
  * the VQ of ssl_content (t2s_encoder#[2-48]), the V2 ref_enc spectrogram path (vits#[3-271])
@@ -93,7 +110,13 @@ typedef struct genie_sampling {
   unsigned long long seed;
   int max_steps;              /* decode-loop bound, reference 500 (Inference.py:95); <=0: 500 */
   int fixed_steps;            /* >0: ignore stop flags and run exactly this many loop iterations */
+  float top_p;                /* nucleus sampling, an EXTENSION: the reference graphs have no top-p node.
+                                 <=0 or >=1: off (reference behaviour).  Applied to the penalised logits before
+                                 temperature and top-k, upstream GPT-SoVITS order: in descending order drop every
+                                 token whose inclusive cumulative probability exceeds top_p, except the first */
 } genie_sampling;
+/* All sampling parameters live in device memory per decode slot, so the captured decode-step graph is independent
+ * of them: changing seed / temperature / top_k / top_p between calls costs nothing. */
 
 /* text_seq: int64 concat over utterances (sum text_len); text_bert: f32 [sum text_len,1024] or NULL.
  * Outputs (host unless io_on_device): y int64[B, y_ld] = prompt tokens followed by every generated
@@ -119,6 +142,32 @@ int genie_t2s_prefill(genie_model* m, genie_prompt* const* prompts, int B, const
 int genie_t2s_decode_steps(genie_model* m, int n_steps, const volatile int* cancel, int* n_active, int* steps_done);
 int genie_t2s_read(genie_model* m, int io_on_device, int64_t* y, int y_ld, int* y_len, int* idx);
 
+/* ---- continuous batching (BASELINE config 5): the T2S stage as a pool of decode SLOTS.  A slot owns a
+ * KV slab of kv_capacity tokens and a token-history row; requests are admitted into free slots (the call runs their
+ * prefill as one ragged batch, Inference.py:76-93) while other slots are mid-decode, every pool_step advances all
+ * active slots together (Inference.py:95-106 per slot, each with its own sampling parameters, stop flag and step
+ * budget), finished slots are read and released.  Per-slot results are independent of what shares the pool.
+ * The batch calls above are the special case "pool sized for the batch, everything admitted at once"; on one
+ * handle use either the batch calls or a pool (a prefill call replaces the pool).
+ *   kv_capacity        tokens per slot: >= Lr + Lt + prompt tokens + max_steps + 1 of the longest request
+ *   max_prompt_tokens  longest prompt-token sequence (Ts/2) that will be admitted
+ *   max_steps          largest decode-loop bound that will be admitted (reference: 500) */
+int genie_t2s_pool_create(genie_model* m, int n_slots, int kv_capacity, int max_prompt_tokens, int max_steps);
+int genie_t2s_pool_info(genie_model* m, int* n_slots, int* kv_capacity, int* hist_ld);
+/* admit n requests into the free slots slots[0..n); text_seq / text_len / text_bert as in genie_t2s_generate (host
+ * pointers); sampling: array of n genie_sampling (NULL: model constants for all) */
+int genie_t2s_admit(genie_model* m, int n, const int* slots, genie_prompt* const* prompts, const int64_t* text_seq,
+                    const int* text_len, const float* text_bert, const genie_sampling* sampling);
+/* up to n_steps decode steps over every active slot (returns early when none is left); n_active: slots still decoding */
+int genie_t2s_pool_step(genie_model* m, int n_steps, int* n_active);
+/* state[i]: 0 free, 1 decoding, 2 finished (stop flag or step budget); n_generated[i]: tokens generated so far
+ * (the first-stage token included); arrays of n >= n_slots entries, either may be NULL */
+int genie_t2s_pool_poll(genie_model* m, int* state, int* n_generated, int n);
+/* y / y_len / idx of one slot, as documented for genie_t2s_generate (valid at any time while the slot is in use) */
+int genie_t2s_pool_read(genie_model* m, int slot, int64_t* y, int y_capacity, int* y_len, int* idx);
+/* free the slot (a slot released while still decoding — a cancelled request — stops at once) */
+int genie_t2s_release(genie_model* m, int slot);
+
 /* ---- SoVITS: replaces vocoder.run (Inference.py:46-61) for a batch.
  * sem: int64 concat of semantic tokens (sum sem_len, every id < 1024);
  * zp_noise: f32 concat per utterance of [192, 2*sem_len[b]] (the graph's RandomNormalLike
@@ -135,6 +184,13 @@ int genie_debug_read_logits(genie_model* m, float* out, int max_floats, int* n_f
 /* intermediate tensors of the last T2S / VITS call by name ("x", "k0", "m_p", "z", ...) */
 int genie_debug_read(genie_model* m, const char* what, float* out, long long max_floats, long long* n_floats);
 int genie_debug_keep(genie_model* m, int enable);
+/* the sampler kernel in isolation (stage#[1775-1821]): rows of host logits f32[rows,1025] with token histories
+ * int64[rows,hist_ld] / hist_len[rows]; n_draws independent draws per row (Philox key (seed + draw, row, hist_len),
+ * or externally supplied noise f32[n_draws, rows, 1025] replacing RandomNormalLike); tokens int64[rows, n_draws],
+ * stop int[rows, n_draws] (may be NULL).  Histories are not modified. */
+int genie_debug_sample(genie_model* m, const float* logits, int rows, const int64_t* hist, int hist_ld,
+                       const int* hist_len, const genie_sampling* sampling, const float* noise, int n_draws,
+                       int64_t* tokens, int* stop);
 /* unit self-test of the tcgen05 implicit-GEMM conv kernel against the exact SIMT kernel on random data:
  * M rows in two ragged segments, ntaps taps with dilation dil; mode 1 = x_hi.w_hi, 2 = (x_hi+x_lo).w_hi,
  * 3 = 2 + x_hi.w_lo; exact_w = weights rounded to fp16 (the T2S case) */

@@ -25,9 +25,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "genie-tts_b200"))
-from genie_tts.weights import ModelDirTables, read_model_dir  # noqa: E402
+from .onnx_wire import read_tensors   # the oracle's own wire reader (independent of the product loader)
 
 EOS = 1024
 N_LAYER = 24
@@ -44,14 +42,17 @@ class PortModel:
     fp16 blob -> fp32)."""
 
     def __init__(self, model_dir: str):
-        tabs: ModelDirTables = read_model_dir(model_dir)
-        self.is_v2pp = tabs.is_v2pp
-        self.enc = {k: _tt(v) for k, v in tabs.encoder.tensors.items()}
-        self.t2s = {k: _tt(v) for k, v in tabs.t2s.tensors.items()}
+        j = lambda n: os.path.join(model_dir, n)  # noqa: E731
+        # V2 vs V2ProPlus by the presence of the prompt encoder (src/genie_tts/ModelManager.py:287-293)
+        self.is_v2pp = os.path.exists(j("prompt_encoder_fp32.onnx"))
+        self.enc = {k: _tt(v) for k, v in read_tensors(j("t2s_encoder_fp32.onnx")).items()}
+        self.t2s = {k: _tt(v) for k, v in
+                    read_tensors(j("t2s_stage_decoder_fp32.onnx"), j("t2s_shared_fp16.bin")).items()}
         self.vits = {k[len("vq_model."):] if k.startswith("vq_model.") else k: _tt(v)
-                     for k, v in tabs.vits.tensors.items()}
-        self.pe = ({k: _tt(v) for k, v in tabs.prompt_encoder.tensors.items()}
-                   if tabs.prompt_encoder else None)
+                     for k, v in read_tensors(j("vits_fp32.onnx"), j("vits_fp16.bin")).items()}
+        self.pe = ({k: _tt(v) for k, v in
+                    read_tensors(j("prompt_encoder_fp32.onnx"), j("prompt_encoder_fp16.bin")).items()}
+                   if self.is_v2pp else None)
         self._wn_cache: Dict[str, torch.Tensor] = {}
 
     def wn(self, prefix: str) -> torch.Tensor:
@@ -169,7 +170,8 @@ def t2s_decode_step(m: PortModel, token: int, pos: int, k_cache, v_cache, T: int
 
 
 def sample_token(logits: torch.Tensor, history: torch.Tensor, noise: Optional[torch.Tensor] = None,
-                 top_k: int = 15, temperature: float = 1.0, penalty: float = 1.35) -> Tuple[int, bool]:
+                 top_k: int = 15, temperature: float = 1.0, penalty: float = 1.35,
+                 top_p: float = 1.0) -> Tuple[int, bool]:
     """stage#[1775-1821]: repetition penalty over every token in ``history``
     (gather -> where(s<0, s*p, s/p) -> scatter, so each distinct token is
     penalised once from the raw logit), /temperature, top-k keeping ties
@@ -179,6 +181,13 @@ def sample_token(logits: torch.Tensor, history: torch.Tensor, noise: Optional[to
     s = raw[history]
     lg = raw.clone()
     lg[history] = torch.where(s < 0, s * penalty, s / penalty)
+    if 0.0 < top_p < 1.0:
+        # EXTENSION (not in the reference graphs; upstream GPT-SoVITS logits_to_probs order and rule):
+        # descending sort, drop every token whose inclusive cumulative probability exceeds top_p, keep the first
+        srt, order = torch.sort(lg, descending=True, stable=True)
+        remove = torch.cumsum(torch.softmax(srt, dim=-1), dim=-1) > top_p
+        remove[0] = False
+        lg[order[remove]] = float("-inf")
     lg = lg / temperature
     kth = torch.topk(lg, top_k).values[-1]
     lg = torch.where(lg < kth, torch.tensor(float("-inf")), lg)
@@ -197,9 +206,18 @@ class T2SResult:
     logits: List[np.ndarray] = field(default_factory=list)
 
 
+def _round_cache(kc, vc, rows: slice, mode: Optional[str]) -> None:
+    """What-if switch for the KV-precision study: store the cache rows ``rows`` rounded through fp16
+    ("kv"), only V ("v") or only K ("k").  None = the reference's fp32 cache."""
+    if mode in ("kv", "k"):
+        kc[:, rows] = kc[:, rows].half().float()
+    if mode in ("kv", "v"):
+        vc[:, rows] = vc[:, rows].half().float()
+
+
 def t2s_generate(m: PortModel, ref_seq, ref_bert, text_seq, text_bert, ssl_content,
                  max_steps: int = 500, noise_fn=None, keep_logits: bool = False,
-                 force_tokens: Optional[int] = None) -> T2SResult:
+                 force_tokens: Optional[int] = None, kv_fp16: Optional[str] = None) -> T2SResult:
     """src/genie_tts/Core/Inference.py:63-109 over the port's stages, including
     the loop quirks: y[0,-1]=0 (:108) and y[:, -idx:] (:109; idx==0 returns all
     of y).  ``force_tokens``: ignore the stop flag and run exactly that many
@@ -216,6 +234,7 @@ def t2s_generate(m: PortModel, ref_seq, ref_bert, text_seq, text_bert, ssl_conte
     vc = torch.zeros(N_LAYER, cap, D_MODEL)
     kc[:, :S] = k0
     vc[:, :S] = v0
+    _round_cache(kc, vc, slice(0, S), kv_fp16)
     y = prompts.tolist()
     all_logits = [logits.numpy().copy()] if keep_logits else []
     tok, _ = sample_token(logits, torch.tensor(y), None if noise_fn is None else noise_fn(0))
@@ -225,6 +244,7 @@ def t2s_generate(m: PortModel, ref_seq, ref_bert, text_seq, text_bert, ssl_conte
     n_iter = max_steps if force_tokens is None else force_tokens
     for idx in range(0, n_iter):
         logits = t2s_decode_step(m, y[-1], Ly + idx + 1, kc, vc, T)
+        _round_cache(kc, vc, slice(T, T + 1), kv_fp16)   # the step itself saw the new token's k / v in fp32
         T += 1
         if keep_logits:
             all_logits.append(logits.numpy().copy())

@@ -31,9 +31,7 @@ from typing import Callable, Dict, List, Optional
 import numpy as np
 import torch
 
-_HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "genie-tts_b200"))
-from genie_tts.onnx_reader import ONNX_DTYPES, Graph, Model, Node, load_model  # noqa: E402
+from .onnx_wire import ONNX_DTYPES, Graph, Model, Node, load_model   # the oracle's own wire reader
 
 _TORCH_DT = {1: torch.float32, 6: torch.int32, 7: torch.int64, 9: torch.bool,
              10: torch.float16, 11: torch.float64, 2: torch.uint8, 3: torch.int8}

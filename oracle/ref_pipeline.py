@@ -69,14 +69,17 @@ def set_sampler_mode(s: RefSessions, greedy: bool, zp_noise: Optional[np.ndarray
 
 
 def t2s_cpu(s: RefSessions, ref_seq, ref_bert, text_seq, text_bert, ssl_content,
-            max_steps: int = 500, stop_event=None, collect: Optional[Dict] = None):
-    """src/genie_tts/Core/Inference.py:63-109, line for line."""
+            max_steps: int = 500, stop_event=None, collect: Optional[Dict] = None, on_step=None):
+    """src/genie_tts/Core/Inference.py:63-109, line for line.  ``on_step(idx, y)`` (tests only) is called after
+    the first-stage run (idx == -1) and after every stage-decoder run, e.g. to read traced logits."""
     x, prompts = s.encoder.run(None, {                                   # :76-85
         "ref_seq": ref_seq, "text_seq": text_seq, "ref_bert": ref_bert,
         "text_bert": text_bert, "ssl_content": ssl_content})
     y, y_emb, *present_key_values = s.first_stage.run(None, {"x": x, "prompts": prompts})   # :88-90
     if collect is not None:
         collect.update(x=x, prompts=prompts, y0=y.copy(), kv0=[k.copy() for k in present_key_values[:2]])
+    if on_step is not None:
+        on_step(-1, y)
     input_names: List[str] = [inp.name for inp in s.stage.get_inputs()]  # :93
     idx = 0
     for idx in range(0, max_steps):                                      # :95
@@ -85,6 +88,8 @@ def t2s_cpu(s: RefSessions, ref_seq, ref_bert, text_seq, text_bert, ssl_content,
         feed = {name: data for name, data in zip(input_names, [y, y_emb, *present_key_values])}
         outputs = s.stage.run(None, feed)                                # :102
         y, y_emb, stop_condition_tensor, *present_key_values = outputs
+        if on_step is not None:
+            on_step(idx, y)
         if stop_condition_tensor:                                        # :105-106
             break
     if collect is not None:

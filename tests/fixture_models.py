@@ -102,8 +102,25 @@ def _stride_of(name: str) -> int:
     return 1
 
 
+EOS_BOOST = 1.6
+RESIDUAL_BRANCH_GAIN = 0.15
+
+
 def write_fixture(out_dir: str, version: str = "v2", seed: int = 0) -> str:
-    """Write a complete character model directory; returns ``out_dir``."""
+    """Write a complete character model directory; returns ``out_dir``.
+
+    ``version`` "v2sharp" is the V2 fixture with two changes to the T2S weights that make greedy decoding a
+    SENSITIVE parity probe.  (1) ``linear2.weight`` / ``out_proj.weight`` of every layer are scaled by
+    RESIDUAL_BRANCH_GAIN: with plain N(0, 1/fan_in) init 24 post-LN ReLU layers sit deep in the ordered phase —
+    the final hidden state (hence the logits) is the same to 2 decimals for every input token, step and sentence,
+    so token equality says little about attention / KV indexing.  With small residual branches the residual
+    stream keeps the token and position identity, logits change from step to step and a wrong cache row flips
+    tokens.  (2) Row 1024 (EOS) of ``ar_predict_layer.weight`` is scaled by EOS_BOOST so the natural-stop path
+    (stop flag = argmax(raw)==1024 or token==1024, stage#[1807-1821]; host slicing Inference.py:105-109) fires
+    after a few to a few dozen steps, different for every sentence (incl. idx 0 and EOS as the first-stage token)."""
+    sharp = version == "v2sharp"
+    if sharp:
+        version = "v2"
     os.makedirs(out_dir, exist_ok=True)
     schema = _schema()
     graphs = ["t2s_encoder_fp32", "t2s_first_stage_decoder_fp32", "t2s_stage_decoder_fp32", "vits_fp32"]
@@ -134,6 +151,10 @@ def write_fixture(out_dir: str, version: str = "v2", seed: int = 0) -> str:
             assert dt == 1 and off == off_expect, (name, off, off_expect)
             arr = _init_tensor(rng, name, dims)
             assert arr.size * 4 == ln, (name, arr.shape, ln)
+            if sharp and name == "ar_predict_layer.weight":
+                arr[1024] *= EOS_BOOST
+            if sharp and name.startswith("transformer_encoder.") and name.endswith(("linear2.weight", "out_proj.weight")):
+                arr *= RESIDUAL_BRANCH_GAIN
             blob[off // 4: (off + ln) // 4] = arr.reshape(-1)
             off_expect = off + ln
         with open(os.path.join(out_dir, bin_name), "wb") as f:

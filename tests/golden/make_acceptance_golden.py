@@ -1,0 +1,117 @@
+"""Generate the acceptance-test vectors of BASELINE.json's north_star ("under greedy decoding, semantic token
+sequences must match exactly on >= 99 % of sentences, first divergences attributed to logit near-ties within 1e-3")
+by executing the REFERENCE's graph files (oracle/onnx_interp.py over oracle/ref_pipeline.py, i.e.
+src/genie_tts/Core/Inference.py:63-109) on seeded fixtures.  Build container only (needs /root/reference or the
+staged oracle/_ref/graphs); the GPU box compares against the committed .npz files.
+
+  acceptance_ja100.npz   the 100 sentences of bench.py's workload (configs[1], rank-0 seeds), greedy, 90-step loop
+                         bound, natural stop honoured as in the reference
+  acceptance_sharp100.npz  the same 100 sentences on the "v2sharp" fixture (tests/fixture_models.py: input-sensitive
+                         logits + boosted EOS): natural stops at many different loop indices inside one batch
+  acceptance_eos48.npz   48 short ragged sentences on "v2sharp": stops incl. the idx == 0 "whole sequence" quirk
+  acceptance_bert16.npz  16 sentences with non-zero 1024-d BERT rows (config-4 shape), full 90 steps
+  acceptance_v2pp_long.npz  2 V2ProPlus-shaped long utterances (config 3: KV beyond 1500 tokens)
+
+Per sentence: y_full (prompt + every generated token), idx (the reference's loop variable at exit), and per decode
+decision the oracle's margin: top-1 minus top-2 of the penalised logits (what greedy arg-max decides on) and the
+margin of the stop test (raw top-1 vs. EOS), so a first divergence can be attributed to a near-tie.
+
+usage: python tests/golden/make_acceptance_golden.py [ja100|sharp100|eos48|bert16|v2pp_long ...]
+"""
+import os
+import sys
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "genie-tts_b200")]
+
+LOGITS = "/ar_predict_layer/MatMul_output_0"
+
+
+def case_inputs(case: str):
+    """(fixture version, fixture seed, [(prompt inputs, text inputs)], max_steps) — shared with the GPU tests."""
+    from synth import make_prompt_inputs, make_text_inputs
+    if case in ("ja100", "sharp100"):
+        from bench import CONFIGS, make_workload
+        pr, texts, _ = make_workload(CONFIGS[2], 100)
+        return ("v2" if case == "ja100" else "v2sharp"), 0, [(pr, t) for t in texts], 90
+    if case == "eos48":
+        prs = [make_prompt_inputs(seed=3000 + k, Lr=16 + 4 * k, Ts=48 + 8 * k, n_audio=32000) for k in range(3)]
+        return "v2sharp", 0, [(prs[i % 3], make_text_inputs(seed=3100 + i, Lt=8 + (i % 13))) for i in range(48)], 60
+    if case == "bert16":
+        pr = make_prompt_inputs(seed=3200, Lr=60, Ts=264, n_audio=169600, bert=True)
+        return "v2", 0, [(pr, make_text_inputs(seed=3210 + i, Lt=40 + (5 * i) % 21, bert=True)) for i in range(16)], 90
+    if case == "v2pp_long":
+        pr = make_prompt_inputs(seed=3300, Lr=200, Ts=500, n_audio=64000, v2pp=True)
+        return "v2ProPlus", 1, [(pr, make_text_inputs(seed=3310 + i, Lt=560 + 20 * i)) for i in range(2)], 500
+    raise KeyError(case)
+
+
+def _margins(raw: np.ndarray, history: np.ndarray, penalty: float = 1.35):
+    """(top-1 - top-2 of the penalised logits, |raw max over non-EOS - raw EOS|) — stage#[1775-1821]."""
+    lg = raw.astype(np.float64).copy()
+    h = np.unique(history)
+    s = lg[h]
+    lg[h] = np.where(s < 0, s * penalty, s / penalty)
+    top = np.sort(lg)[-2:]
+    stop_margin = abs(float(np.max(raw[:1024])) - float(raw[1024]))
+    return float(top[1] - top[0]), stop_margin
+
+
+def _one(args):
+    case, i = args
+    import torch
+    torch.set_num_threads(1)
+    from conftest import fixture_dir
+    from oracle import ref_pipeline as R
+    ver, fseed, items, steps = case_inputs(case)
+    pr, tx = items[i]
+    s = R.load_sessions(fixture_dir(ver, fseed))
+    R.set_sampler_mode(s, greedy=True)
+    for prog in (s.first_stage, s.stage):
+        prog.trace = {}
+        prog.keep = {LOGITS}
+    gaps, stops = [], []
+
+    def on_step(idx, y):
+        prog = s.first_stage if idx < 0 else s.stage
+        raw = prog.trace[LOGITS].numpy().reshape(-1)
+        g, sm = _margins(raw, y[0, :-1])          # history = everything before the token just appended
+        gaps.append(g)
+        stops.append(sm)
+
+    col = {}
+    toks = R.t2s_cpu(s, pr["ref_seq"], pr["ref_bert"], tx["text_seq"], tx["text_bert"], pr["ssl_content"],
+                     max_steps=steps, collect=col, on_step=on_step)
+    return i, col["y_full"][0], int(col["idx"]), np.asarray(gaps, np.float32), np.asarray(stops, np.float32), \
+        toks.reshape(-1)
+
+
+def main(cases):
+    from conftest import fixture_dir
+    for case in cases:
+        ver, fseed, items, steps = case_inputs(case)
+        fixture_dir(ver, fseed)                        # written once, before the workers start
+        n = len(items)
+        with ProcessPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            res = sorted(ex.map(_one, [(case, i) for i in range(n)]))
+        ld = max(len(r[1]) for r in res)
+        y = np.full((n, ld), -1, np.int16)
+        gap = np.full((n, steps + 1), np.nan, np.float32)
+        stopm = np.full((n, steps + 1), np.nan, np.float32)
+        for i, yf, idx, g, sm, _ in res:
+            y[i, :len(yf)] = yf
+            gap[i, :len(g)] = g
+            stopm[i, :len(sm)] = sm
+        out = dict(y_full=y, y_len=np.asarray([len(r[1]) for r in res], np.int32),
+                   idx=np.asarray([r[2] for r in res], np.int32), gap=gap, stop_margin=stopm,
+                   tokens_len=np.asarray([len(r[5]) for r in res], np.int32), max_steps=np.int32(steps))
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"acceptance_{case}.npz"), **out)
+        print(case, "sentences", n, "idx histogram", np.bincount(out["idx"])[:12], "... max", out["idx"].max(),
+              "min decision margin", float(np.nanmin(gap)), "n(margin<1e-3)", int((gap < 1e-3).sum()))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["ja100", "sharp100", "eos48", "bert16", "v2pp_long"])

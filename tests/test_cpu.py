@@ -203,31 +203,25 @@ def test_cabi_exports_every_declared_symbol():
 
 
 # ---------------------------------------------------------------- multi-process (gloo, world_size 2)
-def test_partition_covers():
-    from genie_tts.dispatch import least_loaded, partition
-    for n in (0, 1, 7, 100):
-        for w in (1, 2, 3, 8):
-            spans = [partition(n, w, r) for r in range(w)]
-            assert spans[0][0] == 0 and spans[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
-            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
-    assert sorted(least_loaded([0, 0], [5, 4, 3, 2])) == [0, 0, 1, 1]
-
-
-def test_gloo_world_size_2_sharding(tmp_path):
+def test_gloo_world_size_2_bench_aggregation(tmp_path):
+    """The N > 1 leg of bench.py on CPU: every rank draws the SAME workload (yield-independent scaling), times its
+    own replica, and rank 0 reports max-over-ranks time and summed units (bench.aggregate_over_ranks)."""
     script = tmp_path / "w.py"
     script.write_text(
         "import os, sys, torch, torch.distributed as dist\n"
-        f"sys.path.insert(0, {PKG!r})\n"
-        "from genie_tts.dispatch import partition\n"
+        f"sys.path[:0] = [{ROOT!r}, {PKG!r}, {os.path.join(ROOT, 'tests')!r}]\n"
+        "import numpy as np\n"
+        "import bench\n"
         "dist.init_process_group('gloo')\n"
         "r, w = dist.get_rank(), dist.get_world_size()\n"
-        "a, b = partition(101, w, r)\n"
-        "mine = torch.zeros(101); mine[a:b] = 1\n"
-        "dist.all_reduce(mine)\n"
-        "t = torch.tensor([float(b - a) * (r + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX)\n"
-        "assert bool((mine == 1).all()), 'shards must tile the request list exactly once'\n"
-        "assert t.item() == 100.0\n"
+        "cfg = bench.CONFIGS[2]\n"
+        "pr, texts, berts = bench.make_workload(cfg, 6, rank=r)\n"
+        "sig = torch.tensor([float(sum(int(t['text_seq'].sum()) for t in texts))])\n"
+        "lo, hi = sig.clone(), sig.clone()\n"
+        "dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)\n"
+        "assert lo.item() == hi.item(), 'every rank must synthesise the same sentences'\n"
+        "dt, units = bench.aggregate_over_ranks([0.5 * (r + 1), 0.25], [10.0, 3.0 + r], w, torch.device('cpu'))\n"
+        "assert dt == [0.5 * w, 0.25] and units == [10.0 * w, sum(3.0 + k for k in range(w))], (dt, units)\n"
         "dist.barrier(); print('ok', r)\n")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
@@ -291,6 +285,104 @@ def test_batch_scheduler_batches_orders_and_survives_errors():
     with pytest.raises(ValueError):
         pool.submit([0], np.arange(3))
     pool.close()
+
+
+# ---------------------------------------------------------------- continuous batching (slot pool) host logic
+class _FakePoolModel:
+    """Host-side stand-in for the C-ABI slot pool (genie_t2s_pool_*): a request decodes for len(text) % 7 + 3 steps;
+    records how many slots were busy at each admission, so the test can see requests JOIN a pool that is decoding."""
+
+    def __init__(self, fail_len=None):
+        self.state, self.left, self.meta = [], [], []
+        self.admit_busy, self.vits_batches, self.fail_len = [], [], fail_len
+        self.lock = None
+
+    def pool_create(self, n_slots, kv_capacity, max_prompt_tokens, max_steps=500):
+        self.state, self.left, self.meta = [0] * n_slots, [0] * n_slots, [None] * n_slots
+
+    def pool_admit(self, slots, prompts, text_seqs, text_berts=None, samplings=None):
+        if self.fail_len is not None and any(len(s) == self.fail_len for s in text_seqs):
+            raise ValueError("bad request in admission")
+        self.admit_busy.append(sum(1 for s in self.state if s == 1))
+        for sl, p, seq in zip(slots, prompts, text_seqs):
+            assert self.state[sl] == 0
+            self.state[sl], self.left[sl], self.meta[sl] = 1, len(seq) % 7 + 3, (p, len(seq))
+
+    def pool_step(self, n):
+        import time
+        time.sleep(0.002)
+        for i, s in enumerate(self.state):
+            if s == 1:
+                self.left[i] -= n
+                if self.left[i] <= 0:
+                    self.state[i] = 2
+        return sum(1 for s in self.state if s == 1)
+
+    def pool_poll(self):
+        return np.asarray(self.state), np.zeros(len(self.state), np.int32)
+
+    def pool_read(self, slot):
+        p, n = self.meta[slot]
+        return np.asarray([7, 8] + [n % 1000] * 6, np.int64), 3       # 2 prompt tokens + 6 generated, idx 3
+
+    def pool_release(self, slot):
+        self.state[slot] = 0
+
+    def vits_decode(self, prompts, text_seqs, sems, *a, **k):
+        self.vits_batches.append(len(prompts))
+        return [np.full(2, float(len(s)) + 1000.0 * p.tag, np.float32) for p, s in zip(prompts, text_seqs)]
+
+
+def test_continuous_batcher_admits_into_running_pool_and_isolates_requests():
+    import time
+    from concurrent.futures import wait
+    from types import SimpleNamespace
+    from genie_tts.Scheduler import ContinuousBatcher, ReplicaPool
+    m = _FakePoolModel()
+    prompts = [SimpleNamespace(tag=t, ref_len=10, n_prompt_tokens=20) for t in range(3)]
+    cb = ContinuousBatcher(m, n_slots=8, kv_capacity=600, max_prompt_tokens=64, max_steps=500, steps_per_tick=1,
+                           max_admit=4, vits_max_batch=4, vits_window_ms=1.0)
+    futs = []
+    for i in range(40):                                         # trickle in: later requests arrive mid-decode
+        futs.append(cb.submit(prompts[i % 3], np.arange(5 + i) % 700))
+        if i % 5 == 4:
+            time.sleep(0.004)
+    wait(futs, timeout=30)
+    for i, f in enumerate(futs):                                # every request gets ITS result, whatever shares the pool
+        assert f.result()[0] == 5 + i + 1000.0 * (i % 3)
+    assert any(b > 0 for b in m.admit_busy), "no admission happened while other slots were decoding"
+    assert max(m.vits_batches) <= 4 and sum(m.vits_batches) == 40
+    assert cb.load == 0 and all(s == 0 for s in m.state)
+    # oversize / invalid requests fail alone
+    with pytest.raises(ValueError):
+        cb.submit(prompts[0], np.arange(700) % 700).result(timeout=10)         # needs more KV rows than a slot holds
+    with pytest.raises(ValueError):
+        cb.submit(prompts[0], np.asarray([3, 900])).result(timeout=10)         # phoneme id out of range
+    # a failing admission fails only its own requests; the pool keeps serving
+    m.fail_len = 9
+    bad = cb.submit(prompts[0], np.arange(9))
+    with pytest.raises(ValueError):
+        bad.result(timeout=10)
+    m.fail_len = None
+    assert cb.submit(prompts[1], np.arange(4)).result(timeout=10)[0] == 1004.0
+    # cancel_all drops what is queued / decoding (reference /stop)
+    slow = [cb.submit(prompts[0], np.arange(6)) for _ in range(6)]
+    cb.cancel_all()
+    for f in slow:
+        with pytest.raises(RuntimeError):
+            f.result(timeout=10)
+    assert cb.submit(prompts[2], np.arange(3)).result(timeout=10)[0] == 2003.0
+    assert cb.load == 0
+    # replica pool over two continuous batchers
+    cb2 = ContinuousBatcher(_FakePoolModel(), n_slots=4, kv_capacity=600, max_prompt_tokens=64, steps_per_tick=1,
+                            vits_window_ms=1.0, name="r1")
+    pool = ReplicaPool([cb, cb2])
+    fs = [pool.submit([prompts[0], prompts[1]], np.arange(10)) for _ in range(24)]
+    wait(fs, timeout=30)
+    assert {int(f.result()[0]) // 1000 for f in fs} == {0, 1}
+    pool.close()
+    with pytest.raises(RuntimeError):
+        cb.submit(prompts[0], np.arange(3))
 
 
 # ---------------------------------------------------------------- bench.py contract (reference arm runs on CPU)
