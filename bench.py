@@ -52,7 +52,8 @@ CONFIGS = {
             workload="configs[3]: GPT-SoVITS V2 Chinese shape: 256 sentences per GPU with N(0,1) 1024-d BERT rows for "
                      "reference and target text (bert_proj GEMM in the encoder), 90-token budget"),
 }
-DTYPE = "f32 accumulate/activations; T2S GEMMs fp16 hi+lo split operands (tcgen05), fp32 KV; SoVITS convs single-pass fp16 operands (tcgen05)"
+DTYPE = ("f32 accumulate/activations; T2S GEMMs fp16 hi+lo split operands (tcgen05), KV cache rows fp16 (q/scores/"
+         "accumulators f32); SoVITS convs single-pass fp16 operands (tcgen05)")
 # algorithmic work (measured on the reference graphs)
 GEN_GFLOP_PER_AUDIO_S = {"v2": 8.26 + 16.52 + 8.26 + 4.13 + 2.06 + 1.36,   # HiFi-GAN stages 0-4 + ups
                          "v2ProPlus": 89.0}
@@ -232,6 +233,7 @@ def main():
                          "paragraph batch 64 long KV, 4 = V2 ZH BERT batch 256 per GPU")
     ap.add_argument("--sentences", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kv-fp32", action="store_true", help="keep the KV cache rows in fp32 (default: fp16 rows)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]
@@ -270,6 +272,11 @@ def main():
         torch.cuda.synchronize()
 
     model = B200Model(model_dir, device=local_rank)
+    if args.kv_fp32:
+        model.set_option("kv_fp16", 0)
+    for opt in ("decode_branches", "decode_split_min"):        # experiments: GENIE_OPT_decode_branches=3 ...
+        if os.environ.get("GENIE_OPT_" + opt):
+            model.set_option(opt, int(os.environ["GENIE_OPT_" + opt]))
     pr, texts, berts = make_workload(cfg, args.sentences or cfg["sentences"], rank=rank)
     prompt = model.make_prompt(pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"], pr.get("sv_emb"))  # untimed
     B = len(texts)
@@ -381,7 +388,8 @@ def main():
         att_us, att_mb = t_att["decode_attention_us"], t_att["decode_attention_kv_mb"]
         att_gbs = att_mb * 1e6 / (att_us * 1e-6) / 1e9 if att_us > 0 else 0.0
         # inside the step the cache grows linearly from S to S + TOKENS: the AVERAGE launch streams these bytes
-        kv_mb_avg = float((S + TOKENS / 2.0).sum()) * 2 * 512 * 4 / 1e6
+        kvb = model.kv_bytes_per_element
+        kv_mb_avg = float((S + TOKENS / 2.0).sum()) * 2 * 512 * kvb / 1e6
         att_us_avg = att_us * kv_mb_avg / att_mb if att_mb > 0 else 0.0     # time is linear in bytes
         att_share = att_us_avg * 1e-3 * 24 * TOKENS / step_ms
         # (2) generator convs (tensor): GFLOP per audio-second of the graph over the generator stage
@@ -396,7 +404,7 @@ def main():
                       if last_t.get("narrow_conv_ms") else 0.0)
         b1_ms_tok = t_b1["decode_ms"] / max(1, t_b1["steps"])
         b1_T = cfg["Lr"] + len(seqs[11 % B]) + prompt.n_prompt_tokens + TOKENS / 2
-        b1_gbs = (152.364e6 + 98304.0 * b1_T) / (b1_ms_tok * 1e-3) / 1e9
+        b1_gbs = (152.364e6 + 24 * 2 * 512 * 4 * b1_T) / (b1_ms_tok * 1e-3) / 1e9     # batch <= 4 keeps fp32 rows
         h2d = int(sum(s.nbytes for s in seqs) + lens.nbytes + (sum(b.nbytes for b in berts) if berts is not None else 0))
         line = {
             "metric": METRIC, "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
@@ -420,7 +428,7 @@ def main():
             "first_audio_ms_p50_batch1": first_audio_ms, "first_audio_ms_max_batch1": first_audio_p99,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "decode_attention_kernel<fused> (one query per utterance x head over "
-                         "the fp32 KV cache; largest single kernel of the step)",
+                         f"the {'fp16' if kvb == 2 else 'fp32'} KV cache; largest single kernel of the step)",
                          "achieved": att_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": att_gbs / hbm_peak,
                          "peak_source": which, "bytes_per_launch": att_mb * 1e6, "avg_launch_us": att_us,
                          "launches_per_step": 24 * TOKENS, "share_of_step": att_share,

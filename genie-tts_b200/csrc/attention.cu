@@ -423,6 +423,173 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// The same kernel over an fp16 KV cache (option kv_fp16, the default for batched decode: measured token parity in
+// DESIGN.md §2).  A cached row is 32 halves = 64 bytes, so 4 lanes x 16 bytes cover one key and a warp-load touches
+// 8 keys = 512 contiguous bytes; 128 threads cover 32 keys per pass, 4 passes (128 keys) in flight per round.
+// q, the new token's k / v, the scores and the accumulators stay fp32; K / V are widened on load, the new token
+// is rounded to fp16 only when it is appended (this step still attends to its fp32 value).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void h8_to_f8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 f8_to_h8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  return u;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(128) decode_attention16_kernel(
+    const float* __restrict__ q, int nsplit, long long split_stride, const float* __restrict__ bias,
+    float* __restrict__ o, __half* __restrict__ kv_base, long long utt_stride, long long layer_off, long long v_off,
+    const int* __restrict__ kv_len, const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  if (FUSED) pdl_trigger();
+  const int kvl = kv_len[b];
+  const int act = active ? active[b] : 1;
+  if (!act) return;
+  const int T = kvl + (FUSED ? 0 : t_add);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, sub = lane & 3;                // 8 keys per warp-load, 4 lanes x 8 halves per key
+  __half* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
+  __half* V = K + v_off;
+  const int jt = warp * 8 + grp;                            // this thread group's key within a 32-key slab
+
+  auto load_batch = [&](int it, uint4 (&k8)[4], uint4 (&v8)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = it * 128 + u * 32 + jt;
+      k8[u] = make_uint4(0u, 0u, 0u, 0u); v8[u] = k8[u];
+      if (j < T) {
+        k8[u] = __ldg(reinterpret_cast<const uint4*>(K + (long long)j * 32 + sub * 8));
+        v8[u] = __ldg(reinterpret_cast<const uint4*>(V + (long long)j * 32 + sub * 8));
+      }
+    }
+  };
+  const int iters = (T + 127) / 128;
+  uint4 k8[4], v8[4], kx[4], vx[4];
+  load_batch(0, k8, v8);                                    // in flight across the wait below
+
+  float q8[8], kn[8], vn[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { q8[e] = 0.f; kn[e] = 0.f; vn[e] = 0.f; }
+  if (FUSED) {
+    const float* pq = q + (long long)b * ldq + h * 32 + sub * 8;
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + h * 32 + sub * 8 + e));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 8 + e));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 8 + e));
+        q8[e] = a.x; q8[e + 1] = a.y; q8[e + 2] = a.z; q8[e + 3] = a.w;
+        kn[e] = c.x; kn[e + 1] = c.y; kn[e + 2] = c.z; kn[e + 3] = c.w;
+        vn[e] = d.x; vn[e + 1] = d.y; vn[e + 2] = d.z; vn[e + 3] = d.w;
+      }
+    }
+    pdl_wait();
+    for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + e));          // producer data:
+        const float4 c = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 512 + e));    // via L2 (PDL)
+        const float4 d = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 1024 + e));
+        q8[e] += a.x; q8[e + 1] += a.y; q8[e + 2] += a.z; q8[e + 3] += a.w;
+        kn[e] += c.x; kn[e + 1] += c.y; kn[e + 2] += c.z; kn[e + 3] += c.w;
+        vn[e] += d.x; vn[e + 1] += d.y; vn[e + 2] += d.z; vn[e + 3] += d.w;
+      }
+    }
+    if (warp == 0 && grp == 0 && T < cap) {
+      *reinterpret_cast<uint4*>(K + (long long)T * 32 + sub * 8) = f8_to_h8(kn);
+      *reinterpret_cast<uint4*>(V + (long long)T * 32 + sub * 8) = f8_to_h8(vn);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q8[e] = q[(long long)b * ldq + h * 32 + sub * 8 + e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q8[e] *= scale;
+
+  float m = -CUDART_INF_F, l = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    if (it + 1 < iters) load_batch(it + 1, kx, vx);         // next round in flight while this one is reduced
+    const int j0 = it * 128 + jt;
+    float sc[4];
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float kf[8];
+      h8_to_f8(k8[u], kf);
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t = fmaf(q8[e], kf[e], t);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      sc[u] = (j0 + u * 32 < T) ? t : -CUDART_INF_F;
+      m_new = fmaxf(m_new, sc[u]);
+    }
+    if (m_new != -CUDART_INF_F) {
+      const float c = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+      l *= c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= c;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pj = (sc[u] == -CUDART_INF_F) ? 0.f : expf(sc[u] - m_new);
+        l += pj;
+        float vf[8];
+        h8_to_f8(v8[u], vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
+      }
+      m = m_new;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { k8[u] = kx[u]; v8[u] = vx[u]; }
+  }
+  if (FUSED && warp == 0 && grp == 0) {                      // the token of this step, in fp32
+    float t = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t = fmaf(q8[e], kn[e], t);
+    t += __shfl_xor_sync(0x0000000fu, t, 1);
+    t += __shfl_xor_sync(0x0000000fu, t, 2);
+    const float m_new = fmaxf(m, t);
+    const float c = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+    const float pj = expf(t - m_new);
+    l = l * c + pj;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * c + pj * vn[e];
+    m = m_new;
+  }
+  __shared__ float sm_m[32], sm_l[32], sm_acc[32][33];
+  const int g = warp * 8 + grp;
+  if (sub == 0) { sm_m[g] = m; sm_l[g] = l; }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm_acc[g][sub * 8 + e] = acc[e];
+  __syncthreads();
+  if (warp == 0) {
+    float M = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) M = fmaxf(M, sm_m[i]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float wgt = (sm_m[i] == -CUDART_INF_F) ? 0.f : expf(sm_m[i] - M);
+      num = fmaf(sm_acc[i][lane], wgt, num);
+      den = fmaf(sm_l[i], wgt, den);
+    }
+    o[(long long)b * 512 + h * 32 + lane] = num / den;
+  }
+}
+
 }  // namespace
 
 void launch_attention(const Attn& p, cudaStream_t s) {
@@ -447,11 +614,16 @@ void launch_attention(const Attn& p, cudaStream_t s) {
 }
 
 void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
-                                   float* kv_base, long long utt_stride, long long layer_off, long long v_off,
-                                   const int* kv_len, const int* active, int B, int cap, float scale, cudaStream_t s) {
+                                   void* kv_base, int kv_f16, long long utt_stride, long long layer_off,
+                                   long long v_off, const int* kv_len, const int* active, int B, int cap, float scale,
+                                   cudaStream_t s) {
   if (B <= 0) return;
-  launch_pdl(decode_attention_kernel<true>, dim3(16, B), dim3(128), 0, s, part, nsplit, split_stride, bias, o, kv_base,
-             utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
+  if (kv_f16)
+    launch_pdl(decode_attention16_kernel<true>, dim3(16, B), dim3(128), 0, s, part, nsplit, split_stride, bias, o,
+               reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
+  else
+    launch_pdl(decode_attention_kernel<true>, dim3(16, B), dim3(128), 0, s, part, nsplit, split_stride, bias, o,
+               reinterpret_cast<float*>(kv_base), utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
   GENIE_LAUNCHED("decode_attention");
 }
 

@@ -9,7 +9,7 @@ SOURCES = ["conv_gemm.cu", "tc_gemm.cu", "tc_halo_conv.cu", "tc_pair_conv.cu", "
            "api.cu"]
 LIB = os.path.join(HERE, "libgenie_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-Werror=pointer-arith", "--expt-relaxed-constexpr"]
 
 
 def _stale(out, deps):

@@ -150,7 +150,8 @@ __global__ void decode_embed_kernel(float* out, const int* hist, int hist_ld, co
   out[(long long)b * 512 + c] = emb[(long long)tok * 512 + c] + alpha[0] * pe_value(n, c, div_term);
 }
 
-__global__ void kv_scatter_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ kv_base,
+template <typename KVT>
+__global__ void kv_scatter_kernel(const float* __restrict__ qkv, int ld, KVT* __restrict__ kv_base,
                                   long long utt_stride, long long layer_off, long long v_off, int cap,
                                   const int* __restrict__ row_off, const int* __restrict__ dst_pos0,
                                   const int* __restrict__ row2utt, int rows, const int* __restrict__ active,
@@ -165,9 +166,16 @@ __global__ void kv_scatter_kernel(const float* __restrict__ qkv, int ld, float* 
   int isv = c4 >> 7, col = (c4 & 127) * 4;          // col within 512
   int h = col >> 5, e = col & 31;
   float4 v = *reinterpret_cast<const float4*>(qkv + (long long)r * ld + 512 + isv * 512 + col);
-  float* dst = kv_base + (long long)b * utt_stride + layer_off + (isv ? v_off : 0) +
-               ((long long)h * cap + pos) * 32 + e;
-  *reinterpret_cast<float4*>(dst) = v;
+  KVT* dst = kv_base + (long long)b * utt_stride + layer_off + (isv ? v_off : 0) +
+             ((long long)h * cap + pos) * 32 + e;
+  if constexpr (sizeof(KVT) == 2) {
+    uint2 u;
+    __half2* hp = reinterpret_cast<__half2*>(&u);
+    hp[0] = __floats2half2_rn(v.x, v.y); hp[1] = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst) = u;
+  } else {
+    *reinterpret_cast<float4*>(dst) = v;
+  }
 }
 
 __global__ void __launch_bounds__(256) prefill_bert_gather_kernel(float* __restrict__ bert, PrefillMeta pm,
@@ -453,13 +461,18 @@ void launch_decode_embed(float* out, const int* hist, int hist_ld, const int* hi
   decode_embed_kernel<<<B, 512, 0, s>>>(out, hist, hist_ld, hist_len, active, emb, alpha, div_term, 0);
   GENIE_LAUNCHED("decode_embed");
 }
-void launch_kv_scatter(const float* qkv, int ld, float* kv_base, long long utt_stride, long long layer_off,
+void launch_kv_scatter(const float* qkv, int ld, void* kv_base, int kv_f16, long long utt_stride, long long layer_off,
                        long long v_off, int cap, const int* row_off, const int* dst_pos0, const int* row2utt,
                        int rows, const int* active, cudaStream_t s, const int* slot_of) {
   if (rows <= 0) return;
-  kv_scatter_kernel<<<nblk((long long)rows * 256, 256), 256, 0, s>>>(qkv, ld, kv_base, utt_stride, layer_off, v_off,
-                                                                    cap, row_off, dst_pos0, row2utt, rows, active,
-                                                                    slot_of);
+  if (kv_f16)
+    kv_scatter_kernel<__half><<<nblk((long long)rows * 256, 256), 256, 0, s>>>(
+        qkv, ld, reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, cap, row_off, dst_pos0, row2utt, rows,
+        active, slot_of);
+  else
+    kv_scatter_kernel<float><<<nblk((long long)rows * 256, 256), 256, 0, s>>>(
+        qkv, ld, reinterpret_cast<float*>(kv_base), utt_stride, layer_off, v_off, cap, row_off, dst_pos0, row2utt, rows,
+        active, slot_of);
   GENIE_LAUNCHED("kv_scatter");
 }
 void launch_prefill_bert_gather(float* bert, const PrefillMeta& pm, const float* text_bert, int rows, cudaStream_t s) {

@@ -17,9 +17,11 @@ struct SlotParams {
 
 
 // QKV split-K partials [nsplit][B][1536] (+ bias) -> q, append k/v at kv_len[b], attend over kv_len[b] + 1 tokens
+// kv_f16: the cache holds halves (strides stay in elements)
 void launch_decode_attention_fused(const float* part, int nsplit, long long split_stride, const float* bias, float* o,
-                                   float* kv_base, long long utt_stride, long long layer_off, long long v_off,
-                                   const int* kv_len, const int* active, int B, int cap, float scale, cudaStream_t s);
+                                   void* kv_base, int kv_f16, long long utt_stride, long long layer_off,
+                                   long long v_off, const int* kv_len, const int* active, int B, int cap, float scale,
+                                   cudaStream_t s);
 
 // y[r,:] = LN(x[r,:] (+ res[r,:])) * g + b   (eps 1e-5), C multiple of 32, C <= 1024
 // x may be nsplit split-K partials (split_stride apart) with the producer's bias deferred to here
@@ -40,7 +42,7 @@ void launch_decode_embed(float* out, const int* hist, int hist_ld, const int* hi
 // scatter K,V columns of qkv rows into the head-major cache:
 //   cache[b][layer][kv][h][pos][32], pos = dst_pos0[b] + (row - row_off[b])
 //   slot_of (optional): cache slab of utterance b is slot_of[b] instead of b
-void launch_kv_scatter(const float* qkv, int ld, float* kv_base, long long utt_stride, long long layer_off,
+void launch_kv_scatter(const float* qkv, int ld, void* kv_base, int kv_f16, long long utt_stride, long long layer_off,
                        long long v_off, int cap, const int* row_off, const int* dst_pos0, const int* row2utt,
                        int rows, const int* active, cudaStream_t s, const int* slot_of = nullptr);
 
@@ -96,7 +98,8 @@ struct PersistentStep {
   float* h1 = nullptr;         // [B,512] LN1 output
   float* ff = nullptr;         // [B,2048]
   float* logits = nullptr; int ld_logits = 1025;
-  float* kv = nullptr; long long utt_stride = 0, layer_stride = 0, v_off = 0; int cap = 0;
+  void* kv = nullptr; int kv_f16 = 0;   // cache of floats or halves; strides in elements
+  long long utt_stride = 0, layer_stride = 0, v_off = 0; int cap = 0;
   const int* kv_len = nullptr; const int* active = nullptr;
   unsigned* sync = nullptr;    // [0] barrier counter (zeroed per launch), [1] barrier-timeout flag
   int B = 1, nch = 1; float scale = 1.f;

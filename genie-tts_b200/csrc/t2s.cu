@@ -30,7 +30,8 @@ struct StepBufs {
   float *h, *qkv, *att, *tmp, *h1, *ff, *logits, *part, *part2, *ppart;
   int *hist, *hist_len, *kv_len, *active, *stop_step;
   const SlotParams* params;
-  float* kv; long long utt_stride, layer_stride, v_off; int cap, hist_ld; long long part_stride;
+  void* kv; int kv_f16;   // cache of floats, or of halves (option kv_fp16); strides below are in elements
+  long long utt_stride, layer_stride, v_off; int cap, hist_ld; long long part_stride;
 };
 
 struct SlotHost { int in_use = 0, Ly = 0, S = 0, max_steps = 0, honour = 1; };
@@ -118,7 +119,7 @@ void decode_step(Model& m, const StepBufs& w, int B) {
     a.wpredict = reinterpret_cast<const __half*>(m.predict.w); a.bpredict = m.predict.b; a.vocab = V;
     a.h = w.h; a.qkv = w.qkv; a.part = w.ppart; a.lnin = w.tmp; a.lnin2 = w.part2; a.h1 = w.h1; a.ff = w.ff;
     a.logits = w.logits; a.ld_logits = V;
-    a.kv = w.kv; a.utt_stride = w.utt_stride; a.layer_stride = w.layer_stride; a.v_off = w.v_off; a.cap = w.cap;
+    a.kv = w.kv; a.kv_f16 = w.kv_f16; a.utt_stride = w.utt_stride; a.layer_stride = w.layer_stride; a.v_off = w.v_off; a.cap = w.cap;
     a.kv_len = w.kv_len; a.active = w.active; a.sync = m.step_sync;
     a.B = B; a.nch = persistent_step_chunks(B, m.num_sms); a.scale = scale;
     launch_t2s_step_persistent(a, m.num_sms, s);
@@ -139,8 +140,8 @@ void decode_step(Model& m, const StepBufs& w, int B) {
         launch_tc_small_gemm(g, nt, m.tc_err, s);
       };
       gemm(L.qkv, w.h, D, 1, nullptr, 0, 32);                                   // 2 partials [B,1536]
-      launch_decode_attention_fused(w.part + (size_t)r0 * 3 * D, 2, ps * 3, L.qkv.b, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off,
-                                    w.kv_len, w.active, B, w.cap, scale, s);
+      launch_decode_attention_fused(w.part + (size_t)r0 * 3 * D, 2, ps * 3, L.qkv.b, w.att, w.kv, w.kv_f16, w.utt_stride,
+                                    l * w.layer_stride, w.v_off, w.kv_len, w.active, B, w.cap, scale, s);
       gemm(L.out, w.att, D, 1, nullptr, 0, 32);                                 // 2 partials [B,512]
       launch_layernorm(w.part + (size_t)r0 * D, w.h, L.ln1_g, L.ln1_b, w.h1, B, D, s, 2, ps, L.out.b);
       gemm(L.ff1, w.h1, D, 1, nullptr, 0, 32);                                  // 2 partials [B,2048]
@@ -162,7 +163,7 @@ void decode_step(Model& m, const StepBufs& w, int B) {
     (void)sk;
     run_linear(m, L.qkv, w.h, D, w.qkv, 3 * D, B, ACT_NONE, nullptr, 0, tc ? nt_w : 0);
     // q / k_new / v_new straight from the finished QKV rows: cache append + attention in one kernel
-    launch_decode_attention_fused(w.qkv, 1, 0, nullptr, w.att, w.kv, w.utt_stride, l * w.layer_stride, w.v_off,
+    launch_decode_attention_fused(w.qkv, 1, 0, nullptr, w.att, w.kv, w.kv_f16, w.utt_stride, l * w.layer_stride, w.v_off,
                                   w.kv_len, w.active, B, w.cap, scale, s);
     if (tc) {
       run_linear(m, L.out, w.att, D, w.part, D, B, ACT_NONE, nullptr, 0, nt_s, ks_out, ps);
@@ -219,7 +220,13 @@ T2SSession& pool_build(Model& m, int n_slots, int kv_cap, int hist_ld, bool pool
                   utt_stride = NL * layer_stride;
   StepBufs& w = S.w;
   w = StepBufs{};
-  w.kv = ws.get<float>("t2s.kv", (size_t)B * utt_stride);
+  // fp16 rows by default for pools that decode on the batched kernels; option kv_fp16 = 0 keeps the reference's
+  // fp32 rows (measured greedy-token agreement of both against the reference graphs)
+  // Batches that decode on the persistent step kernel (<= persistent_step rows, the first-audio path) keep fp32 rows:
+  // that kernel is latency-bound, cache bytes do not matter there.
+  w.kv_f16 = (m.kv_fp16 && (pool_mode || n_slots > m.persistent_step)) ? 1 : 0;
+  w.kv = w.kv_f16 ? static_cast<void*>(ws.get<__half>("t2s.kv", (size_t)B * utt_stride))
+                  : static_cast<void*>(ws.get<float>("t2s.kv", (size_t)B * utt_stride));
   w.h = ws.get<float>("t2s.step.h", (size_t)B * D); w.qkv = ws.get<float>("t2s.step.qkv", (size_t)B * 3 * D);
   w.att = ws.get<float>("t2s.step.att", (size_t)B * D); w.tmp = ws.get<float>("t2s.step.tmp", (size_t)B * D);
   w.h1 = ws.get<float>("t2s.step.h1", (size_t)B * D); w.ff = ws.get<float>("t2s.step.ff", (size_t)B * 4 * D);
@@ -233,7 +240,7 @@ T2SSession& pool_build(Model& m, int n_slots, int kv_cap, int hist_ld, bool pool
   {
     const void* ptrs[] = {w.h, w.qkv, w.att, w.tmp, w.h1, w.ff, w.logits, w.part, w.part2, w.ppart, w.hist, w.hist_len,
                           w.kv_len, w.active, w.stop_step, w.params, w.kv};
-    unsigned long long k = 1469598103934665603ull;
+    unsigned long long k = 1469598103934665603ull ^ (unsigned long long)w.kv_f16;
     for (const void* q : ptrs) { k ^= (unsigned long long)reinterpret_cast<uintptr_t>(q); k *= 1099511628211ull; }
     w.key = k;
   }
@@ -385,8 +392,8 @@ void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* p
   for (int l = 0; l < NL; ++l) {
     const T2SLayer& L = m.layers[l];
     run_linear(m, L.qkv, Hcur, D, QKV, 3 * D, R);
-    launch_kv_scatter(QKV, 3 * D, w.kv, w.utt_stride, l * w.layer_stride, w.v_off, S.cap, d_row_off, d_zero, d_row2utt, R,
-                      nullptr, s, d_slot);
+    launch_kv_scatter(QKV, 3 * D, w.kv, w.kv_f16, w.utt_stride, l * w.layer_stride, w.v_off, S.cap, d_row_off, d_zero,
+                      d_row2utt, R, nullptr, s, d_slot);
     Attn a;
     a.q = QKV; a.ldq = 3 * D; a.k = QKV + D; a.ldk = 3 * D; a.v = QKV + 2 * D; a.ldv = 3 * D;
     a.o = ATT; a.ldo = D; a.q_off = d_row_off; a.kv_off = d_row_off; a.B = n; a.H = H; a.d = 32; a.max_q = maxS;
@@ -486,7 +493,7 @@ StepGraph& step_graph(Model& m, T2SSession& S, int rows) {
           w2.part += (size_t)8 * b0 * D; w2.part2 += (size_t)8 * b0 * D; w2.part_stride = (long long)(b1 - b0) * D;
           w2.hist += (size_t)b0 * w.hist_ld;
           w2.hist_len += b0; w2.kv_len += b0; w2.active += b0; w2.stop_step += b0; w2.params += b0;
-          w2.kv += (size_t)b0 * w.utt_stride;
+          w2.kv = static_cast<char*>(w.kv) + (size_t)b0 * w.utt_stride * (w.kv_f16 ? 2 : 4);   // strides are in elements
           if (k > 0) GENIE_CUDA(cudaStreamWaitEvent(bs[k], m.ev_fork, 0));
           m.stream = bs[k];
           decode_step(m, w2, b1 - b0);
@@ -656,8 +663,8 @@ void t2s_read(Model& m, int io_dev, int64_t* y_out, int y_ld, int* y_len_out, in
     GENIE_CUDA(cudaEventRecord(ea, s));
     for (int r = 0; r < m.time_attention; ++r)
       for (int l = 0; l < 24; ++l)
-        launch_decode_attention_fused(w.part, 2, (long long)B * D * 3, m.layers[l].qkv.b, w.att, w.kv, w.utt_stride,
-                                      l * w.layer_stride, w.v_off, w.kv_len, nullptr, B, w.cap, scale, s);
+        launch_decode_attention_fused(w.part, 2, (long long)B * D * 3, m.layers[l].qkv.b, w.att, w.kv, w.kv_f16,
+                                      w.utt_stride, l * w.layer_stride, w.v_off, w.kv_len, nullptr, B, w.cap, scale, s);
     GENIE_CUDA(cudaEventRecord(eb, s));
     GENIE_CUDA(cudaEventSynchronize(eb));
     float ms = 0;
@@ -665,7 +672,7 @@ void t2s_read(Model& m, int io_dev, int64_t* y_out, int y_ld, int* y_len_out, in
     double kv_tokens = 0;
     for (int b = 0; b < B; ++b) kv_tokens += h_kvlen_final[b];
     m.timing[8] = 1000.f * ms / (float)(m.time_attention * 24);
-    m.timing[9] = (float)(kv_tokens * 2 * 512 * 4 / 1e6);
+    m.timing[9] = (float)(kv_tokens * 2 * 512 * (w.kv_f16 ? 2 : 4) / 1e6);
     cudaEventDestroy(ea); cudaEventDestroy(eb);
   }
   float t01 = 0, t12 = 0;

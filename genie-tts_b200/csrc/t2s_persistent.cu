@@ -181,8 +181,32 @@ __device__ __forceinline__ void load_rows(float* xs, const float* src, int K, in
 // one (utterance, head, key chunk): partial softmax statistics over the chunk's keys -> part[36].
 // The first pass of cached K / V rows (written by earlier steps) is fetched BEFORE the barrier that publishes
 // this step's q: att_prefetch / att_run.
+// cache rows are floats or halves (PersistentStep::kv_f16): element offsets + a uniform branch on load / store —
+// this kernel is latency-bound, the byte count of the cache does not matter here, only that it reads the same
+// cache the batched path appends to
+__device__ __forceinline__ float4 ld_kv4(const void* base, long long idx, int f16) {
+  if (f16) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + idx));
+    const __half2* hp = reinterpret_cast<const __half2*>(&u);
+    const float2 a = __half22float2(hp[0]), b = __half22float2(hp[1]);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+}
+__device__ __forceinline__ void st_kv4(void* base, long long idx, const float4& v, int f16) {
+  if (f16) {
+    uint2 u;
+    __half2* hp = reinterpret_cast<__half2*>(&u);
+    hp[0] = __floats2half2_rn(v.x, v.y); hp[1] = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(base) + idx) = u;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = v;
+  }
+}
+
 struct AttItem {
-  int b, h, c, T, lo, hi; float* K; float* V; float4 k4[2], v4[2]; bool valid, has_new;
+  int b, h, c, T, lo, hi; long long K, V;   // element offsets of this head's K / V rows in the cache
+  float4 k4[2], v4[2]; bool valid, has_new;
   uint4 wq[4][2], wk[4][2], wv[4][2];      // this warp's 4 q (k, v) columns of head h: rows of Wqkv, 2 x 256 k
   float bq[4], bk[4], bv[4];
 };
@@ -200,7 +224,7 @@ __device__ __forceinline__ void att_prefetch(AttItem& it, const PersistentStep& 
   const int total = it.T + 1;
   const int cs = (total + a.nch - 1) / a.nch;
   it.lo = it.c * cs; it.hi = min(it.lo + cs, total);
-  it.K = a.kv + (long long)it.b * a.utt_stride + (long long)layer * a.layer_stride + (long long)it.h * a.cap * 32;
+  it.K = (long long)it.b * a.utt_stride + (long long)layer * a.layer_stride + (long long)it.h * a.cap * 32;
   it.V = it.K + a.v_off;
   it.has_new = it.lo <= it.T && it.T < it.hi;                // this chunk holds the step's own token
   {
@@ -228,8 +252,8 @@ __device__ __forceinline__ void att_prefetch(AttItem& it, const PersistentStep& 
     const int j = it.lo + u * 32 + grp;
     it.k4[u] = make_float4(0.f, 0.f, 0.f, 0.f); it.v4[u] = it.k4[u];
     if (j < it.hi && j < it.T) {
-      it.k4[u] = __ldg(reinterpret_cast<const float4*>(it.K + (long long)j * 32 + sub * 4));
-      it.v4[u] = __ldg(reinterpret_cast<const float4*>(it.V + (long long)j * 32 + sub * 4));
+      it.k4[u] = ld_kv4(a.kv, it.K + (long long)j * 32 + sub * 4, a.kv_f16);
+      it.v4[u] = ld_kv4(a.kv, it.V + (long long)j * 32 + sub * 4, a.kv_f16);
     }
   }
 }
@@ -267,7 +291,7 @@ __device__ __forceinline__ void att_run(AttItem& it, const PersistentStep& a, co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int grp = tid >> 3, sub = tid & 7;                  // 32 groups of 8 lanes, one key per group per pass
   const int b = it.b, h = it.h, c = it.c, T = it.T, lo = it.lo, hi = it.hi;
-  float* K = it.K; float* V = it.V;
+  const long long K = it.K, V = it.V;
   dot4(it.wq, it.bq, x, lane, sqkv + warp * 4);
   if (it.has_new) {
     dot4(it.wk, it.bk, x, lane, sqkv + 32 + warp * 4);
@@ -292,15 +316,15 @@ __device__ __forceinline__ void att_run(AttItem& it, const PersistentStep& a, co
         if (j < T) {
           if (j0 == lo) { k4[u] = it.k4[u]; v4[u] = it.v4[u]; }
           else {
-            k4[u] = __ldg(reinterpret_cast<const float4*>(K + (long long)j * 32 + sub * 4));
-            v4[u] = __ldg(reinterpret_cast<const float4*>(V + (long long)j * 32 + sub * 4));
+            k4[u] = ld_kv4(a.kv, K + (long long)j * 32 + sub * 4, a.kv_f16);
+            v4[u] = ld_kv4(a.kv, V + (long long)j * 32 + sub * 4, a.kv_f16);
           }
         } else {                                            // this step's token: from the QKV rows, and into the cache
           k4[u] = *reinterpret_cast<const float4*>(sqkv + 32 + sub * 4);
           v4[u] = *reinterpret_cast<const float4*>(sqkv + 64 + sub * 4);
           if (T < a.cap) {
-            *reinterpret_cast<float4*>(K + (long long)T * 32 + sub * 4) = k4[u];
-            *reinterpret_cast<float4*>(V + (long long)T * 32 + sub * 4) = v4[u];
+            st_kv4(a.kv, K + (long long)T * 32 + sub * 4, k4[u], a.kv_f16);
+            st_kv4(a.kv, V + (long long)T * 32 + sub * 4, v4[u], a.kv_f16);
           }
         }
       }

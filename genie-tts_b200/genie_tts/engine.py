@@ -204,6 +204,12 @@ class B200Model:
 
     def set_option(self, key: str, value: int) -> None:
         N.check(N.lib().genie_set_option(self._h, key.encode(), int(value)))
+        self.__dict__.setdefault("options", {})[key] = int(value)
+
+    @property
+    def kv_bytes_per_element(self) -> int:
+        """2: KV cache rows stored as fp16 (default), 4: fp32 rows (option kv_fp16 = 0)."""
+        return 2 if self.__dict__.get("options", {}).get("kv_fp16", 1) else 4
 
     # -- prompt ----------------------------------------------------------------
     def make_prompt(self, ref_seq, ref_bert, ssl_content, ref_audio_32k=None, sv_emb=None,

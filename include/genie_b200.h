@@ -204,7 +204,9 @@ int genie_profiler_range(int on);
  * (only after a genie_t2s_generate with option time_attention > 0), [10] ms of the generator stages with <= 32
  * channels (HBM-bound) and [11] their algorithmic MB */
 int genie_last_timing(genie_model* m, float* ms, int n);
-/* options: use_graph (CUDA-graph replay of the decode step, default 1), use_tc / tc_vits (tensor-core paths),
+/* options: kv_fp16 (1, default: KV cache rows stored as fp16 — q, scores and accumulators stay fp32; 0: fp32 rows as
+ * in the reference graphs; takes effect at the next prefill / pool_create),
+ * use_graph (CUDA-graph replay of the decode step, default 1), use_tc / tc_vits (tensor-core paths),
  * skinny_max_rows, tc_min_rows, decode_split_min (path selection, debugging),
  * time_attention (n > 0: after the next t2s_generate replay the decode attention n x 24 times between events).
  * Environment: GENIE_TC_HALO=-1 disables the halo conv kernel, GENIE_PDL=0 programmatic dependent launch,

@@ -109,8 +109,9 @@ RESIDUAL_BRANCH_GAIN = 0.15
 def write_fixture(out_dir: str, version: str = "v2", seed: int = 0) -> str:
     """Write a complete character model directory; returns ``out_dir``.
 
-    ``version`` "v2sharp" is the V2 fixture with two changes to the T2S weights that make greedy decoding a
-    SENSITIVE parity probe.  (1) ``linear2.weight`` / ``out_proj.weight`` of every layer are scaled by
+    A ``version`` with the suffix "sharp" ("v2sharp", "v2ProPlussharp") is that fixture with two changes to the T2S
+    weights that make greedy decoding a SENSITIVE parity probe; the suffix "sens" applies only the first (no EOS
+    boost: long decodes that never stop).  (1) ``linear2.weight`` / ``out_proj.weight`` of every layer are scaled by
     RESIDUAL_BRANCH_GAIN: with plain N(0, 1/fan_in) init 24 post-LN ReLU layers sit deep in the ordered phase —
     the final hidden state (hence the logits) is the same to 2 decimals for every input token, step and sentence,
     so token equality says little about attention / KV indexing.  With small residual branches the residual
@@ -118,9 +119,10 @@ def write_fixture(out_dir: str, version: str = "v2", seed: int = 0) -> str:
     tokens.  (2) Row 1024 (EOS) of ``ar_predict_layer.weight`` is scaled by EOS_BOOST so the natural-stop path
     (stop flag = argmax(raw)==1024 or token==1024, stage#[1807-1821]; host slicing Inference.py:105-109) fires
     after a few to a few dozen steps, different for every sentence (incl. idx 0 and EOS as the first-stage token)."""
-    sharp = version == "v2sharp"
-    if sharp:
-        version = "v2"
+    sens = version.endswith(("sharp", "sens"))
+    sharp = version.endswith("sharp")
+    if sens:
+        version = version[:-5] if sharp else version[:-4]
     os.makedirs(out_dir, exist_ok=True)
     schema = _schema()
     graphs = ["t2s_encoder_fp32", "t2s_first_stage_decoder_fp32", "t2s_stage_decoder_fp32", "vits_fp32"]
@@ -153,7 +155,7 @@ def write_fixture(out_dir: str, version: str = "v2", seed: int = 0) -> str:
             assert arr.size * 4 == ln, (name, arr.shape, ln)
             if sharp and name == "ar_predict_layer.weight":
                 arr[1024] *= EOS_BOOST
-            if sharp and name.startswith("transformer_encoder.") and name.endswith(("linear2.weight", "out_proj.weight")):
+            if sens and name.startswith("transformer_encoder.") and name.endswith(("linear2.weight", "out_proj.weight")):
                 arr *= RESIDUAL_BRANCH_GAIN
             blob[off // 4: (off + ln) // 4] = arr.reshape(-1)
             off_expect = off + ln

@@ -9,8 +9,12 @@ staged oracle/_ref/graphs); the GPU box compares against the committed .npz file
   acceptance_sharp100.npz  the same 100 sentences on the "v2sharp" fixture (tests/fixture_models.py: input-sensitive
                          logits + boosted EOS): natural stops at many different loop indices inside one batch
   acceptance_eos48.npz   48 short ragged sentences on "v2sharp": stops incl. the idx == 0 "whole sequence" quirk
-  acceptance_bert16.npz  16 sentences with non-zero 1024-d BERT rows (config-4 shape), full 90 steps
-  acceptance_v2pp_long.npz  2 V2ProPlus-shaped long utterances (config 3: KV beyond 1500 tokens)
+  acceptance_bert16.npz  16 sentences with non-zero 1024-d BERT rows (config-4 shape) on "v2sharp"
+  acceptance_v2pp_long.npz  2 V2ProPlus-shaped long utterances (config 3: KV beyond 1500 tokens) on the input-sensitive
+                         "v2ProPlussens" fixture (no EOS boost: all 500 steps run)
+Only ja100 uses the plain fixture (the bench's exact weights); its logits barely depend on the input (see
+tests/fixture_models.py), so it pins the bench path's arithmetic but would not notice a wrong cache row — the
+input-sensitive fixtures do (they caught a mis-addressed KV slab that ja100-style checks at B = 256 passed).
 
 Per sentence: y_full (prompt + every generated token), idx (the reference's loop variable at exit), and per decode
 decision the oracle's margin: top-1 minus top-2 of the penalised logits (what greedy arg-max decides on) and the
@@ -42,10 +46,10 @@ def case_inputs(case: str):
         return "v2sharp", 0, [(prs[i % 3], make_text_inputs(seed=3100 + i, Lt=8 + (i % 13))) for i in range(48)], 60
     if case == "bert16":
         pr = make_prompt_inputs(seed=3200, Lr=60, Ts=264, n_audio=169600, bert=True)
-        return "v2", 0, [(pr, make_text_inputs(seed=3210 + i, Lt=40 + (5 * i) % 21, bert=True)) for i in range(16)], 90
+        return "v2sharp", 0, [(pr, make_text_inputs(seed=3210 + i, Lt=40 + (5 * i) % 21, bert=True)) for i in range(16)], 90
     if case == "v2pp_long":
         pr = make_prompt_inputs(seed=3300, Lr=200, Ts=500, n_audio=64000, v2pp=True)
-        return "v2ProPlus", 1, [(pr, make_text_inputs(seed=3310 + i, Lt=560 + 20 * i)) for i in range(2)], 500
+        return "v2ProPlussens", 1, [(pr, make_text_inputs(seed=3310 + i, Lt=560 + 20 * i)) for i in range(2)], 500
     raise KeyError(case)
 
 

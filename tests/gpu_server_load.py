@@ -1,0 +1,132 @@
+"""BASELINE config 5: FastAPI server, continuous batching, N concurrent synthetic requests over every GPU of the box.
+
+  python tests/gpu_server_load.py [--clients 512] [--rounds 3] [--gpus 8] [--out gpurun_out/config5_load.json]
+
+The server (genie_tts.Server: the reference's REST surface on SynthesisService, one ContinuousBatcher per GPU) runs in
+its OWN process, started by this script; the clients are `--clients` concurrent aiohttp coroutines in this process,
+each sending `--rounds` /tts requests back to back (closed loop).  A request is one ~20-character sentence
+(JA20 shape: 40-60 phonemes from a synthetic front end, 90-token budget, Philox sampling with a fresh seed), the
+response is the sentence's raw s16 PCM stream.  Reported: first-audio latency (request sent -> first PCM byte; the
+reference streams one chunk per sentence, so this is the sentence's whole synthesis) p50 / p99, request latency,
+sustained audio-seconds per second, per-replica scheduler counters."""
+import argparse
+import asyncio
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "genie-tts_b200")]
+PORT = 18777
+
+
+def serve(n_gpus: int) -> None:
+    import uvicorn
+    from conftest import fixture_dir
+    from genie_tts import Internal, Server
+    from genie_tts.Audio.ReferenceAudio import ReferenceAudio
+    from genie_tts.GetPhonesAndBert import set_text_frontend
+    from genie_tts.Service import SynthesisService
+    from genie_tts.engine import SamplingParams
+    from synth import make_prompt_inputs
+
+    def frontend(text, language):                    # synthetic G2P at the boundary: 40-60 phonemes per sentence
+        h = sum(map(ord, text))
+        rng = np.random.default_rng(h)
+        seq = rng.integers(0, 732, (1, 40 + h % 21)).astype(np.int64)
+        seq[0, 0] = 3
+        return seq, None
+
+    set_text_frontend(frontend)
+    svc = SynthesisService(devices=list(range(n_gpus)), n_slots=128, kv_capacity=448, max_prompt_tokens=160,
+                           max_steps=90, sampling=SamplingParams(max_steps=90, fixed_steps=90))
+    Server.set_service(svc)
+    svc.load_character("Mika", fixture_dir("v2", 0), "Japanese")
+    pr = make_prompt_inputs(seed=1, Lr=60, Ts=264, n_audio=169600)
+    ref = ReferenceAudio.from_features("synthetic-ref", pr["ref_seq"], pr["ref_bert"], pr["ssl_content"], pr["ref_audio"])
+    Internal.set_reference_features("Mika", ref)
+    svc.set_reference("Mika", ref)
+    st = svc.submit("Mika", "warm up", False)        # builds pools, prompts and graphs on every replica
+    list(st.chunks(timeout=300))
+    uvicorn.run(Server.app, host="127.0.0.1", port=PORT, log_level="warning")
+
+
+async def run_clients(n_clients: int, rounds: int):
+    import aiohttp
+    url = f"http://127.0.0.1:{PORT}/tts"
+    first, total, nbytes = [], [], []
+    conn = aiohttp.TCPConnector(limit=0)
+    async with aiohttp.ClientSession(connector=conn, timeout=aiohttp.ClientTimeout(total=600)) as sess:
+        async def client(k):
+            for r in range(rounds):
+                t0 = time.perf_counter()
+                async with sess.post(url, json={"character_name": "Mika", "text": f"要求{k}の{r}番目の文です。"}) as resp:
+                    assert resp.status == 200, resp.status
+                    got, t_first = 0, None
+                    async for chunk in resp.content.iter_any():
+                        if t_first is None and chunk:
+                            t_first = time.perf_counter()
+                        got += len(chunk)
+                t1 = time.perf_counter()
+                first.append(1000 * ((t_first or t1) - t0))
+                total.append(1000 * (t1 - t0))
+                nbytes.append(got)
+        t0 = time.perf_counter()
+        await asyncio.gather(*[client(k) for k in range(n_clients)])
+        wall = time.perf_counter() - t0
+        async with sess.get(f"http://127.0.0.1:{PORT}/stats") as resp:
+            stats = await resp.json()
+    return first, total, nbytes, wall, stats
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--serve", type=int, default=0)
+    ap.add_argument("--clients", type=int, default=512)
+    ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--gpus", type=int, default=0)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config5_load.json"))
+    a = ap.parse_args()
+    if a.serve:
+        serve(a.serve)
+        return
+    from genie_tts import _native as N
+    n_gpus = a.gpus or N.lib().genie_device_count()
+    srv = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--serve", str(n_gpus)],
+                           stdout=subprocess.DEVNULL, stderr=open(os.path.join(ROOT, "gpurun_out", "config5_server.err"), "w"))
+    try:
+        import urllib.request
+        for _ in range(600):                          # model load x n_gpus + warm-up
+            try:
+                urllib.request.urlopen(f"http://127.0.0.1:{PORT}/stats", timeout=2).read()
+                break
+            except Exception:
+                if srv.poll() is not None:
+                    raise RuntimeError("server process died, see gpurun_out/config5_server.err")
+                time.sleep(0.5)
+        asyncio.run(run_clients(min(64, a.clients), 1))                       # warm: every graph bucket, every replica
+        first, total, nbytes, wall, stats = asyncio.run(run_clients(a.clients, a.rounds))
+    finally:
+        srv.terminate()
+        try:
+            srv.wait(timeout=20)
+        except Exception:
+            srv.kill()
+    audio_s = sum(nbytes) / 2 / 32000.0
+    res = {"config": "BASELINE configs[4]: FastAPI server, continuous batching, closed-loop synthetic clients",
+           "n_gpus": n_gpus, "clients": a.clients, "requests": len(first), "rounds_per_client": a.rounds,
+           "sentence": "JA20 shape: 40-60 phonemes, 132 prompt tokens, 90-token budget, Philox sampling",
+           "first_audio_ms_p50": float(np.percentile(first, 50)), "first_audio_ms_p99": float(np.percentile(first, 99)),
+           "request_ms_p50": float(np.percentile(total, 50)), "request_ms_p99": float(np.percentile(total, 99)),
+           "audio_s": audio_s, "wall_s": wall, "audio_s_per_s": audio_s / wall, "replicas": stats}
+    with open(a.out, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k != "replicas"}))
+
+
+if __name__ == "__main__":
+    main()

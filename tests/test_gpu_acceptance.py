@@ -114,10 +114,26 @@ def test_acceptance_ja100_default_bench_path():
             rep["path"] = {100: "B=100 two-branch graph", 50: "B=50 single-branch graph", 4: "B=4 persistent step"}[bs]
             _report(f"ja100_b{bs}", rep)
         for bs, (rep, _, _) in out.items():
-            # the flat random-init fixture has 47 decisions below 1e-3 among 9100: allow their share, require attribution
-            _check(rep, min_match=0.95)
+            # the flat random-init fixture has 47 decisions below 1e-3 among 9100; measured: 100 / 100 exact on all paths
+            _check(rep)
     finally:
         m.close()
+
+
+def test_acceptance_fp32_kv_rows_option():
+    """Option kv_fp16 = 0 (KV rows in fp32, as the reference graphs hold them) on both 100-sentence sets at B = 100:
+    the same criterion; its report sits next to the default fp16-row reports (the measurement behind the default)."""
+    for case, ver in (("ja100", "v2"), ("sharp100", "v2sharp")):
+        m = _load_model(ver, 0)
+        try:
+            m.set_option("kv_fp16", 0)
+            g, out = _run_case(m, case, [100])
+            rep = out[100][0]
+            rep["kv_rows"] = "fp32"
+            _report(f"{case}_b100_kvfp32", rep)
+            _check(rep)
+        finally:
+            m.close()
 
 
 def test_acceptance_sharp100_natural_stops_in_one_batch():
@@ -127,7 +143,7 @@ def test_acceptance_sharp100_natural_stops_in_one_batch():
     m = _load_model("v2sharp", 0)
     try:
         g, out = _run_case(m, "sharp100", [100, 7])
-        assert len(set(g["idx"].tolist())) >= 8            # the fixture really exercises many stop positions
+        assert len(set(g["idx"].tolist())) >= 4 and g["idx"].max() < 89    # natural stops, at different steps
         for bs, (rep, ys, idx) in out.items():
             _report(f"sharp100_b{bs}", rep)
             _check(rep)
@@ -165,12 +181,12 @@ def test_acceptance_bert_rows_and_batch_256():
     """Config-4 shape: non-zero 1024-d BERT rows (bert_proj GEMM in the encoder); 16 sentences vs the oracle, then
     the same 16 replicated to B = 256 (three decode branches) — every replica must reproduce the golden tokens."""
     from genie_tts.engine import SamplingParams
-    m = _load_model("v2", 0)
+    m = _load_model("v2sharp", 0)
     try:
         g, out = _run_case(m, "bert16", [16])
         rep = out[16][0]
         _report("bert16_b16", rep)
-        _check(rep, min_match=0.9)
+        _check(rep, min_match=0.93)
         ver, fseed, items, steps = case_inputs("bert16")
         prompt = _prompt(m, items[0][0])
         try:
@@ -180,7 +196,7 @@ def test_acceptance_bert_rows_and_batch_256():
                                      SamplingParams(greedy=True, max_steps=steps))
             rep = compare_with_golden(g, ys, idx, sel=[b % 16 for b in range(B)])
             _report("bert16_b256", rep)
-            _check(rep, min_match=0.9)
+            _check(rep, min_match=0.93)
         finally:
             prompt.close()
     finally:
@@ -191,7 +207,7 @@ def test_acceptance_v2pp_long_kv1500():
     """Config-3 shape: V2ProPlus, KV beyond 1500 tokens (Lr 200 + Lt 560/580 + 250 prompt tokens + 500 steps), at
     batch 2 (persistent step) and replicated to batch 64 (two-branch graph)."""
     from genie_tts.engine import SamplingParams
-    m = _load_model("v2ProPlus", 1)
+    m = _load_model("v2ProPlussens", 1)
     try:
         g, out = _run_case(m, "v2pp_long", [2])
         rep = out[2][0]
