@@ -188,6 +188,19 @@ def load_cpu_reference(cfg, model_dir):
     return P.PortModel(model_dir), "port"
 
 
+def line_config(cfg, args, world):
+    """The `config` object of the JSON line — identical for both arms (the driver compares them)."""
+    depth = max(1, args.pipeline)
+    return {"workload": cfg["workload"], "bench_config": args.config,
+            "sentences_per_gpu": args.sentences or cfg["sentences"], "tokens_per_sentence": cfg["tokens"],
+            "sampling": "top_k=15 T=1.0 rep=1.35 Philox",
+            "l2": "working set (KV cache, vocoder activations) >> 126 MB L2, no explicit flush",
+            "parallelism": f"dp{world} by utterance, replicas only; every rank synthesises the same sentences "
+                           "(yield-independent scaling)",
+            "pipeline": f"{depth} steps in flight per GPU on {depth} execution contexts (T2S of one step overlaps "
+                        "SoVITS of another); stage_ms / rooflines / share_of_step are measured on isolated steps"}
+
+
 def cpu_sample_tokens(cfg):
     """Bounded CPU sample: the config's own token budget, capped so one sentence stays within ~20 s of CPU work."""
     return min(cfg["tokens"], 90)
@@ -216,7 +229,7 @@ def run_reference_arm(args, cfg, model_dir, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "sample": sample},
+        "config": line_config(cfg, args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -234,6 +247,9 @@ def main():
     ap.add_argument("--sentences", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kv-fp32", action="store_true", help="keep the KV cache rows in fp32 (default: fp16 rows)")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="batches in flight per GPU (execution contexts on the same weights): 1 = one step after "
+                         "the other; 2 (default) overlaps the T2S stage of one step with the SoVITS stage of another")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]
@@ -286,22 +302,26 @@ def main():
     sp = SamplingParams(greedy=False, seed=2026, max_steps=TOKENS, fixed_steps=TOKENS)
     genie = GENIE()
 
-    # ---- device-resident leg
+    # ---- device-resident leg: `pipeline` execution contexts on the same weights, one set of I/O buffers each
     dev = torch.device("cuda", local_rank)
+    depth = max(1, args.pipeline)
+    ctxs = model.pipeline_contexts(depth)
     seq_dev = torch.from_numpy(np.concatenate(seqs)).to(dev)
     bert_dev = torch.from_numpy(np.concatenate(berts, axis=0)).to(dev) if berts is not None else None
     y_ld = prompt.n_prompt_tokens + TOKENS + 2
-    y_dev = torch.zeros((B, y_ld), dtype=torch.int64, device=dev)
-    audio_dev = torch.zeros(B * TOKENS * 1280, dtype=torch.float32, device=dev)
+    io = [(torch.zeros((B, y_ld), dtype=torch.int64, device=dev),
+           torch.zeros(B * TOKENS * 1280, dtype=torch.float32, device=dev)) for _ in ctxs]
     stage_ms = {"prefill": [], "decode": [], "vits": [], "generator": []}
 
     dbg = os.environ.get("BENCH_DEBUG") == "1"
 
-    def step_device():
+    def step_device(k=0, record=True):
+        ctx = ctxs[k]
+        y_dev, audio_dev = io[k]
         w0 = time.perf_counter()
-        y_len, idx = model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev, text_bert_cat=bert_dev)
+        y_len, idx = ctx.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev, text_bert_cat=bert_dev)
         w1 = time.perf_counter()
-        t = model.last_timing()
+        t = ctx.last_timing()
         # host glue of the reference (Inference.py:41-44,108-109) on the small token matrix
         y = y_dev.cpu().numpy()
         sems = [strip_eos(finish_t2s(y[b, :y_len[b]], int(idx[b]))).reshape(-1) for b in range(B)]
@@ -309,50 +329,74 @@ def main():
         sl = np.asarray([len(s) for s in sems], dtype=np.int32)
         sem_dev = torch.from_numpy(np.concatenate(sems)).to(dev)
         w2 = time.perf_counter()
-        alen = model.vits_decode_device(prompts, seq_dev, lens, sem_dev, sl, audio_dev, seed=sp.seed)
+        alen = ctx.vits_decode_device(prompts, seq_dev, lens, sem_dev, sl, audio_dev, seed=sp.seed)
         w3 = time.perf_counter()
-        t2 = model.last_timing()
+        t2 = ctx.last_timing()
         if dbg and rank == 0:
-            print(f"[dbg] t2s call {1e3 * (w1 - w0):.2f} ms (stages {t['t2s_ms']:.2f}), glue {1e3 * (w2 - w1):.2f} ms, "
+            print(f"[dbg] ctx{k} t2s call {1e3 * (w1 - w0):.2f} ms (stages {t['t2s_ms']:.2f}), glue {1e3 * (w2 - w1):.2f} ms, "
                   f"vits call {1e3 * (w3 - w2):.2f} ms (stage {t2['vits_ms']:.2f})", file=sys.stderr)
-        stage_ms["prefill"].append(t["prefill_ms"]); stage_ms["decode"].append(t["decode_ms"])
-        stage_ms["vits"].append(t2["vits_ms"]); stage_ms["generator"].append(t2["generator_ms"])
+        if record:
+            stage_ms["prefill"].append(t["prefill_ms"]); stage_ms["decode"].append(t["decode_ms"])
+            stage_ms["vits"].append(t2["vits_ms"]); stage_ms["generator"].append(t2["generator_ms"])
         return float(alen.sum()) / 32000.0, t2
 
-    def step_host():
-        auds = genie.tts_batch(model, prompts, seqs, berts, sampling=sp)
+    def run_steps(n, fn):
+        """n steps on `depth` worker threads, each bound to its own context; returns the summed first results."""
+        if depth == 1:
+            return [fn(0) for _ in range(n)]
+        from concurrent.futures import ThreadPoolExecutor
+        import queue as _q
+        free = _q.Queue()
+        for k in range(depth):
+            free.put(k)
+
+        def work(_):
+            k = free.get()
+            try:
+                return fn(k)
+            finally:
+                free.put(k)
+        with ThreadPoolExecutor(max_workers=depth) as ex:
+            return list(ex.map(work, range(n)))
+
+    def step_host(k=0):
+        auds = genie.tts_batch(ctxs[k], prompts, seqs, berts, sampling=sp)
         return sum(len(a) for a in auds) / 32000.0, sum(a.nbytes for a in auds)
 
+    # warm-up: every context once (graphs, workspaces), then W isolated steps on context 0 — their stage events are
+    # the per-stage figures of the line (under overlap a stage's event span also contains the other batch's kernels)
+    for k in range(depth):
+        step_device(k, record=False)
     for _ in range(args.warmup):
-        step_device()
-    for k in stage_ms:
-        stage_ms[k].clear()
+        step_device(0)
+    last_t = None
+    t_iso0 = time.perf_counter()
+    _, last_t = step_device(0)
+    iso_step_ms = 1000 * (time.perf_counter() - t_iso0)
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = N.lib().genie_launch_count()
     N.lib().genie_profiler_range(1)     # no-op unless run under `ncu --profile-from-start off`; outside the timed
     barrier()                           # region: the first cudaProfilerStart of a process costs tens of ms
     t0 = time.perf_counter()
-    audio_s = 0.0
-    last_t = None
-    for _ in range(args.steps):
-        a, last_t = step_device()
-        audio_s += a
+    res = run_steps(args.steps, lambda k: step_device(k, record=False))
+    audio_s = sum(r[0] for r in res)
     barrier()
     dt = time.perf_counter() - t0
     N.lib().genie_profiler_range(0)
     launches = N.lib().genie_launch_count() - launches0
     clk = clocks.stop()
 
-    # ---- e2e leg (host buffers through the reference-facing call)
-    step_host()
+    # ---- e2e leg (host buffers through the reference-facing call, same pipelining)
+    for k in range(depth):
+        step_host(k)
     barrier()
     t1 = time.perf_counter()
     e_audio, d2h = 0.0, 0
-    for _ in range(args.steps):
-        a, nb = step_host()
-        e_audio += a
-        d2h = nb + B * y_ld * 8
+    # the public throughput call: a stream of batches, `depth` in flight (GENIE.tts_batch_stream)
+    for auds in genie.tts_batch_stream(model, ((prompts, seqs, berts) for _ in range(args.steps)), sampling=sp, depth=depth):
+        e_audio += sum(len(a) for a in auds) / 32000.0
+        d2h = sum(a.nbytes for a in auds) + B * y_ld * 8
     barrier()
     dt_e = time.perf_counter() - t1
 
@@ -373,7 +417,7 @@ def main():
     # ---- dominant kernel, timed live: decode_attention sits inside the step's CUDA graph, so the library
     # replays it on the final KV cache (24 layers back to back, GBs >> L2) between CUDA events on its stream
     model.set_option("time_attention", 20)
-    model.t2s_generate_device(prompts, seq_dev, lens, sp, y_dev, text_bert_cat=bert_dev)
+    model.t2s_generate_device(prompts, seq_dev, lens, sp, io[0][0], text_bert_cat=bert_dev)
     t_att = model.last_timing()
     model.set_option("time_attention", 0)
 
@@ -382,6 +426,7 @@ def main():
         sm = {k: float(np.mean(v)) for k, v in stage_ms.items()}
         audio_per_step = audio_s / args.steps / world
         step_ms = 1000 * dt / args.steps
+        solo_ms = sm["prefill"] + sm["decode"] + sm["vits"]     # one step alone: what the shares below refer to
         S = np.asarray([cfg["Lr"] + len(q) + prompt.n_prompt_tokens for q in seqs], dtype=np.float64)   # prefill rows
         # (1) decode attention (HBM): algorithmic bytes = K and V rows of every cached token of one layer, fp32.
         # The replay runs on the FINAL cache (S + TOKENS rows per utterance): its bytes and its time belong together.
@@ -391,7 +436,7 @@ def main():
         kvb = model.kv_bytes_per_element
         kv_mb_avg = float((S + TOKENS / 2.0).sum()) * 2 * 512 * kvb / 1e6
         att_us_avg = att_us * kv_mb_avg / att_mb if att_mb > 0 else 0.0     # time is linear in bytes
-        att_share = att_us_avg * 1e-3 * 24 * TOKENS / step_ms
+        att_share = att_us_avg * 1e-3 * 24 * TOKENS / solo_ms
         # (2) generator convs (tensor): GFLOP per audio-second of the graph over the generator stage
         n_gen = max(1, last_t["generator_launches"])
         gen_tf = GEN_GFLOP_PER_AUDIO_S[cfg["version"]] * 1e9 * audio_per_step / (sm["generator"] * 1e-3) / 1e12
@@ -410,20 +455,15 @@ def main():
             "metric": METRIC, "value": audio_s / dt, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-            "config": {"workload": cfg["workload"], "bench_config": args.config, "sentences_per_gpu": B,
-                       "tokens_per_sentence": TOKENS,
-                       "sampling": "top_k=15 T=1.0 rep=1.35 Philox", "l2": "working set (KV cache, vocoder "
-                       "activations) >> 126 MB L2, no explicit flush",
-                       "parallelism": f"dp{world} by utterance, replicas only; every rank synthesises the same "
-                                      "sentences (yield-independent scaling)"},
+            "config": line_config(cfg, args, world),
+            "isolated_step_ms": iso_step_ms,
             # yield-independent companion of `value`: decode tokens x 40 ms (value counts the audio actually
             # produced, i.e. after the reference's slicing quirks and EOS strip)
             "token_audio_s_per_s": world * B * TOKENS * 0.04 * args.steps / dt,
             "e2e": {"value": e_audio / dt_e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
-            "t2s_tokens_per_s": world * B * TOKENS * args.steps / (np.sum(stage_ms["decode"]) * 1e-3) / 1.0
-            if stage_ms["decode"] else None,
+            "t2s_tokens_per_s": world * B * TOKENS / (sm["decode"] * 1e-3),        # decode stage of an isolated step
             "stage_ms": sm,
             "first_audio_ms_p50_batch1": first_audio_ms, "first_audio_ms_max_batch1": first_audio_p99,
             "clocks": clk,
@@ -443,17 +483,17 @@ def main():
                 {"stage": "sovits generator convs (tc_conv_gemm / tc_halo_conv, tcgen05)", "bound": "tensor",
                  "achieved": gen_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gen_tf / tf_peak,
                  "launches_per_step": n_gen, "avg_launch_ms": sm["generator"] / n_gen,
-                 "share_of_step": sm["generator"] / step_ms},
+                 "share_of_step": sm["generator"] / solo_ms},
                 # narrow generator stages (<= 32 channels: tc_halo_conv, fused transposed convs, conv_post): every
                 # tensor of every conv counted once per read / write, over the stage events of the last timed step
                 {"stage": "sovits generator narrow stages (C <= 32)", "bound": "hbm", "achieved": narrow_gbs,
                  "peak": hbm_peak, "unit": "GB/s", "frac": narrow_gbs / hbm_peak,
-                 "ms": last_t.get("narrow_conv_ms"), "share_of_step": (last_t.get("narrow_conv_ms") or 0.0) / step_ms},
+                 "ms": last_t.get("narrow_conv_ms"), "share_of_step": (last_t.get("narrow_conv_ms") or 0.0) / solo_ms},
                 {"stage": "t2s decode step (all kernels, CUDA graph), bytes of the step-average KV length",
                  "bound": "hbm", "achieved": dec_gbs,
-                 "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "share_of_step": sm["decode"] / step_ms},
+                 "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "share_of_step": sm["decode"] / solo_ms},
                 {"stage": "t2s prefill (tc_conv_gemm split-fp16 + attention)", "bound": "tensor", "achieved": pre_tf,
-                 "peak": tf_peak, "unit": "TFLOP/s", "frac": pre_tf / tf_peak, "share_of_step": sm["prefill"] / step_ms},
+                 "peak": tf_peak, "unit": "TFLOP/s", "frac": pre_tf / tf_peak, "share_of_step": sm["prefill"] / solo_ms},
                 # batch 1 (first-audio path): one persistent kernel per token; bytes = fp16 weights + fp32 KV read
                 {"stage": "t2s decode batch 1 (t2s_step_persistent_kernel)", "bound": "hbm",
                  "achieved": b1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": b1_gbs / hbm_peak,

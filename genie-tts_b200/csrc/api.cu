@@ -3,6 +3,7 @@
 #include "../../include/genie_b200.h"
 #include "model.h"
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -39,11 +40,21 @@ void genie::set_error(const std::string& msg) { g_err = msg; }
 namespace {
 // streams / events of one handle; `user_stream` non-null binds the handle to a caller-owned stream
 void init_exec_state(Model& m, void* user_stream) {
+  int least = 0, greatest = 0;
+  GENIE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  static const bool prio = [] { const char* e = getenv("GENIE_STREAM_PRIO"); return !(e && e[0] == '0'); }();
+  const int hi = prio ? greatest : least;
   if (user_stream) { m.stream = reinterpret_cast<cudaStream_t>(user_stream); m.stream_owned = false; }
-  else GENIE_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
-  GENIE_CUDA(cudaStreamCreateWithFlags(&m.stream2, cudaStreamNonBlocking));
-  GENIE_CUDA(cudaStreamCreateWithFlags(&m.stream3, cudaStreamNonBlocking));
-  GENIE_CUDA(cudaStreamCreateWithFlags(&m.stream4, cudaStreamNonBlocking));
+  else {
+    GENIE_CUDA(cudaStreamCreateWithPriority(&m.stream, cudaStreamNonBlocking, hi));
+    if (prio) {
+      GENIE_CUDA(cudaStreamCreateWithPriority(&m.stream_bulk, cudaStreamNonBlocking, least));
+      GENIE_CUDA(cudaEventCreateWithFlags(&m.ev_bulk, cudaEventDisableTiming));
+    }
+  }
+  GENIE_CUDA(cudaStreamCreateWithPriority(&m.stream2, cudaStreamNonBlocking, hi));
+  GENIE_CUDA(cudaStreamCreateWithPriority(&m.stream3, cudaStreamNonBlocking, hi));
+  GENIE_CUDA(cudaStreamCreateWithPriority(&m.stream4, cudaStreamNonBlocking, hi));
   GENIE_CUDA(cudaEventCreateWithFlags(&m.ev_join3, cudaEventDisableTiming));
   GENIE_CUDA(cudaEventCreateWithFlags(&m.ev_join4, cudaEventDisableTiming));
   GENIE_CUDA(cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
@@ -125,6 +136,7 @@ int genie_set_stream(genie_model* h, void* cuda_stream) {
     GENIE_CUDA(cudaStreamSynchronize(m.stream));
     m.t2s_graphs.reset();                       // captured steps were recorded on the old stream's branches
     if (m.stream && m.stream_owned) GENIE_CUDA(cudaStreamDestroy(m.stream));
+    if (m.stream_bulk) { cudaStreamSynchronize(m.stream_bulk); cudaStreamDestroy(m.stream_bulk); m.stream_bulk = nullptr; }
     if (cuda_stream) { m.stream = reinterpret_cast<cudaStream_t>(cuda_stream); m.stream_owned = false; }
     else { GENIE_CUDA(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking)); m.stream_owned = true; }
     return 0;
@@ -390,6 +402,9 @@ int genie_set_option(genie_model* h, const char* key, int value) {
                       {"kv_fp16", &m.kv_fp16, false},
                       {"decode_split_min", &m.decode_split_min, true}, {"decode_branches", &m.decode_branches, true},
                       {"skinny_max_rows", &m.skinny_max_rows, true}, {"tc_min_rows", &m.tc_min_rows, true}};
+  if (std::strcmp(key, "sm_partition") == 0) {
+    return guarded([&] { model_enable_partition(m, value); return 0; });
+  }
   for (const Opt& o : opts)
     if (std::strcmp(key, o.name) == 0) {
       *o.field = value;

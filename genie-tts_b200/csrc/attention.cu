@@ -6,6 +6,7 @@
 //    head-major fp32 KV cache (stage#[63-96] without the per-step Concat).
 #include "common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace genie {
 namespace {
@@ -590,6 +591,203 @@ __global__ void __launch_bounds__(128) decode_attention16_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Bulk-copy variant of the fp16-cache decode attention (the default): the K and V rows of one (utterance, head)
+// are CONTIGUOUS in the head-major cache, so ONE thread streams them into a shared-memory ring with cp.async.bulk
+// (128-key chunks of 8 KB + 8 KB, mbarrier expect_tx / complete_tx); all chunks of a ~20-character sentence
+// (<= 384 cached tokens) are in flight before the CTA has even read q.  In-flight bytes are bounded by shared memory
+// (48 KB per CTA, 4 CTAs per SM) instead of registers: the register-staged kernel above keeps ~8 KB per CTA in
+// flight and a chain of three dependent load rounds per CTA, this one a single round trip for the whole slab.
+// The arithmetic (and its order) is the register kernel's: 4 lanes x 8 halves per key, 8 keys per warp pass.
+// ---------------------------------------------------------------------------
+constexpr int ACH = 128;                           // keys per ring stage
+constexpr int AST = 3;                             // ring stages
+constexpr uint32_t ASTAGE = 2u * ACH * 64u;        // K chunk + V chunk
+constexpr size_t ATT_BULK_SMEM = (size_t)AST * ASTAGE + 64 + (32 + 32 + 32 * 33) * sizeof(float) + 128;
+
+__device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool FUSED>
+__global__ void __launch_bounds__(128) decode_attention16_bulk_kernel(
+    const float* __restrict__ q, int nsplit, long long split_stride, const float* __restrict__ bias,
+    float* __restrict__ o, __half* __restrict__ kv_base, long long utt_stride, long long layer_off, long long v_off,
+    const int* __restrict__ kv_len, const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
+  extern __shared__ uint8_t att_smem_raw[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  if (FUSED) pdl_trigger();
+  const int kvl = kv_len[b];
+  const int act = active ? active[b] : 1;
+  if (!act) return;
+  const int T = kvl + (FUSED ? 0 : t_add);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 2, sub = lane & 3;
+  __half* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
+  __half* V = K + v_off;
+  uint8_t* ring = att_smem_raw + ((128u - (att_smem_u32(att_smem_raw) & 127u)) & 127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)AST * ASTAGE);
+  float* sm_m = reinterpret_cast<float*>(ring + (size_t)AST * ASTAGE + 64);
+  float* sm_l = sm_m + 32;
+  float* sm_acc = sm_l + 32;                                  // [32][33]
+  const int nch = (T + ACH - 1) / ACH;
+
+  auto issue = [&](int c) {                                   // thread 0: chunk c -> stage c % AST
+    const int rows = min(ACH, T - c * ACH);
+    const uint32_t bytes = (uint32_t)rows * 64u;
+    uint64_t* bar = &full[c % AST];
+    uint8_t* dst = ring + (size_t)(c % AST) * ASTAGE;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(2u * bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(att_smem_u32(dst)), "l"(K + (long long)c * ACH * 32), "r"(bytes), "r"(att_smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(att_smem_u32(dst + ACH * 64)), "l"(V + (long long)c * ACH * 32), "r"(bytes), "r"(att_smem_u32(bar)) : "memory");
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < AST; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(att_smem_u32(&full[s])), "r"(1u));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // cached rows were written by earlier steps / the prefill: complete before this step's first kernel started,
+    // so the whole slab may be requested ahead of the PDL wait
+    for (int c = 0; c < nch && c < AST; ++c) issue(c);
+  }
+  __syncthreads();
+
+  float q8[8], kn[8], vn[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { q8[e] = 0.f; kn[e] = 0.f; vn[e] = 0.f; }
+  if (FUSED) {
+    const float* pq = q + (long long)b * ldq + h * 32 + sub * 8;
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + h * 32 + sub * 8 + e));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(bias + 512 + h * 32 + sub * 8 + e));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(bias + 1024 + h * 32 + sub * 8 + e));
+        q8[e] = a.x; q8[e + 1] = a.y; q8[e + 2] = a.z; q8[e + 3] = a.w;
+        kn[e] = c.x; kn[e + 1] = c.y; kn[e + 2] = c.z; kn[e + 3] = c.w;
+        vn[e] = d.x; vn[e + 1] = d.y; vn[e + 2] = d.z; vn[e + 3] = d.w;
+      }
+    }
+    pdl_wait();
+    for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + e));
+        const float4 c = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 512 + e));
+        const float4 d = __ldcg(reinterpret_cast<const float4*>(pq + sp * split_stride + 1024 + e));
+        q8[e] += a.x; q8[e + 1] += a.y; q8[e + 2] += a.z; q8[e + 3] += a.w;
+        kn[e] += c.x; kn[e + 1] += c.y; kn[e + 2] += c.z; kn[e + 3] += c.w;
+        vn[e] += d.x; vn[e + 1] += d.y; vn[e + 2] += d.z; vn[e + 3] += d.w;
+      }
+    }
+    if (warp == 0 && grp == 0 && T < cap) {
+      *reinterpret_cast<uint4*>(K + (long long)T * 32 + sub * 8) = f8_to_h8(kn);
+      *reinterpret_cast<uint4*>(V + (long long)T * 32 + sub * 8) = f8_to_h8(vn);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q8[e] = q[(long long)b * ldq + h * 32 + sub * 8 + e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q8[e] *= scale;
+
+  float m = -CUDART_INF_F, l = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    const int st = c % AST;
+    const uint32_t parity = (uint32_t)((c / AST) & 1);
+    {
+      uint32_t done = 0;
+      for (uint32_t i = 0; i < (1u << 24) && !done; ++i)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(att_smem_u32(&full[st])), "r"(parity) : "memory");
+    }
+    const uint8_t* kc = ring + (size_t)st * ASTAGE;
+    const uint8_t* vc = kc + ACH * 64;
+    const int rows = min(ACH, T - c * ACH);
+    float sc[4];
+    uint4 v8[4];
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = u * 32 + warp * 8 + grp;                  // same key order as the register kernel
+      uint4 k8 = make_uint4(0u, 0u, 0u, 0u);
+      v8[u] = k8;
+      if (j < rows) {
+        k8 = *reinterpret_cast<const uint4*>(kc + j * 64 + sub * 16);
+        v8[u] = *reinterpret_cast<const uint4*>(vc + j * 64 + sub * 16);
+      }
+      float kf[8];
+      h8_to_f8(k8, kf);
+      float t = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t = fmaf(q8[e], kf[e], t);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      sc[u] = (j < rows) ? t : -CUDART_INF_F;
+      m_new = fmaxf(m_new, sc[u]);
+    }
+    if (m_new != -CUDART_INF_F) {
+      const float cf = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+      l *= cf;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= cf;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pj = (sc[u] == -CUDART_INF_F) ? 0.f : expf(sc[u] - m_new);
+        l += pj;
+        float vf[8];
+        h8_to_f8(v8[u], vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
+      }
+      m = m_new;
+    }
+    if (c + AST < nch) {                                      // long caches: recycle the stage
+      __syncthreads();
+      if (tid == 0) issue(c + AST);
+    }
+  }
+  if (FUSED && warp == 0 && grp == 0) {                      // the token of this step, in fp32
+    float t = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t = fmaf(q8[e], kn[e], t);
+    t += __shfl_xor_sync(0x0000000fu, t, 1);
+    t += __shfl_xor_sync(0x0000000fu, t, 2);
+    const float m_new = fmaxf(m, t);
+    const float cf = (m == -CUDART_INF_F) ? 0.f : expf(m - m_new);
+    const float pj = expf(t - m_new);
+    l = l * cf + pj;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * cf + pj * vn[e];
+    m = m_new;
+  }
+  const int g = warp * 8 + grp;
+  if (sub == 0) { sm_m[g] = m; sm_l[g] = l; }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm_acc[g * 33 + sub * 8 + e] = acc[e];
+  __syncthreads();
+  if (warp == 0) {
+    float M = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) M = fmaxf(M, sm_m[i]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float wgt = (sm_m[i] == -CUDART_INF_F) ? 0.f : expf(sm_m[i] - M);
+      num = fmaf(sm_acc[i * 33 + lane], wgt, num);
+      den = fmaf(sm_l[i], wgt, den);
+    }
+    o[(long long)b * 512 + h * 32 + lane] = num / den;
+  }
+}
+
 }  // namespace
 
 void launch_attention(const Attn& p, cudaStream_t s) {
@@ -618,7 +816,14 @@ void launch_decode_attention_fused(const float* part, int nsplit, long long spli
                                    long long v_off, const int* kv_len, const int* active, int B, int cap, float scale,
                                    cudaStream_t s) {
   if (B <= 0) return;
-  if (kv_f16)
+  static const bool bulk = [] { const char* e = getenv("GENIE_ATT_BULK"); return !(e && e[0] == '0'); }();
+  if (kv_f16 && bulk) {
+    static DynSmemAttr attr;
+    attr.ensure(decode_attention16_bulk_kernel<true>, ATT_BULK_SMEM);
+    launch_pdl(decode_attention16_bulk_kernel<true>, dim3(16, B), dim3(128), ATT_BULK_SMEM, s, part, nsplit, split_stride,
+               bias, o, reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0,
+               1536);
+  } else if (kv_f16)
     launch_pdl(decode_attention16_kernel<true>, dim3(16, B), dim3(128), 0, s, part, nsplit, split_stride, bias, o,
                reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0, 1536);
   else

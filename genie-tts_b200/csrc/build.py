@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["conv_gemm.cu", "tc_gemm.cu", "tc_halo_conv.cu", "tc_pair_conv.cu", "selftest.cu", "skinny_gemm.cu", "tc_small_gemm.cu", "attention.cu", "elementwise.cu", "sampler.cu", "weights.cu", "t2s.cu", "t2s_persistent.cu", "vits.cu",
-           "api.cu"]
+           "partition.cu", "api.cu"]
 LIB = os.path.join(HERE, "libgenie_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-Werror=pointer-arith", "--expt-relaxed-constexpr"]

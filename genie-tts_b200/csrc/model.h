@@ -76,6 +76,16 @@ struct Workspace {
   unsigned long long generation = 0;   // bumped whenever any buffer moves (invalidates captured graphs)
 };
 
+// SM partition of one device (partition.cu): a decode partition and a bulk partition (CUDA green contexts) shared
+// by every handle that opts in, plus the two tokens that make the handles alternate between them.
+struct DevicePartition {
+  int device = 0, decode_sms_requested = 0, decode_sms = 0, bulk_sms = 0;
+  void* green_decode = nullptr; void* green_bulk = nullptr;      // CUgreenCtx
+  std::mutex tok_decode, tok_bulk;
+};
+DevicePartition* device_partition(int device, int decode_sms);
+cudaStream_t partition_stream(DevicePartition* p, bool decode, int priority);
+
 // Device allocations holding a model's weights.  Shared (ref-counted) by the model handle and every execution
 // context cloned from it (genie_context_create): the weights are freed when the last of them is destroyed.
 struct WeightOwner {
@@ -135,6 +145,15 @@ struct Model : ModelWeights {
   // the decode-step graph runs the batch as up to 4 independent branches (contiguous utterance ranges) on
   // their own streams: every decode kernel is latency-bound, so the branches overlap
   cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+  // Bulk work (prefill, SoVITS) runs on a LOWER-priority stream than the decode step: when two handles share a GPU
+  // (GENIE.tts_batch_stream, server contexts) the tiny latency-bound decode kernels of one batch are scheduled ahead
+  // of the remaining CTAs of the other batch's vocoder kernels.  Null when the handle is bound to a caller's stream.
+  cudaStream_t stream_bulk = nullptr;
+  cudaEvent_t ev_bulk = nullptr;
+  // option sm_partition = N: the decode streams live in an N-SM partition of the device, the bulk stream in the
+  // rest (partition.cu); decode_sms is what the decode kernels may size their grids for
+  DevicePartition* partition = nullptr;
+  int decode_sms = 0;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
   int decode_split_min = 64;          // batches >= this are split; decode_branches = number of branches
   int decode_branches = 2;
@@ -222,6 +241,20 @@ void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, in
                 const Half2Part* y16 = nullptr);
 inline bool tc_linear_ok(const Model& m, const Linear& L, int M) { return m.use_tc && L.tc.hi && M >= m.tc_min_rows; }
 void keep_tensor(Model& m, const char* name, const float* dev, long long n);
+// RAII: route the launches of a bulk stage to the handle's low-priority stream (ordered after what is already queued
+// on the main stream); on exit the main stream waits for the stage's work
+struct BulkStreamScope {
+  Model& m; cudaStream_t keep; bool locked = false;
+  explicit BulkStreamScope(Model& mm);
+  ~BulkStreamScope();
+};
+// RAII: the decode token of a partitioned device (no-op otherwise); released after the decode stream has drained
+struct DecodeTokenScope {
+  Model& m; bool locked = false;
+  explicit DecodeTokenScope(Model& mm);
+  ~DecodeTokenScope();
+};
+void model_enable_partition(Model& m, int decode_sms);
 void check_tc_error(Model& m);
 template <typename T> T* dev_alloc(std::vector<void*>& owned, size_t count) {
   void* p = nullptr;

@@ -266,8 +266,9 @@ T2SSession& pool_build(Model& m, int n_slots, int kv_cap, int hist_ld, bool pool
 void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* prompts, const int64_t* text_seq,
            const int* text_len, const float* text_bert, const SamplingCfg* cfgs, int n_cfg, int io_dev) {
   GENIE_CHECK(n > 0, "empty batch");
-  cudaStream_t s = m.stream;
   GENIE_CUDA(cudaSetDevice(m.device));
+  const BulkStreamScope bulk(m);             // prefill is throughput-bound: the handle's low-priority stream; the
+  cudaStream_t s = m.stream;                 // decode steps (main stream) are ordered after it when the scope ends
   // ---- geometry
   std::vector<int> Lr(n), Lt(n), Ly(n), Lx(n), Sx(n), slot(n), row_off(n + 1, 0), txt_off(n + 1, 0), txt_in_off(n + 1, 0);
   bool any_bert = text_bert != nullptr;
@@ -590,6 +591,7 @@ void t2s_prefill(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
 int t2s_decode_steps(Model& m, int n_steps, const volatile int* cancel, int* n_active_out, int* steps_done_out) {
   T2SSession& S = session_of(m);
   GENIE_CHECK(!S.pool_mode, "this handle runs a slot pool: use genie_t2s_pool_step");
+  const DecodeTokenScope token(m);           // partitioned device: one handle decodes at a time
   cudaStream_t s = m.stream;
   GENIE_CUDA(cudaSetDevice(m.device));
   const int B = S.B;
@@ -719,6 +721,7 @@ void t2s_pool_admit(Model& m, int n, const int* slots, Prompt* const* prompts, c
 int t2s_pool_step(Model& m, int n_steps, int* n_active_out) {
   T2SSession& S = session_of(m);
   GENIE_CHECK(S.pool_mode, "no slot pool on this handle");
+  const DecodeTokenScope token(m);
   GENIE_CUDA(cudaSetDevice(m.device));
   cudaStream_t s = m.stream;
   int hi = -1;

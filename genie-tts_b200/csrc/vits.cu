@@ -259,6 +259,7 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
   GENIE_CHECK(m.finalized, "model not finalized");
   GENIE_CHECK(B > 0, "empty batch");
   GENIE_CUDA(cudaSetDevice(m.device));
+  const BulkStreamScope bulk(m);             // throughput-bound stage: the handle's low-priority stream
   cudaStream_t s = m.stream;
   Workspace& ws = m.ws;
   if (noise_scale < 0.f) noise_scale = m.noise_scale;

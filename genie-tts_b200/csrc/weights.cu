@@ -22,6 +22,8 @@ Model::~Model() {
   for (void* p : ctx_owned) cudaFree(p);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
+  if (stream_bulk) cudaStreamDestroy(stream_bulk);
+  if (ev_bulk) cudaEventDestroy(ev_bulk);
   if (stream2) cudaStreamDestroy(stream2);
   if (stream3) cudaStreamDestroy(stream3);
   if (stream4) cudaStreamDestroy(stream4);
@@ -383,6 +385,60 @@ void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, in
   GENIE_CHECK(ksplit == 1, "run_linear: split-K needs the tcgen05 path");
   GENIE_CHECK(!a16 && !y16, "run_linear: fp16 hi/lo hand-over needs the tcgen05 path");
   launch_conv_gemm(p, m.stream);
+}
+
+BulkStreamScope::BulkStreamScope(Model& mm) : m(mm), keep(mm.stream) {
+  if (!m.stream_bulk) return;
+  if (m.partition) { m.partition->tok_bulk.lock(); locked = true; }   // one bulk stage at a time on the bulk SMs
+  cudaEventRecord(m.ev_bulk, m.stream);
+  cudaStreamWaitEvent(m.stream_bulk, m.ev_bulk, 0);
+  m.stream = m.stream_bulk;
+}
+BulkStreamScope::~BulkStreamScope() {
+  if (!m.stream_bulk) return;
+  m.stream = keep;
+  cudaEventRecord(m.ev_bulk, m.stream_bulk);
+  cudaStreamWaitEvent(m.stream, m.ev_bulk, 0);
+  if (locked) {
+    cudaStreamSynchronize(m.stream_bulk);      // the token passes on when the bulk SMs are really free
+    m.partition->tok_bulk.unlock();
+  }
+}
+
+DecodeTokenScope::DecodeTokenScope(Model& mm) : m(mm) {
+  if (m.partition) { m.partition->tok_decode.lock(); locked = true; }
+}
+DecodeTokenScope::~DecodeTokenScope() {
+  if (locked) {
+    cudaStreamSynchronize(m.stream);
+    m.partition->tok_decode.unlock();
+  }
+}
+
+// Move the handle's streams into the device's SM partitions (see partition.cu).  Captured decode steps are dropped
+// (they were recorded on the old streams); the persistent small-batch kernel sizes its grid for the whole device
+// and is switched off on a partitioned handle.
+void model_enable_partition(Model& m, int decode_sms) {
+  GENIE_CHECK(m.stream_owned, "sm_partition: the handle is bound to a caller-owned stream");
+  GENIE_CHECK(m.partition == nullptr, "sm_partition: already partitioned");
+  GENIE_CUDA(cudaSetDevice(m.device));
+  DevicePartition* p = device_partition(m.device, decode_sms);
+  GENIE_CUDA(cudaDeviceSynchronize());
+  m.t2s_graphs.reset();
+  m.t2s_session.reset();
+  int least = 0, greatest = 0;
+  GENIE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  for (cudaStream_t* s : {&m.stream, &m.stream2, &m.stream3, &m.stream4}) {
+    if (*s) cudaStreamDestroy(*s);
+    *s = partition_stream(p, true, greatest);
+  }
+  if (m.stream_bulk) cudaStreamDestroy(m.stream_bulk);
+  m.stream_bulk = partition_stream(p, false, least);
+  if (!m.ev_bulk) GENIE_CUDA(cudaEventCreateWithFlags(&m.ev_bulk, cudaEventDisableTiming));
+  m.partition = p;
+  m.decode_sms = p->decode_sms;
+  m.persistent_ok = 0;
+  ++m.options_gen;
 }
 
 void check_tc_error(Model& m) {

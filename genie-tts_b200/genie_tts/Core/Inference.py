@@ -132,4 +132,34 @@ class GENIE:
         return out
 
 
+    def tts_batch_stream(self, model, batches, sampling: Optional[SamplingParams] = None, depth: int = 2):
+        """Throughput form of ``tts_batch`` for a stream of batches: keeps ``depth`` batches in flight on ``depth``
+        execution contexts of ``model`` (same weights, own streams / workspaces) and yields each batch's waveforms
+        in order.  A decode step leaves most of the GPU idle (a chain of latency-bound kernels) while
+        the vocoder is throughput-bound, so the T2S stage of one batch overlaps the SoVITS stage of another.
+        ``batches``: iterable of (prompts, text_seqs, text_berts or None)."""
+        import queue as _q
+        from concurrent.futures import ThreadPoolExecutor
+        ctxs = model.pipeline_contexts(max(1, depth))
+        free: "_q.Queue" = _q.Queue()
+        for c in ctxs:
+            free.put(c)
+
+        def work(b):
+            ctx = free.get()
+            try:
+                return self.tts_batch(ctx, b[0], b[1], b[2] if len(b) > 2 else None, sampling=sampling)
+            finally:
+                free.put(ctx)
+
+        with ThreadPoolExecutor(max_workers=len(ctxs)) as ex:
+            pending = []
+            for b in batches:
+                pending.append(ex.submit(work, b))
+                if len(pending) > len(ctxs):             # bounded look-ahead: at most depth + 1 batches queued
+                    yield pending.pop(0).result()
+            for f in pending:
+                yield f.result()
+
+
 tts_client: GENIE = GENIE()

@@ -188,6 +188,15 @@ class B200Model:
         self._contexts.add(ctx)
         return ctx
 
+    def pipeline_contexts(self, depth: int) -> List["B200Model"]:
+        """``depth`` handles onto these weights (this one first): batches synthesised concurrently on them overlap
+        the latency-bound T2S decode of one batch with the throughput-bound SoVITS decode of another."""
+        ctxs = self.__dict__.setdefault("_pipe_ctxs", [])
+        ctxs[:] = [c for c in ctxs if not c.closed]
+        while len(ctxs) < depth - 1:
+            ctxs.append(self.create_context())
+        return [self] + ctxs[:depth - 1]
+
     def set_stream(self, cuda_stream: Optional[int]) -> None:
         N.check(N.lib().genie_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 

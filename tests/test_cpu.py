@@ -394,7 +394,7 @@ def test_bench_reference_arm_json_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "audio-sec/sec" and line["unit"] == "audio-s/s"
     assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
-    assert "workload" in line["config"] and "sample" in line["config"]
+    assert "workload" in line["config"] and line["config"]["bench_config"] == 2      # same object as the b200 arm's
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     e2e = line["e2e"]

@@ -242,6 +242,35 @@ def test_two_contexts_decode_concurrently_from_two_threads(v2):
         prompt.close()
 
 
+def test_tts_batch_stream_pipelined_equals_sequential(v2):
+    """GENIE.tts_batch_stream keeps two batches in flight on two execution contexts (T2S of one overlaps SoVITS of
+    the other, bulk stages on a lower-priority stream): every batch must come back in order with exactly the
+    waveforms the sequential call produces (seeded sampling, seeded z_p noise)."""
+    from genie_tts.Core.Inference import GENIE
+    from genie_tts.engine import SamplingParams
+    m, _ = v2
+    g = GENIE()
+    pr = make_prompt_inputs(seed=1800, Lr=20, Ts=64, n_audio=32000)
+    prompt = _prompt(m, pr)
+    sp = SamplingParams(seed=21, max_steps=20, fixed_steps=20)
+    batches = []
+    for k in range(5):
+        n = 9 + 3 * k
+        txs = [make_text_inputs(seed=1810 + 40 * k + i, Lt=8 + (i % 7)) for i in range(n)]
+        batches.append(([prompt] * n, [t["text_seq"] for t in txs], None))
+    try:
+        ref = [g.tts_batch(m, *b, sampling=sp) for b in batches]
+        for depth in (2, 3):
+            got = list(g.tts_batch_stream(m, batches, sampling=sp, depth=depth))
+            assert len(got) == len(ref)
+            for a, b in zip(got, ref):
+                assert len(a) == len(b)
+                for x, y in zip(a, b):
+                    assert x.shape == y.shape and np.array_equal(x, y)
+    finally:
+        prompt.close()
+
+
 def test_model_and_prompt_lifetimes(v2_dir):
     """closing a model while prompts built on it are alive must not leave dangling handles: the model
     closes its prompts (their HBM goes with it), later prompt.close() / __del__ are no-ops, and a prompt destroyed
