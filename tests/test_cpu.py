@@ -224,8 +224,12 @@ def test_gloo_world_size_2_bench_aggregation(tmp_path):
         "assert dt == [0.5 * w, 0.25] and units == [10.0 * w, sum(3.0 + k for k in range(w))], (dt, units)\n"
         "dist.barrier(); print('ok', r)\n")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    import socket
+    with socket.socket() as sk:                       # a free port: a fixed one can still be in TIME_WAIT
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
