@@ -197,8 +197,9 @@ def line_config(cfg, args, world):
             "l2": "working set (KV cache, vocoder activations) >> 126 MB L2, no explicit flush",
             "parallelism": f"dp{world} by utterance, replicas only; every rank synthesises the same sentences "
                            "(yield-independent scaling)",
-            "pipeline": f"{depth} steps in flight per GPU on {depth} execution contexts (T2S of one step overlaps "
-                        "SoVITS of another); stage_ms / rooflines / share_of_step are measured on isolated steps"}
+            "pipeline": f"{depth} steps in flight per GPU on {depth} execution contexts, stage-aligned: prefills one "
+                        "after the other, the decodes of all steps in flight at the same time, then the vocoder passes; "
+                        "stage_ms / rooflines / share_of_step are measured on isolated steps"}
 
 
 def cpu_sample_tokens(cfg):
@@ -249,7 +250,7 @@ def main():
     ap.add_argument("--kv-fp32", action="store_true", help="keep the KV cache rows in fp32 (default: fp16 rows)")
     ap.add_argument("--pipeline", type=int, default=2,
                     help="batches in flight per GPU (execution contexts on the same weights): 1 = one step after "
-                         "the other; 2 (default) overlaps the T2S stage of one step with the SoVITS stage of another")
+                         "the other; 2 (default): two steps in flight, their decode stages run at the same time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]
@@ -340,24 +341,38 @@ def main():
             stage_ms["vits"].append(t2["vits_ms"]); stage_ms["generator"].append(t2["generator_ms"])
         return float(alen.sum()) / 32000.0, t2
 
-    def run_steps(n, fn):
-        """n steps on `depth` worker threads, each bound to its own context; returns the summed first results."""
-        if depth == 1:
-            return [fn(0) for _ in range(n)]
-        from concurrent.futures import ThreadPoolExecutor
-        import queue as _q
-        free = _q.Queue()
-        for k in range(depth):
-            free.put(k)
+    def vocode_device(k, y_len, idx):
+        ctx = ctxs[k]
+        y_dev, audio_dev = io[k]
+        y = y_dev.cpu().numpy()
+        sems = [strip_eos(finish_t2s(y[b, :y_len[b]], int(idx[b]))).reshape(-1) for b in range(B)]
+        sems = [s if len(s) else np.zeros(1, np.int64) for s in sems]
+        sl = np.asarray([len(s) for s in sems], dtype=np.int32)
+        sem_dev = torch.from_numpy(np.concatenate(sems)).to(dev)
+        alen = ctx.vits_decode_device(prompts, seq_dev, lens, sem_dev, sl, audio_dev, seed=sp.seed)
+        return float(alen.sum()) / 32000.0
 
-        def work(_):
-            k = free.get()
-            try:
-                return fn(k)
-            finally:
-                free.put(k)
+    def run_steps_device(n):
+        """n steps, `depth` in flight, stage-aligned like GENIE.tts_batch_stream: per wave the prefills one after the
+        other, ALL decodes at the same time (one host thread per context), then the vocoder passes."""
+        if depth == 1:
+            return sum(step_device(0, record=False)[0] for _ in range(n))
+        from concurrent.futures import ThreadPoolExecutor
+        total, done = 0.0, 0
+
+        def dec(k):
+            ctxs[k].t2s_decode_steps(TOKENS)
+            return ctxs[k].t2s_read_device(io[k][0])
         with ThreadPoolExecutor(max_workers=depth) as ex:
-            return list(ex.map(work, range(n)))
+            while done < n:
+                w = min(depth, n - done)
+                for k in range(w):
+                    ctxs[k].t2s_prefill_device(prompts, seq_dev, lens, sp, text_bert_cat=bert_dev)
+                toks = list(ex.map(dec, range(w)))
+                for k in range(w):
+                    total += vocode_device(k, *toks[k])
+                done += w
+        return total
 
     def step_host(k=0):
         auds = genie.tts_batch(ctxs[k], prompts, seqs, berts, sampling=sp)
@@ -379,8 +394,7 @@ def main():
     N.lib().genie_profiler_range(1)     # no-op unless run under `ncu --profile-from-start off`; outside the timed
     barrier()                           # region: the first cudaProfilerStart of a process costs tens of ms
     t0 = time.perf_counter()
-    res = run_steps(args.steps, lambda k: step_device(k, record=False))
-    audio_s = sum(r[0] for r in res)
+    audio_s = run_steps_device(args.steps)
     barrier()
     dt = time.perf_counter() - t0
     N.lib().genie_profiler_range(0)

@@ -601,15 +601,19 @@ __global__ void __launch_bounds__(128) decode_attention16_kernel(
 // flight and a chain of three dependent load rounds per CTA, this one a single round trip for the whole slab.
 // The arithmetic (and its order) is the register kernel's: 4 lanes x 8 halves per key, 8 keys per warp pass.
 // ---------------------------------------------------------------------------
-constexpr int ACH = 128;                           // keys per ring stage
-constexpr int AST = 3;                             // ring stages
-constexpr uint32_t ASTAGE = 2u * ACH * 64u;        // K chunk + V chunk
-constexpr size_t ATT_BULK_SMEM = (size_t)AST * ASTAGE + 64 + (32 + 32 + 32 * 33) * sizeof(float) + 128;
+// Two shapes.  LONG caches (slab >= 640 rows): 128 threads, 128-key stages, 3 stages (48 KB, 4 CTAs per SM).
+// SHORT caches (the ~20-character sentences of the headline workload, ~290 cached rows): 64 threads, 64-key stages,
+// 2 stages (16 KB) so that 11-12 CTAs fit an SM and ALL 16 x B CTAs of a 100-utterance batch are resident in ONE
+// wave — with 4-5 resident CTAs per SM the register-staged kernel needs three waves, the last one nearly empty.
+template <int NW, int CH, int NST>
+constexpr size_t att_bulk_smem() {
+  return (size_t)NST * 2 * CH * 64 + 64 + (size_t)(NW * 8 * 2 + NW * 8 * 33) * sizeof(float) + 128;
+}
 
 __device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(128) decode_attention16_bulk_kernel(
+template <bool FUSED, int NW, int CH, int NST>
+__global__ void __launch_bounds__(NW * 32, NW == 2 ? 12 : 4) decode_attention16_bulk_kernel(
     const float* __restrict__ q, int nsplit, long long split_stride, const float* __restrict__ bias,
     float* __restrict__ o, __half* __restrict__ kv_base, long long utt_stride, long long layer_off, long long v_off,
     const int* __restrict__ kv_len, const int* __restrict__ active, int cap, float scale, int t_add, int ldq) {
@@ -624,11 +628,13 @@ __global__ void __launch_bounds__(128) decode_attention16_bulk_kernel(
   const int grp = lane >> 2, sub = lane & 3;
   __half* K = kv_base + (long long)b * utt_stride + layer_off + (long long)h * cap * 32;
   __half* V = K + v_off;
+  constexpr int ACH = CH, AST = NST, NG = NW * 8;             // NG thread groups of 4 lanes: one key each per pass
+  constexpr uint32_t ASTAGE = 2u * ACH * 64u;                 // K chunk + V chunk
   uint8_t* ring = att_smem_raw + ((128u - (att_smem_u32(att_smem_raw) & 127u)) & 127u);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)AST * ASTAGE);
   float* sm_m = reinterpret_cast<float*>(ring + (size_t)AST * ASTAGE + 64);
-  float* sm_l = sm_m + 32;
-  float* sm_acc = sm_l + 32;                                  // [32][33]
+  float* sm_l = sm_m + NG;
+  float* sm_acc = sm_l + NG;                                  // [NG][33]
   const int nch = (T + ACH - 1) / ACH;
 
   auto issue = [&](int c) {                                   // thread 0: chunk c -> stage c % AST
@@ -711,12 +717,13 @@ __global__ void __launch_bounds__(128) decode_attention16_bulk_kernel(
     const uint8_t* kc = ring + (size_t)st * ASTAGE;
     const uint8_t* vc = kc + ACH * 64;
     const int rows = min(ACH, T - c * ACH);
-    float sc[4];
-    uint4 v8[4];
+    constexpr int NU = ACH / NG;                              // passes per stage
+    float sc[NU];
+    uint4 v8[NU];
     float m_new = m;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = u * 32 + warp * 8 + grp;                  // same key order as the register kernel
+    for (int u = 0; u < NU; ++u) {
+      const int j = u * NG + warp * 8 + grp;
       uint4 k8 = make_uint4(0u, 0u, 0u, 0u);
       v8[u] = k8;
       if (j < rows) {
@@ -739,7 +746,7 @@ __global__ void __launch_bounds__(128) decode_attention16_bulk_kernel(
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] *= cf;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const float pj = (sc[u] == -CUDART_INF_F) ? 0.f : expf(sc[u] - m_new);
         l += pj;
         float vf[8];
@@ -776,10 +783,10 @@ __global__ void __launch_bounds__(128) decode_attention16_bulk_kernel(
   if (warp == 0) {
     float M = -CUDART_INF_F;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) M = fmaxf(M, sm_m[i]);
+    for (int i = 0; i < NG; ++i) M = fmaxf(M, sm_m[i]);
     float num = 0.f, den = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NG; ++i) {
       float wgt = (sm_m[i] == -CUDART_INF_F) ? 0.f : expf(sm_m[i] - M);
       num = fmaf(sm_acc[i * 33 + lane], wgt, num);
       den = fmaf(sm_l[i], wgt, den);
@@ -816,13 +823,24 @@ void launch_decode_attention_fused(const float* part, int nsplit, long long spli
                                    long long v_off, const int* kv_len, const int* active, int B, int cap, float scale,
                                    cudaStream_t s) {
   if (B <= 0) return;
-  static const bool bulk = [] { const char* e = getenv("GENIE_ATT_BULK"); return !(e && e[0] == '0'); }();
-  if (kv_f16 && bulk) {
+  // slab size (`cap`) is what the host knows when the step is captured: long slabs take the 128-thread / 48 KB ring,
+  // short ones the 64-thread / 16 KB ring (one wave); GENIE_ATT_BULK=0 falls back to the register-staged kernel
+  static const int bulk_mode = [] { const char* e = getenv("GENIE_ATT_BULK"); return e ? atoi(e) : 3; }();
+  const bool long_cache = cap >= 640;
+  if (kv_f16 && long_cache && (bulk_mode & 1)) {
+    constexpr size_t smem = att_bulk_smem<4, 128, 3>();
     static DynSmemAttr attr;
-    attr.ensure(decode_attention16_bulk_kernel<true>, ATT_BULK_SMEM);
-    launch_pdl(decode_attention16_bulk_kernel<true>, dim3(16, B), dim3(128), ATT_BULK_SMEM, s, part, nsplit, split_stride,
-               bias, o, reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0,
-               1536);
+    attr.ensure(decode_attention16_bulk_kernel<true, 4, 128, 3>, smem);
+    launch_pdl(decode_attention16_bulk_kernel<true, 4, 128, 3>, dim3(16, B), dim3(128), smem, s, part, nsplit,
+               split_stride, bias, o, reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active,
+               cap, scale, 0, 1536);
+  } else if (kv_f16 && !long_cache && (bulk_mode & 2)) {
+    constexpr size_t smem = att_bulk_smem<2, 64, 2>();
+    static DynSmemAttr attr;
+    attr.ensure(decode_attention16_bulk_kernel<true, 2, 64, 2>, smem);
+    launch_pdl(decode_attention16_bulk_kernel<true, 2, 64, 2>, dim3(16, B), dim3(64), smem, s, part, nsplit,
+               split_stride, bias, o, reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active,
+               cap, scale, 0, 1536);
   } else if (kv_f16)
     launch_pdl(decode_attention16_kernel<true>, dim3(16, B), dim3(128), 0, s, part, nsplit, split_stride, bias, o,
                reinterpret_cast<__half*>(kv_base), utt_stride, layer_off, v_off, kv_len, active, cap, scale, 0, 1536);

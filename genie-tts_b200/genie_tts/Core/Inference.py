@@ -120,6 +120,10 @@ class GENIE:
         ys, idx = model.t2s_generate(prompts, text_seqs, text_berts, sp, cancel_flag=self.stop_event.c_flag)
         if not ys:
             return []
+        return self._vocode_batch(model, prompts, text_seqs, ys, idx, sp, zp_noise)
+
+    def _vocode_batch(self, model, prompts, text_seqs, ys, idx, sp, zp_noise) -> List[np.ndarray]:
+        """Host glue of Inference.py:41-44,108-109 per utterance, then ONE vocoder call for the batch."""
         sems = [strip_eos(finish_t2s(y, i)).reshape(-1) for y, i in zip(ys, idx)]
         keep = [b for b, s in enumerate(sems) if len(s) > 0]
         out: List[np.ndarray] = [np.zeros(0, np.float32) for _ in sems]
@@ -133,33 +137,44 @@ class GENIE:
 
 
     def tts_batch_stream(self, model, batches, sampling: Optional[SamplingParams] = None, depth: int = 2):
-        """Throughput form of ``tts_batch`` for a stream of batches: keeps ``depth`` batches in flight on ``depth``
-        execution contexts of ``model`` (same weights, own streams / workspaces) and yields each batch's waveforms
-        in order.  A decode step leaves most of the GPU idle (a chain of latency-bound kernels) while
-        the vocoder is throughput-bound, so the T2S stage of one batch overlaps the SoVITS stage of another.
-        ``batches``: iterable of (prompts, text_seqs, text_berts or None)."""
-        import queue as _q
+        """Throughput form of ``tts_batch`` for a stream of batches: ``depth`` batches are in flight together on
+        ``depth`` execution contexts of ``model`` (same weights, own streams / workspaces), and each batch's
+        waveforms are yielded in order.  The schedule is stage-aligned, per wave of ``depth`` batches:
+
+            prefill of every batch (one after the other: throughput-bound, nothing to gain from overlap)
+            decode of ALL batches at the same time (a decode step is a chain of latency-bound kernels; measured:
+                two 100-sentence decodes side by side take 1.46x the time of one — DESIGN.md section 5)
+            SoVITS of every batch (one after the other)
+
+        Per-batch results are exactly those of ``tts_batch``.  ``batches``: iterable of
+        (prompts, text_seqs, text_berts or None)."""
         from concurrent.futures import ThreadPoolExecutor
+        sp = sampling or self.sampling
         ctxs = model.pipeline_contexts(max(1, depth))
-        free: "_q.Queue" = _q.Queue()
-        for c in ctxs:
-            free.put(c)
-
-        def work(b):
-            ctx = free.get()
-            try:
-                return self.tts_batch(ctx, b[0], b[1], b[2] if len(b) > 2 else None, sampling=sampling)
-            finally:
-                free.put(ctx)
-
+        it = iter(batches)
         with ThreadPoolExecutor(max_workers=len(ctxs)) as ex:
-            pending = []
-            for b in batches:
-                pending.append(ex.submit(work, b))
-                if len(pending) > len(ctxs):             # bounded look-ahead: at most depth + 1 batches queued
-                    yield pending.pop(0).result()
-            for f in pending:
-                yield f.result()
+            while True:
+                wave = []
+                for _ in ctxs:
+                    try:
+                        wave.append(next(it))
+                    except StopIteration:
+                        break
+                if not wave:
+                    return
+                for ctx, b in zip(ctxs, wave):
+                    ctx.t2s_prefill(b[0], b[1], b[2] if len(b) > 2 else None, sp)
+
+                def decode(ctx):
+                    steps = sp.fixed_steps if sp.fixed_steps > 0 else (sp.max_steps if sp.max_steps > 0 else MAX_DECODE_STEPS)
+                    _, _, cancelled = ctx.t2s_decode_steps(steps, cancel_flag=self.stop_event.c_flag)
+                    return None if cancelled else ctx.t2s_read()
+                toks = list(ex.map(decode, ctxs[:len(wave)]))
+                for ctx, b, tk in zip(ctxs, wave, toks):
+                    if tk is None:
+                        yield []
+                        continue
+                    yield self._vocode_batch(ctx, b[0], b[1], tk[0], tk[1], sp, None)
 
 
 tts_client: GENIE = GENIE()

@@ -393,6 +393,26 @@ class B200Model:
                                            _ptr(idx)))
         return y_len, idx
 
+    def t2s_prefill_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sampling: SamplingParams,
+                           text_bert_cat=None) -> None:
+        """Device-resident form of ``t2s_prefill`` (inputs are CUDA tensors)."""
+        B = len(prompts)
+        lens = np.ascontiguousarray(text_lens, dtype=np.int32)
+        hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        csp = sampling.to_c()
+        steps = sampling.fixed_steps if sampling.fixed_steps > 0 else (sampling.max_steps if sampling.max_steps > 0 else 500)
+        self._inflight = (B, max(p.n_prompt_tokens for p in prompts) + steps + 2)
+        N.check(N.lib().genie_t2s_prefill(self._h, hs, B, _ptr(text_seq_cat), _ptr(lens), _ptr(text_bert_cat),
+                                          C.byref(csp), 1))
+
+    def t2s_read_device(self, y_out) -> Tuple[np.ndarray, np.ndarray]:
+        """Device-resident form of ``t2s_read``: tokens into the CUDA tensor ``y_out`` [B, y_ld]; (y_len, idx) on the host."""
+        B = self._inflight[0]
+        y_len = np.zeros(B, dtype=np.int32)
+        idx = np.zeros(B, dtype=np.int32)
+        N.check(N.lib().genie_t2s_read(self._h, 1, _ptr(y_out), int(y_out.shape[1]), _ptr(y_len), _ptr(idx)))
+        return y_len, idx
+
     def vits_decode_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sem_cat, sem_lens: np.ndarray,
                            audio_out, seed: int = 0) -> np.ndarray:
         B = len(prompts)
