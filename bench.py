@@ -59,7 +59,8 @@ GEN_GFLOP_PER_AUDIO_S = {"v2": 8.26 + 16.52 + 8.26 + 4.13 + 2.06 + 1.36,   # HiF
                          "v2ProPlus": 89.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one decode_attention launch from the committed `ncu --set full`
 # capture of the CURRENT kernel (profiles/), with the algorithmic bytes of that same launch
-ATT_NCU = {"file": "profiles/r01_v5_ncu_full_decode_attention.txt", "dram_bytes": 104438016, "algorithmic_bytes": 100.4e6}
+ATT_NCU = {"file": "profiles/r02/ncu_full_decode_attention16_bulk.txt (one branch launch of the two-branch step: 50 "
+                   "utterances, kv_len ~245, fp16 rows)", "dram_bytes": 25341184, "algorithmic_bytes": 25.0e6}
 
 
 def peaks():
