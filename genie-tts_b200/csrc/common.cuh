@@ -172,6 +172,7 @@ struct Attn {
   const float* rel_k = nullptr;                // [2*window+1, d] or null
   const float* rel_v = nullptr;
   int window = 0;
+  int use_mma = 0;                             // head dim 32, no rel-pos: tensor-core kernel (hi/lo split operands)
 };
 void launch_attention(const Attn& p, cudaStream_t s);
 

@@ -389,6 +389,7 @@ void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* p
   // ---- K4: 24 prefill layers over all rows of all admitted utterances
   const StepBufs& w = S.w;
   const float scale = 1.0f / std::sqrt(32.0f);
+  static const bool prefill_mma = [] { const char* e = getenv("GENIE_PREFILL_MMA"); return !(e && e[0] == '0'); }();
   float* Hcur = X;
   for (int l = 0; l < NL; ++l) {
     const T2SLayer& L = m.layers[l];
@@ -399,6 +400,7 @@ void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* p
     a.q = QKV; a.ldq = 3 * D; a.k = QKV + D; a.ldk = 3 * D; a.v = QKV + 2 * D; a.ldv = 3 * D;
     a.o = ATT; a.ldo = D; a.q_off = d_row_off; a.kv_off = d_row_off; a.B = n; a.H = H; a.d = 32; a.max_q = maxS;
     a.scale = scale; a.mask_mode = 1; a.lx = d_lx;
+    a.use_mma = prefill_mma ? 1 : 0;                   // tensor-core kernel, 3-product split precision
     launch_attention(a, s);
     run_linear(m, L.out, ATT, D, TMP, D, R, ACT_NONE, Hcur, D);
     launch_layernorm(TMP, nullptr, L.ln1_g, L.ln1_b, H1, R, D, s);
