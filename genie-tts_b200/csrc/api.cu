@@ -332,14 +332,15 @@ int genie_t2s_read(genie_model* h, int io_on_device, int64_t* y, int y_ld, int* 
 
 int genie_vits_decode(genie_model* h, genie_prompt* const* prompts, int B, const int64_t* text_seq,
                       const int* text_len, const int64_t* sem, const int* sem_len, const float* zp_noise,
-                      unsigned long long seed, float noise_scale, int io_on_device, float* audio, int* audio_len) {
+                      unsigned long long seed, float noise_scale, int io_on_device, float* audio, int* audio_len,
+                      const int* noise_ids) {
   return guarded([&] {
     GENIE_CHECK(h && prompts && text_seq && text_len && sem && sem_len, "null argument");
     std::lock_guard<std::mutex> lock(h->m.mu);
     std::vector<Prompt*> ps(B);
     for (int b = 0; b < B; ++b) { GENIE_CHECK(prompts[b], "null prompt"); ps[b] = &prompts[b]->p; }
     vits_decode(h->m, ps.data(), B, text_seq, text_len, sem, sem_len, zp_noise, seed, noise_scale, io_on_device,
-                audio, audio_len);
+                audio, audio_len, noise_ids);
     return 0;
   });
 }

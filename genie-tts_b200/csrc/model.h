@@ -231,7 +231,7 @@ void t2s_pool_release(Model& m, int slot);
 void t2s_pool_info(Model& m, int* n_slots, int* kv_cap, int* hist_ld);
 void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
                  const int64_t* sem, const int* sem_len, const float* zp_noise, unsigned long long seed,
-                 float noise_scale, int io_dev, float* audio, int* audio_len);
+                 float noise_scale, int io_dev, float* audio, int* audio_len, const int* noise_ids = nullptr);
 
 // helpers shared by the stage files
 // fp16 hi/lo pair: v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (operand hand-over between linears)

@@ -112,7 +112,7 @@ void run_vits_encoder(Model& m, const VitsEncLayer* L, int n, float* x, const Se
   }
 }
 
-__global__ void zp_noise_kernel(const float* __restrict__ stats, const float* __restrict__ noise,
+__global__ void zp_noise_kernel(const float* __restrict__ stats, const float* __restrict__ noise, const int* __restrict__ ids,
                                 unsigned long long seed, const int* __restrict__ row2utt,
                                 const int* __restrict__ off, float* __restrict__ zp, float scale, int rows) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,7 +122,7 @@ __global__ void zp_noise_kernel(const float* __restrict__ stats, const float* __
   float mu = stats[(long long)r * 384 + c], logs = stats[(long long)r * 384 + 192 + c];
   // graph layout of the noise is [192, 2T] per utterance (vits#[6490])
   float nz = noise ? noise[192LL * off[b] + (long long)c * T2 + t]
-                   : philox_normal(seed, (uint32_t)b, (uint32_t)t, (uint32_t)c, 1u);
+                   : philox_normal(seed, (uint32_t)(ids ? ids[b] : b), (uint32_t)t, (uint32_t)c, 1u);
   zp[i] = mu + nz * expf(logs) * scale;     // vits#[6491-6495]
 }
 
@@ -255,7 +255,7 @@ void prompt_build(Model& m, Prompt& p, const int64_t* ref_seq, int Lr, const flo
 // ---------------------------------------------------------------------------
 void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_seq, const int* text_len,
                  const int64_t* sem, const int* sem_len, const float* zp_noise, unsigned long long seed,
-                 float noise_scale, int io_dev, float* audio, int* audio_len) {
+                 float noise_scale, int io_dev, float* audio, int* audio_len, const int* noise_ids) {
   GENIE_CHECK(m.finalized, "model not finalized");
   GENIE_CHECK(B > 0, "empty batch");
   GENIE_CUDA(cudaSetDevice(m.device));
@@ -364,8 +364,14 @@ void vits_decode(Model& m, Prompt* const* prompts, int B, const int64_t* text_se
       GENIE_CUDA(cudaMemcpyAsync(NZ, zp_noise, (size_t)R2 * 192 * 4, in_kind, s));
       nz = NZ;
     }
-    zp_noise_kernel<<<(unsigned)(((long long)R2 * 192 + 255) / 256), 256, 0, s>>>(STATS, nz, seed, d_r2u, s2.off, Z,
-                                                                                 noise_scale, R2);
+    const int* d_ids = nullptr;
+    if (noise_ids) {                                   // Philox stream per utterance: its index in ITS OWN batch
+      int* ids = ws.get<int>("v.noise_ids", B);
+      GENIE_CUDA(cudaMemcpyAsync(ids, noise_ids, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+      d_ids = ids;
+    }
+    zp_noise_kernel<<<(unsigned)(((long long)R2 * 192 + 255) / 256), 256, 0, s>>>(STATS, nz, d_ids, seed, d_r2u, s2.off,
+                                                                                 Z, noise_scale, R2);
     GENIE_LAUNCHED("zp_noise");
   }
   // ---- K13: flow reverse (vits#[6500-7820])

@@ -122,15 +122,23 @@ class GENIE:
             return []
         return self._vocode_batch(model, prompts, text_seqs, ys, idx, sp, zp_noise)
 
-    def _vocode_batch(self, model, prompts, text_seqs, ys, idx, sp, zp_noise) -> List[np.ndarray]:
-        """Host glue of Inference.py:41-44,108-109 per utterance, then ONE vocoder call for the batch."""
+    def _vocode_batch(self, model, prompts, text_seqs, ys, idx, sp, zp_noise, noise_ids=None) -> List[np.ndarray]:
+        """Host glue of Inference.py:41-44,108-109 per utterance, then ONE vocoder call for the batch.
+        ``noise_ids[b]``: the utterance's index within its own batch when several batches share the call."""
         sems = [strip_eos(finish_t2s(y, i)).reshape(-1) for y, i in zip(ys, idx)]
         keep = [b for b, s in enumerate(sems) if len(s) > 0]
         out: List[np.ndarray] = [np.zeros(0, np.float32) for _ in sems]
         if keep:
+            # the vocoder numbers the utterances it receives 0..n-1: keep every utterance on the noise stream
+            # of its position among its own batch's non-empty utterances
+            if noise_ids is not None:
+                ids = [noise_ids[b] for b in keep]
+            else:
+                ids = None
             auds = model.vits_decode([prompts[b] for b in keep], [text_seqs[b] for b in keep],
                                      [sems[b] for b in keep],
-                                     [zp_noise[b] for b in keep] if zp_noise is not None else None, seed=sp.seed)
+                                     [zp_noise[b] for b in keep] if zp_noise is not None else None, seed=sp.seed,
+                                     noise_ids=ids)
             for b, a in zip(keep, auds):
                 out[b] = a
         return out
@@ -170,11 +178,24 @@ class GENIE:
                     _, _, cancelled = ctx.t2s_decode_steps(steps, cancel_flag=self.stop_event.c_flag)
                     return None if cancelled else ctx.t2s_read()
                 toks = list(ex.map(decode, ctxs[:len(wave)]))
-                for ctx, b, tk in zip(ctxs, wave, toks):
+                # ONE vocoder call for the whole wave (throughput-bound: a 200-utterance pass costs ~10 % less than
+                # two 100-utterance passes); every utterance keeps the Philox stream it has in a call of its own
+                # batch: its position among that batch's non-empty utterances
+                prm, seqs, ys, idx, ids, spans = [], [], [], [], [], []
+                for b, tk in zip(wave, toks):
                     if tk is None:
-                        yield []
+                        spans.append(None)
                         continue
-                    yield self._vocode_batch(ctx, b[0], b[1], tk[0], tk[1], sp, None)
+                    spans.append((len(ys), len(tk[0])))
+                    prm += list(b[0]); seqs += list(b[1]); ys += tk[0]; idx += tk[1]
+                    nonempty = 0
+                    for y, i in zip(tk[0], tk[1]):
+                        ids.append(nonempty)
+                        if strip_eos(finish_t2s(y, i)).shape[-1] > 0:
+                            nonempty += 1
+                auds = self._vocode_batch(ctxs[0], prm, seqs, ys, idx, sp, None, noise_ids=ids) if ys else []
+                for sp_ in spans:
+                    yield [] if sp_ is None else auds[sp_[0]:sp_[0] + sp_[1]]
 
 
 tts_client: GENIE = GENIE()

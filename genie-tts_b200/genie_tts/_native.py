@@ -64,7 +64,7 @@ SIGNATURES = {
     "genie_t2s_pool_read": (C.c_int, [_P, C.c_int, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "genie_t2s_release": (C.c_int, [_P, C.c_int]),
     "genie_vits_decode": (C.c_int, [_P, C.POINTER(_P), C.c_int, _P, _P, _P, _P, _P, C.c_ulonglong, C.c_float,
-                                    C.c_int, _P, _P]),
+                                    C.c_int, _P, _P, _P]),
     "genie_debug_record_logits": (C.c_int, [_P, C.c_int]),
     "genie_debug_read_logits": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     "genie_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.c_longlong, C.POINTER(C.c_longlong)]),

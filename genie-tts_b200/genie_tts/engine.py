@@ -345,7 +345,8 @@ class B200Model:
     # -- SoVITS -----------------------------------------------------------------
     def vits_decode(self, prompts: Sequence["B200Prompt"], text_seqs: Sequence[np.ndarray],
                     semantic: Sequence[np.ndarray], zp_noise: Optional[Sequence[np.ndarray]] = None,
-                    seed: Optional[int] = None, noise_scale: float = -1.0) -> List[np.ndarray]:
+                    seed: Optional[int] = None, noise_scale: float = -1.0,
+                    noise_ids: Optional[Sequence[int]] = None) -> List[np.ndarray]:
         """``seed=None``: fresh z_p noise per call, as the reference's unseeded RandomNormalLike (vits#[6490])."""
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
@@ -367,9 +368,10 @@ class B200Model:
         alen = np.zeros(B, dtype=np.int32)
         hs = (C.c_void_p * B)(*[p._h for p in prompts])
         seq_cat, sem_cat = np.concatenate(seqs), np.concatenate(sems)   # keep alive across the call
+        ids = np.ascontiguousarray(noise_ids, dtype=np.int32) if noise_ids is not None else None
         N.check(N.lib().genie_vits_decode(self._h, hs, B, _ptr(seq_cat), _ptr(tl),
                                           _ptr(sem_cat), _ptr(sl), _ptr(noise), seed & (2 ** 64 - 1),
-                                          noise_scale, 0, _ptr(audio), _ptr(alen)))
+                                          noise_scale, 0, _ptr(audio), _ptr(alen), _ptr(ids)))
         out, o = [], 0
         for b in range(B):
             out.append(audio[o:o + alen[b]])
@@ -414,14 +416,15 @@ class B200Model:
         return y_len, idx
 
     def vits_decode_device(self, prompts, text_seq_cat, text_lens: np.ndarray, sem_cat, sem_lens: np.ndarray,
-                           audio_out, seed: int = 0) -> np.ndarray:
+                           audio_out, seed: int = 0, noise_ids=None) -> np.ndarray:
         B = len(prompts)
         tl = np.ascontiguousarray(text_lens, dtype=np.int32)
         sl = np.ascontiguousarray(sem_lens, dtype=np.int32)
         alen = np.zeros(B, dtype=np.int32)
         hs = (C.c_void_p * B)(*[p._h for p in prompts])
+        ids = np.ascontiguousarray(noise_ids, dtype=np.int32) if noise_ids is not None else None
         N.check(N.lib().genie_vits_decode(self._h, hs, B, _ptr(text_seq_cat), _ptr(tl), _ptr(sem_cat), _ptr(sl), None,
-                                          seed & (2 ** 64 - 1), -1.0, 1, _ptr(audio_out), _ptr(alen)))
+                                          seed & (2 ** 64 - 1), -1.0, 1, _ptr(audio_out), _ptr(alen), _ptr(ids)))
         return alen
 
     # -- debug ------------------------------------------------------------------

@@ -172,10 +172,13 @@ int genie_t2s_release(genie_model* m, int slot);
  * sem: int64 concat of semantic tokens (sum sem_len, every id < 1024);
  * zp_noise: f32 concat per utterance of [192, 2*sem_len[b]] (the graph's RandomNormalLike
  * layout, vits#[6490]) or NULL -> Philox N(0,1) from `seed`; noise_scale < 0 -> model constant.
- * audio: f32 concat, 1280 samples per semantic token; audio_len[B]. */
+ * audio: f32 concat, 1280 samples per semantic token; audio_len[B].
+ * noise_ids: int[B] or NULL — the Philox stream of utterance b is keyed by (seed, noise_ids[b]) instead of (seed, b),
+ * so that several batches vocoded in ONE call draw the noise they would have drawn in separate calls (host int[B]). */
 int genie_vits_decode(genie_model* m, genie_prompt* const* prompts, int B, const int64_t* text_seq,
                       const int* text_len, const int64_t* sem, const int* sem_len, const float* zp_noise,
-                      unsigned long long seed, float noise_scale, int io_on_device, float* audio, int* audio_len);
+                      unsigned long long seed, float noise_scale, int io_on_device, float* audio, int* audio_len,
+                      const int* noise_ids);
 
 /* ---- introspection for parity tests (host pointers only) */
 /* logits of the last T2S call: f32[B, n_steps+1, 1025] when recording was enabled */
