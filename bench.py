@@ -199,7 +199,7 @@ def line_config(cfg, args, world):
             "parallelism": f"dp{world} by utterance, replicas only; every rank synthesises the same sentences "
                            "(yield-independent scaling)",
             "pipeline": f"{depth} steps in flight per GPU on {depth} execution contexts, stage-aligned: prefills one "
-                        "after the other, the decodes of all steps in flight at the same time, one vocoder pass per wave; "
+                        "after the other, the decodes of all steps in flight at the same time, then the vocoder passes; "
                         "stage_ms / rooflines / share_of_step are measured on isolated steps"}
 
 
@@ -342,8 +342,21 @@ def main():
             stage_ms["vits"].append(t2["vits_ms"]); stage_ms["generator"].append(t2["generator_ms"])
         return float(alen.sum()) / 32000.0, t2
 
+    from genie_tts.Core.Inference import MERGE_WAVE_VOCODER as merge_vocoder
+
+    def vocode_device(k, y_len, idx):
+        y_dev, audio_dev = io[k]
+        y = y_dev.cpu().numpy()
+        sems = [strip_eos(finish_t2s(y[b, :y_len[b]], int(idx[b]))).reshape(-1) for b in range(B)]
+        sems = [x if len(x) else np.zeros(1, np.int64) for x in sems]
+        sl = np.asarray([len(x) for x in sems], dtype=np.int32)
+        sem_dev = torch.from_numpy(np.concatenate(sems)).to(dev)
+        alen = ctxs[k].vits_decode_device(prompts, seq_dev, lens, sem_dev, sl, audio_dev, seed=sp.seed)
+        return float(alen.sum()) / 32000.0
+
     seq_dev_w = torch.cat([seq_dev] * depth) if depth > 1 else seq_dev
-    audio_dev_w = torch.zeros(depth * B * TOKENS * 1280, dtype=torch.float32, device=dev) if depth > 1 else None
+    audio_dev_w = (torch.zeros(depth * B * TOKENS * 1280, dtype=torch.float32, device=dev)
+                   if depth > 1 and merge_vocoder else None)
 
     def vocode_device_wave(toks):
         """ONE vocoder pass for the whole wave (as GENIE.tts_batch_stream does): utterances of all steps in flight,
@@ -378,7 +391,11 @@ def main():
                 for k in range(w):
                     ctxs[k].t2s_prefill_device(prompts, seq_dev, lens, sp, text_bert_cat=bert_dev)
                 toks = list(ex.map(dec, range(w)))
-                total += vocode_device_wave(toks)
+                if merge_vocoder:
+                    total += vocode_device_wave(toks)
+                else:
+                    for k in range(w):
+                        total += vocode_device(k, *toks[k])
                 done += w
         return total
 

@@ -8,6 +8,7 @@
 // LayerNorm (elementwise.cu), the fused decode attention (attention.cu) or this kernel's own A-operand loader (FFN2 reads
 // relu(sum FFN1 partials + bias)).
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace genie {
 namespace {
@@ -229,7 +230,11 @@ void launch_nt(const SmallGemm& p, int* err_flag, cudaStream_t s) {
 
 void launch_tc_small_gemm(const SmallGemm& p, int nt, int* err_flag, cudaStream_t s) {
   GENIE_CHECK(p.M >= 1 && p.M <= 128 && p.K % KS == 0 && p.ldx % 4 == 0 && p.ldw % 8 == 0, "tc_small_gemm: bad shape");
+  // experiment knob: GENIE_SMALL_NT=64 doubles the N tile of the <= 64-row variant (half the CTAs per GEMM: less
+  // pressure on the 2-CTA-per-SM shared-memory slots when several decode chains run side by side)
+  static const int env_nt = [] { const char* e = getenv("GENIE_SMALL_NT"); return e ? atoi(e) : 0; }();
   if (nt == 64) launch_nt<64, 512>(p, err_flag, s);
+  else if (p.M <= 64 && env_nt == 64 && p.N % 64 == 0) launch_nt<64, 256>(p, err_flag, s);
   else if (p.M <= 64) launch_nt<32, 256>(p, err_flag, s);
   else launch_nt<32, 512>(p, err_flag, s);
 }

@@ -17,6 +17,10 @@ import numpy as np
 from ..GetPhonesAndBert import get_phones_and_bert
 from ..engine import SamplingParams
 
+import os as _os
+# one vocoder call per wave instead of one per batch: +1.5 % device-resident, but -4 % through host buffers (measured,
+# DESIGN.md section 5), so the default keeps one call per batch
+MERGE_WAVE_VOCODER = _os.environ.get("GENIE_WAVE_VOCODER", "split") == "merged"
 MAX_T2S_LEN = 1000
 MAX_DECODE_STEPS = 500      # reference Inference.py:95
 
@@ -151,8 +155,8 @@ class GENIE:
 
             prefill of every batch (one after the other: throughput-bound, nothing to gain from overlap)
             decode of ALL batches at the same time (a decode step is a chain of latency-bound kernels; measured:
-                two 100-sentence decodes side by side take 1.46x the time of one — DESIGN.md section 5)
-            SoVITS of every batch (one after the other)
+                two 100-sentence decodes side by side take 1.4x the time of one — DESIGN.md section 5)
+            SoVITS of every batch (one after the other; GENIE_WAVE_VOCODER=merged: one call for the wave)
 
         Per-batch results are exactly those of ``tts_batch``.  ``batches``: iterable of
         (prompts, text_seqs, text_berts or None)."""
@@ -193,9 +197,13 @@ class GENIE:
                         ids.append(nonempty)
                         if strip_eos(finish_t2s(y, i)).shape[-1] > 0:
                             nonempty += 1
-                auds = self._vocode_batch(ctxs[0], prm, seqs, ys, idx, sp, None, noise_ids=ids) if ys else []
-                for sp_ in spans:
-                    yield [] if sp_ is None else auds[sp_[0]:sp_[0] + sp_[1]]
+                if MERGE_WAVE_VOCODER:
+                    auds = self._vocode_batch(ctxs[0], prm, seqs, ys, idx, sp, None, noise_ids=ids) if ys else []
+                    for sp_ in spans:
+                        yield [] if sp_ is None else auds[sp_[0]:sp_[0] + sp_[1]]
+                else:
+                    for ctx, b, tk in zip(ctxs, wave, toks):
+                        yield [] if tk is None else self._vocode_batch(ctx, b[0], b[1], tk[0], tk[1], sp, None)
 
 
 tts_client: GENIE = GENIE()
