@@ -249,9 +249,9 @@ def main():
     ap.add_argument("--sentences", type=int, default=0, help="override the config's batch size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kv-fp32", action="store_true", help="keep the KV cache rows in fp32 (default: fp16 rows)")
-    ap.add_argument("--pipeline", type=int, default=2,
+    ap.add_argument("--pipeline", type=int, default=3,
                     help="batches in flight per GPU (execution contexts on the same weights): 1 = one step after "
-                         "the other; 2 (default): two steps in flight, their decode stages run at the same time")
+                         "the other; 3 (default): three steps in flight, their decode stages run at the same time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = CONFIGS[args.config]

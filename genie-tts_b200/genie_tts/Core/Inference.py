@@ -148,7 +148,7 @@ class GENIE:
         return out
 
 
-    def tts_batch_stream(self, model, batches, sampling: Optional[SamplingParams] = None, depth: int = 2):
+    def tts_batch_stream(self, model, batches, sampling: Optional[SamplingParams] = None, depth: int = 3):
         """Throughput form of ``tts_batch`` for a stream of batches: ``depth`` batches are in flight together on
         ``depth`` execution contexts of ``model`` (same weights, own streams / workspaces), and each batch's
         waveforms are yielded in order.  The schedule is stage-aligned, per wave of ``depth`` batches:
