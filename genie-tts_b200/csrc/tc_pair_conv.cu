@@ -1,4 +1,4 @@
-// One HiFi-GAN resblock pair in ONE kernel for the narrow stages (C = 16 / 32 channels, sm_100a):
+// One HiFi-GAN resblock pair in ONE kernel (C = 16 / 32 / 64 channels, sm_100a):
 //
 //     y = conv2( lrelu( conv1( lrelu(x) ) + b1 ) ) + b2 + x  [+ running sum]
 //
@@ -14,16 +14,17 @@
 //      a second swizzled tile in shared memory (each thread owns one row: plain 16-byte stores);
 //   4. conv2 = k x 4 MMAs on that tile with row shifts 0..k-1 into the same TMEM columns;
 //   5. epilogue 2 (tc_epilogue.cuh): + b2 + residual (+ running sum), 16-byte coalesced stores.
-// The weights of one conv (k x C x C fp16, <= 22.5 KB) sit in shared memory whole; conv2's are fetched with
-// cp.async while epilogue 1 runs.
+// The weights of one conv (k x C x C fp16: <= 22.5 KB at C <= 32, up to 88 KB at C = 64) sit in shared memory
+// whole; conv2's are fetched with cp.async while epilogue 1 runs.  C = 64 (round 2) uses 256-row tiles (two
+// accumulators, SWIZZLE_128B rows) so that x tile + intermediate tile + 88 KB of weights fit one SM.
 #include "common.cuh"
 #include "tc_epilogue.cuh"
+#include <cstdlib>
 
 namespace genie {
 namespace {
 
 constexpr int NTHR = 256;
-constexpr int MT = 4, ROWS = MT * 128;
 constexpr int IPAD = 16;                                 // rows behind the intermediate tile that conv2's last taps touch
 
 struct PairGeom {
@@ -58,14 +59,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
 
-template <int C>
-__global__ void __launch_bounds__(NTHR, 2) tc_pair_conv_kernel(ConvGemm p, const __half* __restrict__ w1,
-                                                               const float* __restrict__ bias1, int kpad1, PairGeom g,
-                                                               int* err_flag) {
-  constexpr int ROWB = 2 * C;                          // bytes per fp16 row (32 / 64)
+template <int C, int MT>
+__global__ void __launch_bounds__(NTHR, C >= 64 ? 1 : 2) tc_pair_conv_kernel(ConvGemm p, const __half* __restrict__ w1,
+                                                                             const float* __restrict__ bias1, int kpad1,
+                                                                             PairGeom g, int* err_flag) {
+  constexpr int ROWS = MT * 128;
+  constexpr int ROWB = 2 * C;                          // bytes per fp16 row (32 / 64 / 128)
   constexpr int CH = ROWB / 16;
-  constexpr uint32_t SWMASK = ROWB == 64 ? 3u : 1u;    // Swizzle<2|1, 4, 3>
-  constexpr uint64_t LAYOUT = ROWB == 64 ? 4 : 6;      // SWIZZLE_64B / SWIZZLE_32B
+  constexpr uint32_t SWMASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;    // Swizzle<3|2|1, 4, 3>
+  constexpr uint64_t LAYOUT = ROWB == 128 ? 2 : ROWB == 64 ? 4 : 6;       // SWIZZLE_128B / 64B / 32B
+  constexpr int CW = C < 32 ? C : 32;                  // accumulator columns per tcgen05.ld chunk
   constexpr uint32_t SBO = 8 * ROWB;
   constexpr uint32_t UNIT = C * ROWB;                  // one tap of weights
   constexpr uint32_t TCOLS = MT * C < 32 ? 32 : MT * C;
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(NTHR, 2) tc_pair_conv_kernel(ConvGemm p, const
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ int s_to[ROWS];
-  __shared__ __align__(16) float s_b1[32], s_b2[32];
+  __shared__ __align__(16) float s_b1[64], s_b2[64];
 
   const int seg = blockIdx.z;
   int r0 = 0, Tseg = p.M;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(NTHR, 2) tc_pair_conv_kernel(ConvGemm p, const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int r = tid; r < ROWS; r += NTHR) s_to[r] = (r < g.T && q0 + r < Tseg) ? q0 + r : -1;
-  if (tid < 32) {
+  if (tid < 64) {
     s_b1[tid] = (tid < C && bias1) ? bias1[tid] : 0.f;
     s_b2[tid] = (tid < C && p.bias) ? p.bias[tid] : 0.f;
   }
@@ -186,25 +189,28 @@ __global__ void __launch_bounds__(NTHR, 2) tc_pair_conv_kernel(ConvGemm p, const
   {
     const int rq = (warp & 3) * 32;
     for (int mt = warp >> 2; mt < MT; mt += 2) {
-      uint32_t v[32];
-      tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)(mt * C), C >= 32, v);
       const int i = mt * 128 + rq + lane;
       const int t = q0 - g.p2 + i;
       const bool inside = (unsigned)t < (unsigned)Tseg;          // outside the utterance conv2 sees zero padding
 #pragma unroll
-      for (int c8 = 0; c8 < CH; ++c8) {
-        uint32_t pk[4];
+      for (int cc = 0; cc < C; cc += 32) {                       // 32 accumulator columns per tcgen05.ld
+        uint32_t v[32];
+        tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)(mt * C + cc), C >= 32, v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float a = __uint_as_float(v[c8 * 8 + 2 * e]) + s_b1[c8 * 8 + 2 * e];
-          float b = __uint_as_float(v[c8 * 8 + 2 * e + 1]) + s_b1[c8 * 8 + 2 * e + 1];
-          a = fmaxf(a, a * 0.1f); b = fmaxf(b, b * 0.1f);
-          const __half2 h = __floats2half2_rn(inside ? a : 0.f, inside ? b : 0.f);
-          pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int c8 = 0; c8 < CW / 8; ++c8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = __uint_as_float(v[c8 * 8 + 2 * e]) + s_b1[cc + c8 * 8 + 2 * e];
+            float b = __uint_as_float(v[c8 * 8 + 2 * e + 1]) + s_b1[cc + c8 * 8 + 2 * e + 1];
+            a = fmaxf(a, a * 0.1f); b = fmaxf(b, b * 0.1f);
+            const __half2 h = __floats2half2_rn(inside ? a : 0.f, inside ? b : 0.f);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          const uint32_t off = (uint32_t)(i * ROWB + cc * 2 + c8 * 16);
+          *reinterpret_cast<uint4*>(sbase + g.x_bytes + (off ^ (((off >> 7) & SWMASK) << 4))) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        const uint32_t off = (uint32_t)(i * ROWB + c8 * 16);
-        *reinterpret_cast<uint4*>(sbase + g.x_bytes + (off ^ (((off >> 7) & SWMASK) << 4))) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
     // the IPAD rows behind the tile are only read for accumulator rows that are never stored: keep them finite
@@ -233,10 +239,13 @@ __global__ void __launch_bounds__(NTHR, 2) tc_pair_conv_kernel(ConvGemm p, const
     const int rq = (warp & 3) * 32;
     for (int mt = warp >> 2; mt < MT; mt += 2) {
       if (mt * 128 >= g.T || q0 + mt * 128 >= Tseg) break;
-      uint32_t v[32];
-      tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)(mt * C), C >= 32, v);
-      if (C >= 32) tc_epi::store_chunk<32>(v, tile, s_b2, s_to + mt * 128 + rq, r0, 0, ea, lane);
-      else tc_epi::store_chunk<16>(v, tile, s_b2, s_to + mt * 128 + rq, r0, 0, ea, lane);
+#pragma unroll
+      for (int cc = 0; cc < C; cc += 32) {
+        uint32_t v[32];
+        tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)(mt * C + cc), C >= 32, v);
+        if (C >= 32) tc_epi::store_chunk<32>(v, tile, s_b2 + cc, s_to + mt * 128 + rq, r0, cc, ea, lane);
+        else tc_epi::store_chunk<16>(v, tile, s_b2, s_to + mt * 128 + rq, r0, 0, ea, lane);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -246,9 +255,10 @@ __global__ void __launch_bounds__(NTHR, 2) tc_pair_conv_kernel(ConvGemm p, const
   }
 }
 
-template <int C>
+template <int C, int MT>
 void launch_pair(const ConvGemm& p, const __half* w1, const float* bias1, int kpad1, int d1, int* err_flag,
                  cudaStream_t s) {
+  constexpr int ROWS = MT * 128;
   PairGeom g;
   g.k = p.ntaps; g.d1 = d1; g.p1 = d1 * (g.k - 1) / 2; g.p2 = (g.k - 1) / 2;
   g.T = ROWS - 2 * g.p2; g.R1 = ROWS + 2 * g.p1;
@@ -258,16 +268,20 @@ void launch_pair(const ConvGemm& p, const __half* w1, const float* bias1, int kp
   g.i_bytes = up((size_t)(ROWS + IPAD) * 2 * C);
   g.w_bytes = up((size_t)g.k * C * 2 * C);
   const size_t smem = (size_t)g.x_bytes + g.i_bytes + g.w_bytes + 1024;
+  GENIE_CHECK(smem <= 227 * 1024, "tc_pair_conv: tile does not fit shared memory");
   static DynSmemAttr attr;
-  attr.ensure(tc_pair_conv_kernel<C>, smem);
+  attr.ensure(tc_pair_conv_kernel<C, MT>, smem);
   dim3 grid((p.M + g.T - 1) / g.T, 1, p.B);
-  tc_pair_conv_kernel<C><<<grid, NTHR, smem, s>>>(p, w1, bias1, kpad1, g, err_flag);
+  tc_pair_conv_kernel<C, MT><<<grid, NTHR, smem, s>>>(p, w1, bias1, kpad1, g, err_flag);
   GENIE_LAUNCHED("tc_pair_conv");
 }
 
 }  // namespace
 
-bool tc_pair_conv_supported(int C, int k) { return (C == 16 || C == 32) && k >= 3 && k <= 11 && (k & 1); }
+bool tc_pair_conv_supported(int C, int k) {
+  static const bool c64 = [] { const char* e = getenv("GENIE_PAIR64"); return !(e && e[0] == '0'); }();
+  return (C == 16 || C == 32 || (C == 64 && c64)) && k >= 3 && k <= 11 && (k & 1);
+}
 
 // p describes conv2 (weights tc_w / tc_kpad, bias, res, y, accumulate, segments) with x = the PAIR's input and
 // pre_slope = its pre-activation; w1 / bias1 / d1 describe conv1
@@ -278,8 +292,9 @@ void launch_tc_pair_conv(const ConvGemm& p, const __half* w1, const float* bias1
               "tc_pair_conv: needs packed weights and segment offsets shared by input and output");
   GENIE_CHECK(p.pre_slope >= 0.f && p.pre_slope <= 1.f && IPAD >= p.ntaps - 1, "tc_pair_conv: bad activation / taps");
   if (p.M <= 0 || p.B <= 0) return;
-  if (p.Cin == 16) launch_pair<16>(p, w1, bias1, kpad1, d1, err_flag, s);
-  else launch_pair<32>(p, w1, bias1, kpad1, d1, err_flag, s);
+  if (p.Cin == 16) launch_pair<16, 4>(p, w1, bias1, kpad1, d1, err_flag, s);
+  else if (p.Cin == 32) launch_pair<32, 4>(p, w1, bias1, kpad1, d1, err_flag, s);
+  else launch_pair<64, 2>(p, w1, bias1, kpad1, d1, err_flag, s);
 }
 
 }  // namespace genie
