@@ -516,9 +516,10 @@ def main():
                          "peak_source": which, "bytes_per_launch": att_mb * 1e6, "avg_launch_us": att_us,
                          "launches_per_step": 24 * TOKENS, "share_of_step": att_share,
                          "bytes_per_launch_step_average": kv_mb_avg * 1e6,
-                         "timing": "replayed alone after the timed steps on the FINAL KV cache, 20 x 24 layers back "
-                                   "to back, CUDA events on the launching stream (inside the step it is a CUDA-graph "
-                                   "node); share_of_step scales that time to the step-average KV length",
+                         "timing": "replayed alone after the timed steps on the FINAL KV cache as ONE launch over all "
+                                   "utterances, 20 x 24 layers back to back, CUDA events on the launching stream (inside "
+                                   "the step it is a CUDA-graph node, issued as two half-batch launches on the two branch "
+                                   "streams); share_of_step scales that time to the step-average KV length",
                          "traffic": ATT_NCU["dram_bytes"],
                          "traffic_note": f"{ATT_NCU['file']}: dram read+write of one launch whose algorithmic bytes "
                                          f"are {ATT_NCU['algorithmic_bytes'] / 1e6:.1f} MB"},

@@ -319,9 +319,13 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t& b0, uint32_t& b1, const 
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
 }
 
-constexpr int MQ = 64, MK = 64, KLD = 40;             // tile sizes; padded smem leading dimension (halves)
+constexpr int MK = 64, KLD = 40;                      // key tile; padded smem leading dimension (halves)
 
-__global__ void __launch_bounds__(128) prefill_attention_mma_kernel(Attn p) {
+// NW warps x 16 query rows per CTA (128 rows at NW = 8: each K / V tile is loaded and split once per 128 queries);
+// the next key tile's fp32 rows are fetched into registers while the current one is multiplied.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) prefill_attention_mma_kernel(Attn p) {
+  constexpr int MQ = NW * 16, NT = NW * 32, LPT = MK * 8 / NT;   // float4 per thread and tile (K and V each)
   __shared__ __align__(16) __half Kh[MK][KLD], Kl[MK][KLD];     // [key][d], hi / lo
   __shared__ __align__(16) __half Vh[MK][KLD], Vl[MK][KLD];     // [key][d], hi / lo
   const int b = blockIdx.z, h = blockIdx.y;
@@ -360,22 +364,32 @@ __global__ void __launch_bounds__(128) prefill_attention_mma_kernel(Attn p) {
     const int last_q = min(q0 + MQ, Tq) - 1;
     k_end = (last_q < lx) ? lx : last_q + 1;           // text rows never see audio keys; audio rows are causal
   }
+  float4 kreg[LPT], vreg[LPT];
+  auto fetch = [&](int k0) {                           // raw fp32 rows of one key tile -> registers
+#pragma unroll
+    for (int u = 0; u < LPT; ++u) {
+      const int i = tid + u * NT, r = i >> 3, c4 = i & 7;
+      kreg[u] = make_float4(0.f, 0.f, 0.f, 0.f); vreg[u] = kreg[u];
+      if (k0 + r < Tk) {
+        kreg[u] = *reinterpret_cast<const float4*>(p.k + (long long)(ks + k0 + r) * p.ldk + h * 32 + c4 * 4);
+        vreg[u] = *reinterpret_cast<const float4*>(p.v + (long long)(ks + k0 + r) * p.ldv + h * 32 + c4 * 4);
+      }
+    }
+  };
+  if (k_end > 0) fetch(0);
   for (int k0 = 0; k0 < k_end; k0 += MK) {
     __syncthreads();                                   // previous tile fully consumed
-    for (int i = tid; i < MK * 8; i += 128) {          // K / V tile: fp32 -> fp16 hi / lo
-      const int r = i >> 3, c4 = i & 7;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (k0 + r < Tk) {
-        kv = *reinterpret_cast<const float4*>(p.k + (long long)(ks + k0 + r) * p.ldk + h * 32 + c4 * 4);
-        vv = *reinterpret_cast<const float4*>(p.v + (long long)(ks + k0 + r) * p.ldv + h * 32 + c4 * 4);
-      }
+#pragma unroll
+    for (int u = 0; u < LPT; ++u) {                    // K / V tile: fp32 -> fp16 hi / lo
+      const int i = tid + u * NT, r = i >> 3, c4 = i & 7;
       uint2 hi, lo;
-      split_h2(kv.x, kv.y, hi.x, lo.x); split_h2(kv.z, kv.w, hi.y, lo.y);
+      split_h2(kreg[u].x, kreg[u].y, hi.x, lo.x); split_h2(kreg[u].z, kreg[u].w, hi.y, lo.y);
       *reinterpret_cast<uint2*>(&Kh[r][c4 * 4]) = hi; *reinterpret_cast<uint2*>(&Kl[r][c4 * 4]) = lo;
-      split_h2(vv.x, vv.y, hi.x, lo.x); split_h2(vv.z, vv.w, hi.y, lo.y);
+      split_h2(vreg[u].x, vreg[u].y, hi.x, lo.x); split_h2(vreg[u].z, vreg[u].w, hi.y, lo.y);
       *reinterpret_cast<uint2*>(&Vh[r][c4 * 4]) = hi; *reinterpret_cast<uint2*>(&Vl[r][c4 * 4]) = lo;
     }
     __syncthreads();
+    if (k0 + MK < k_end) fetch(k0 + MK);               // in flight while this tile is multiplied
 
     // ---- S = Q K^T for this warp's 16 rows x 64 keys
     float sc[8][4];
@@ -971,7 +985,7 @@ void launch_attention(const Attn& p, cudaStream_t s) {
       ((reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.k) | reinterpret_cast<uintptr_t>(p.v)) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(p.o) & 7) == 0) {
     if (p.use_mma) {
-      prefill_attention_mma_kernel<<<dim3((p.max_q + MQ - 1) / MQ, p.H, p.B), 128, 0, s>>>(p);
+      prefill_attention_mma_kernel<8><<<dim3((p.max_q + 127) / 128, p.H, p.B), 256, 0, s>>>(p);
       GENIE_LAUNCHED("prefill_attention_mma");
       return;
     }
