@@ -34,7 +34,7 @@ def get_service() -> SynthesisService:
     global _service
     with _service_lock:
         if _service is None:
-            _service = SynthesisService(n_slots=int(os.getenv("GENIE_SLOTS", "128")),
+            _service = SynthesisService(n_slots=int(os.getenv("GENIE_SLOTS", "256")),
                                         kv_capacity=int(os.getenv("GENIE_KV_CAPACITY", "1024")))
         return _service
 

@@ -73,14 +73,18 @@ class RequestStream:
 
 
 class SynthesisService:
-    def __init__(self, devices: Optional[Sequence[int]] = None, n_slots: int = 128, kv_capacity: int = 1024,
-                 max_prompt_tokens: int = 512, max_steps: int = 500, sampling=None):
+    def __init__(self, devices: Optional[Sequence[int]] = None, n_slots: int = 256, kv_capacity: int = 1024,
+                 max_prompt_tokens: int = 512, max_steps: int = 500, sampling=None,
+                 contexts_per_gpu: Optional[int] = None):
         from . import _native as N
         N.require_gpu()
         if devices is None:
             env = os.getenv("GENIE_DEVICES")
             devices = [int(x) for x in env.split(",")] if env else list(range(N.lib().genie_device_count()))
         self.devices = list(devices)
+        # schedulers per GPU, each on its own execution context (own streams, slot pool and graphs; the weights are
+        # shared).  Measured on one B200, 256 closed-loop clients: 1714 / 1743 / 1556 audio-s/s for 1 / 2 / 3 - no gain, default 1
+        self.contexts_per_gpu = int(contexts_per_gpu or os.getenv("GENIE_CONTEXTS_PER_GPU", "1"))
         self.pool_cfg = dict(n_slots=n_slots, kv_capacity=kv_capacity, max_prompt_tokens=max_prompt_tokens,
                              max_steps=max_steps, sampling=sampling)
         self.managers: List[ModelManager] = [model_manager if d == model_manager.device else ModelManager(device=d)
@@ -138,8 +142,9 @@ class SynthesisService:
                         raise KeyError(f"character '{name}' is not loaded")
                     # the pool lives on its own context: the character's main handle stays free for the
                     # reference-facing batch-1 path (genie.tts) next to the server
-                    ctx = gsv.engine.create_context()
-                    bs.append(ContinuousBatcher(ctx, name=f"{key}@cuda{mgr.device}", **self.pool_cfg))
+                    for k in range(self.contexts_per_gpu):
+                        ctx = gsv.engine.create_context()
+                        bs.append(ContinuousBatcher(ctx, name=f"{key}@cuda{mgr.device}.{k}", **self.pool_cfg))
                 self._batchers[key] = bs
                 self._pools[key] = ReplicaPool(bs)
             return self._pools[key]
@@ -182,7 +187,7 @@ class SynthesisService:
     def stats(self) -> dict:
         out = {}
         for name, bs in self._batchers.items():
-            out[name] = [dict(b.stats.summary(), device=mgr.device) for b, mgr in zip(bs, self.managers)]
+            out[name] = [dict(b.stats.summary(), device=b.model.device) for b in bs]
         return out
 
     def close(self) -> None:

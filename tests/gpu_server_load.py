@@ -42,7 +42,7 @@ def serve(n_gpus: int) -> None:
         return seq, None
 
     set_text_frontend(frontend)
-    svc = SynthesisService(devices=list(range(n_gpus)), n_slots=128, kv_capacity=448, max_prompt_tokens=160,
+    svc = SynthesisService(devices=list(range(n_gpus)), n_slots=int(os.getenv("LOAD_SLOTS", "256")), kv_capacity=448, max_prompt_tokens=160,
                            max_steps=90, sampling=SamplingParams(max_steps=90, fixed_steps=90))
     Server.set_service(svc)
     svc.load_character("Mika", fixture_dir("v2", 0), "Japanese")
@@ -89,6 +89,8 @@ def main():
     ap.add_argument("--clients", type=int, default=512)
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--gpus", type=int, default=0)
+    ap.add_argument("--contexts", type=int, default=0, help="schedulers per GPU (0: the service's default)")
+    ap.add_argument("--slots", type=int, default=256)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "config5_load.json"))
     a = ap.parse_args()
     if a.serve:
@@ -96,6 +98,9 @@ def main():
         return
     from genie_tts import _native as N
     n_gpus = a.gpus or N.lib().genie_device_count()
+    if a.contexts:
+        os.environ["GENIE_CONTEXTS_PER_GPU"] = str(a.contexts)
+    os.environ["LOAD_SLOTS"] = str(a.slots)
     srv = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--serve", str(n_gpus)],
                            stdout=subprocess.DEVNULL, stderr=open(os.path.join(ROOT, "gpurun_out", "config5_server.err"), "w"))
     try:
@@ -108,7 +113,7 @@ def main():
                 if srv.poll() is not None:
                     raise RuntimeError("server process died, see gpurun_out/config5_server.err")
                 time.sleep(0.5)
-        asyncio.run(run_clients(min(64, a.clients), 1))                       # warm: every graph bucket, every replica
+        asyncio.run(run_clients(a.clients, 2))                                # warm: every graph bucket, every replica
         first, total, nbytes, wall, stats = asyncio.run(run_clients(a.clients, a.rounds))
     finally:
         srv.terminate()
@@ -118,7 +123,8 @@ def main():
             srv.kill()
     audio_s = sum(nbytes) / 2 / 32000.0
     res = {"config": "BASELINE configs[4]: FastAPI server, continuous batching, closed-loop synthetic clients",
-           "n_gpus": n_gpus, "clients": a.clients, "requests": len(first), "rounds_per_client": a.rounds,
+           "n_gpus": n_gpus, "contexts_per_gpu": len(next(iter(stats.values()))) // n_gpus, "slots": a.slots,
+           "clients": a.clients, "requests": len(first), "rounds_per_client": a.rounds,
            "sentence": "JA20 shape: 40-60 phonemes, 132 prompt tokens, 90-token budget, Philox sampling",
            "first_audio_ms_p50": float(np.percentile(first, 50)), "first_audio_ms_p99": float(np.percentile(first, 99)),
            "request_ms_p50": float(np.percentile(total, 50)), "request_ms_p99": float(np.percentile(total, 99)),
