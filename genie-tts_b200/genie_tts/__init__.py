@@ -13,6 +13,12 @@ def start_server(host: str = "127.0.0.1", port: int = 8000, workers: int = 1):
     return _s(host=host, port=port, workers=workers)
 
 
+def start_server_per_gpu(host: str = "127.0.0.1", base_port: int = 8000, devices=None, block: bool = True):
+    """Extension: one server process per GPU on consecutive ports (Server.start_server_per_gpu)."""
+    from .Server import start_server_per_gpu as _s
+    return _s(host=host, base_port=base_port, devices=devices, block=block)
+
+
 __all__ = ["load_character", "unload_character", "set_reference_audio", "tts_async", "tts", "stop",
-           "convert_to_onnx", "clear_reference_audio_cache", "start_server", "wait_for_playback_done",
+           "convert_to_onnx", "clear_reference_audio_cache", "start_server", "start_server_per_gpu", "wait_for_playback_done",
            "load_predefined_character", "download_genie_data", "set_reference_features"]
