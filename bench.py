@@ -292,7 +292,7 @@ def main():
     model = B200Model(model_dir, device=local_rank)
     if args.kv_fp32:
         model.set_option("kv_fp16", 0)
-    for opt in ("decode_branches", "decode_split_min"):        # experiments: GENIE_OPT_decode_branches=3 ...
+    for opt in ("decode_branches", "decode_split_min", "prefill_single"):        # experiments: GENIE_OPT_decode_branches=3 ...
         if os.environ.get("GENIE_OPT_" + opt):
             model.set_option(opt, int(os.environ["GENIE_OPT_" + opt]))
     pr, texts, berts = make_workload(cfg, args.sentences or cfg["sentences"], rank=rank)

@@ -117,7 +117,7 @@ int genie_context_create(genie_model* src, void* cuda_stream, genie_model** out)
     // options that select kernels travel with the clone
     h->m.use_graph = src->m.use_graph; h->m.use_tc = src->m.use_tc; h->m.tc_vits = src->m.tc_vits;
     h->m.tc_min_rows = src->m.tc_min_rows; h->m.skinny_max_rows = src->m.skinny_max_rows;
-    h->m.fuse_pairs = src->m.fuse_pairs; h->m.persistent_step = src->m.persistent_step; h->m.kv_fp16 = src->m.kv_fp16;
+    h->m.fuse_pairs = src->m.fuse_pairs; h->m.persistent_step = src->m.persistent_step; h->m.kv_fp16 = src->m.kv_fp16; h->m.prefill_single = src->m.prefill_single;
     h->m.decode_split_min = src->m.decode_split_min; h->m.decode_branches = src->m.decode_branches;
     init_exec_state(h->m, cuda_stream);
     h->m.tc_err = dev_alloc<int>(h->m.ctx_owned, 1);
@@ -400,7 +400,7 @@ int genie_set_option(genie_model* h, const char* key, int value) {
   const Opt opts[] = {{"use_graph", &m.use_graph, false}, {"time_attention", &m.time_attention, false},
                       {"persistent_step", &m.persistent_step, true}, {"use_tc", &m.use_tc, true},
                       {"tc_vits", &m.tc_vits, false}, {"fuse_pairs", &m.fuse_pairs, false},
-                      {"kv_fp16", &m.kv_fp16, false},
+                      {"kv_fp16", &m.kv_fp16, false}, {"prefill_single", &m.prefill_single, false},
                       {"decode_split_min", &m.decode_split_min, true}, {"decode_branches", &m.decode_branches, true},
                       {"skinny_max_rows", &m.skinny_max_rows, true}, {"tc_min_rows", &m.tc_min_rows, true}};
   if (std::strcmp(key, "sm_partition") == 0) {

@@ -168,6 +168,8 @@ struct Model : ModelWeights {
   // tc_vits: 1 = x_hi . w_hi, 2 = (x_hi+x_lo) . w_hi, 3 = (x_hi+x_lo) . w_hi + x_hi . w_lo
   int use_tc = 1, tc_vits = 1, tc_min_rows = 9, skinny_max_rows = 8;
   int fuse_pairs = 1;                  // narrow resblock pairs as one kernel (tc_pair_conv.cu)
+  int prefill_single = 0;              // experiment: prefill linears as ONE fp16 product (activations rounded to fp16)
+  int lin_single_now = 0;              // set around the prefill layer loop when prefill_single is on
   int kv_fp16 = 1;                     // KV cache rows stored as fp16 (q, scores, accumulators fp32); 0 = fp32 rows
   int* tc_err = nullptr;               // device flag: 1 = tcgen05 mbarrier timeout, 2 = input id out of range
   unsigned* step_sync = nullptr;       // persistent step: [0] barrier counter, [1] barrier-timeout flag

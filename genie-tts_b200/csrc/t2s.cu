@@ -308,7 +308,7 @@ void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* p
   // the same bytes viewed as two fp16 matrices [R, 2048] (hi | lo) when the FFN pair hands over in fp16
   __half* FF16 = reinterpret_cast<__half*>(FF);
   static const bool ffn16_env = [] { const char* e = getenv("GENIE_FFN16"); return !(e && e[0] == '0'); }();
-  const bool ffn16 = ffn16_env && m.use_tc && R >= m.tc_min_rows && R > m.skinny_max_rows && m.layers[0].ff1.tc.hi &&
+  const bool ffn16 = ffn16_env && !m.prefill_single && m.use_tc && R >= m.tc_min_rows && R > m.skinny_max_rows && m.layers[0].ff1.tc.hi &&
                      m.layers[0].ff2.tc.hi && !m.layers[0].ff2.tc.lo;
   float* XT = any_bert ? ws.get<float>("t2s.xtext", (size_t)txt_rows * D) : nullptr;
   float* BERT = any_bert ? ws.get<float>("t2s.bert", (size_t)txt_rows * 1024) : nullptr;
@@ -391,6 +391,7 @@ void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* p
   const float scale = 1.0f / std::sqrt(32.0f);
   static const bool prefill_mma = [] { const char* e = getenv("GENIE_PREFILL_MMA"); return !(e && e[0] == '0'); }();
   float* Hcur = X;
+  m.lin_single_now = m.prefill_single;
   for (int l = 0; l < NL; ++l) {
     const T2SLayer& L = m.layers[l];
     run_linear(m, L.qkv, Hcur, D, QKV, 3 * D, R);
@@ -424,6 +425,7 @@ void admit(Model& m, T2SSession& S, int n, const int* slots_in, Prompt* const* p
   }
   // logits for the last row of each utterance (first_stage#[1785-1788]) and the first sampled token (#[1789-1820];
   // the first-stage graph has no stop output)
+  m.lin_single_now = 0;
   launch_gather_rows(LAST, D, X, D, LASTIDX, n, 1, s);
   run_linear(m, m.predict, LAST, D, LOGITS_PRE, V, n);
   S.LOGITS_PRE = LOGITS_PRE;

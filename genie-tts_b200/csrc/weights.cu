@@ -375,7 +375,7 @@ void run_linear(Model& m, const Linear& L, const float* x, int ldx, float* y, in
   }
   if (m.use_tc && L.tc.hi && M >= m.tc_min_rows) {
     // fp16-exact weights: (x_hi + x_lo) . w keeps the fp32 graphs' token parity
-    p.tc_w = L.tc.hi; p.tc_wlo = L.tc.lo; p.tc_kpad = L.tc.kpad; p.tc_split_a = 1;
+    p.tc_w = L.tc.hi; p.tc_wlo = L.tc.lo; p.tc_kpad = L.tc.kpad; p.tc_split_a = m.lin_single_now ? 0 : 1;
     p.tc_nt = nt; p.ksplit = ksplit; p.split_stride = split_stride;
     if (a16) { p.x16 = a16->hi; p.x16_lo = a16->lo; }
     if (y16) { p.y16 = y16->hi; p.y16_lo = y16->lo; }

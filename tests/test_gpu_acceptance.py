@@ -26,7 +26,11 @@ MIN_MATCH = 0.99
 def _load_model(version, seed):
     from conftest import fixture_dir
     from genie_tts.engine import B200Model
-    return B200Model(fixture_dir(version, seed))
+    m = B200Model(fixture_dir(version, seed))
+    for kv in filter(None, os.environ.get("GENIE_TEST_OPTS", "").split(",")):    # experiments: "prefill_single=1,..."
+        k, v = kv.split("=")
+        m.set_option(k, int(v))
+    return m
 
 
 def _prompt(m, pr):
