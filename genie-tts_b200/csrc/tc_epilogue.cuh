@@ -26,9 +26,12 @@ struct Args {
   __half* y16 = nullptr; int ldy16 = 0;             // fp16 output instead of y (no residual / accumulate): the
                                                     // consumer conv reads it as its ready-made A operand
   __half* y16_lo = nullptr;                         // + fp16(v - fp16(v)) for the hi/lo-split consumers
+  // residual rows already staged in shared memory (tc_halo_pipe_kernel): the chunk's 32 rows x 32 columns start at
+  // res_s, rows res_s_ld floats apart; replaces the global loads of `res`
+  const float* res_s = nullptr; int res_s_ld = 0;
 };
 
-__device__ __forceinline__ bool vec_ok(const float* y, int ldy, const float* res, int ldr, int Cout) {
+__host__ __device__ __forceinline__ bool vec_ok(const float* y, int ldy, const float* res, int ldr, int Cout) {
   return ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res)) & 15) == 0 && (ldy & 3) == 0 &&
          (ldr & 3) == 0 && (Cout & 3) == 0;
 }
@@ -92,7 +95,10 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
     for (int i = 0; i < NP; ++i) {
       to[i] = cok ? rows[i * RPP + rsub] : -1;
       add[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (to[i] >= 0 && a.res) add[i] = __ldg(reinterpret_cast<const float4*>(a.res + (out0 + to[i]) * a.ldr + n));
+      if (to[i] >= 0 && a.res_s)
+        add[i] = *reinterpret_cast<const float4*>(a.res_s + (i * RPP + rsub) * a.res_s_ld + c4 * 4);
+      else if (to[i] >= 0 && a.res)
+        add[i] = __ldg(reinterpret_cast<const float4*>(a.res + (out0 + to[i]) * a.ldr + n));
     }
     if (a.acc) {
 #pragma unroll

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "tc_epilogue.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace genie {
@@ -519,6 +520,370 @@ __global__ void __launch_bounds__(BTHR, 2) tc_halo_bulk_kernel(ConvGemm p, HaloG
   }
 }
 
+// ---------------------------------------------------------------------------
+// Round 2: the same operands as tc_halo_bulk_kernel in a PERSISTENT, role-split CTA - one per SM.
+//
+// What bounds the one-tile kernel above (ncu, C = 128 k = 3: 2.4 TB/s read, tensor pipe 10 % active): every global
+// load sits in a register until it is converted, so the bytes in flight per SM are threads x 8 x 16 B = 32-64 KB,
+// and each CTA is a chain of latencies (stage the halo -> MMAs -> residual loads -> stores).  Here:
+//   warps 0-3  loaders: halo tile of tile i+1 into the second A buffer while tile i is multiplied - fp32 rows
+//              with 24 x 16 B per thread in flight (one CTA per SM leaves the registers for it), fp16 rows with
+//              cp.async straight into the swizzled tile; they also PREFETCH the residual rows of the tile with
+//              cp.async.bulk (one 256-byte row segment per thread and column half, mbarrier complete_tx) so that
+//              the epilogue never waits on a global load
+//   warp  8    one thread streams the pre-tiled weights (cp.async.bulk ring, running ahead across tile
+//              boundaries) and issues the MMAs of tile i into TMEM accumulator i & 1; its loop carries slots,
+//              phases and descriptor words incrementally (no division between two tcgen05.mma)
+//   warps 4-7  epilogue: drain accumulator (i-1) & 1 while tile i is multiplied; residual from shared memory
+// All waits are bounded mbarrier polls (err_flag on timeout).
+// ---------------------------------------------------------------------------
+constexpr int PLD = 128;                            // loader threads (warps 0-3); epilogue threads = warps 4-7
+constexpr uint32_t RES_HALF = 128 * 64 * 4;         // residual staging: 128 rows x 64 columns fp32 per half
+
+struct PipeTile { int seg, q0, ny, in0, Tin, out0, Tout, nq; };
+
+__device__ __forceinline__ bool pipe_tile(const ConvGemm& p, int t, int TX, int NY, PipeTile& o) {
+  o.ny = t % NY;
+  const int r = t / NY;
+  o.seg = r / TX;
+  o.q0 = (r - o.seg * TX) * 128;
+  o.in0 = 0; o.Tin = p.M; o.out0 = 0; o.Tout = p.M_out;
+  if (p.in_off) { o.in0 = __ldg(p.in_off + o.seg); o.Tin = __ldg(p.in_off + o.seg + 1) - o.in0; }
+  if (p.out_off) { o.out0 = __ldg(p.out_off + o.seg); o.Tout = __ldg(p.out_off + o.seg + 1) - o.out0; }
+  o.nq = o.Tin + p.q_extra;
+  return o.q0 < o.nq;
+}
+
+struct PipeCfg { int TX, total, nslot, nA, use_res; };
+
+// PUNR: 16-byte loads in flight per loader thread (fp32 rows); MINB: CTAs per SM the registers are budgeted for
+template <int PUNR, int MINB>
+__global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, HaloGeom g, PipeCfg cfg, int* err_flag) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT], a_ready[2], a_free[2], acc_ready[2], acc_free[2],
+      res_ready[2], res_free[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_to[2][128];
+  __shared__ __align__(16) float s_bias[2][BNT];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NY = p.Cout / BNT;
+  const int TX = cfg.TX, total = cfg.total, nslot = cfg.nslot, nA = cfg.nA;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_bytes = (uint32_t)g.slabs * g.slab_bytes;
+  const uint32_t sA = base;
+  const uint32_t oW = a_bytes * (uint32_t)nA;
+  const uint32_t sW = base + oW;
+  const uint32_t oR = oW + (uint32_t)nslot * BTILE;                 // residual staging (2 halves) when cfg.use_res
+  const uint32_t oE = oR + (cfg.use_res ? 2 * RES_HALF : 0u);       // epilogue transpose tiles: 4 warps
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)(2 * BNT)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_ready[i], PLD); mbar_init(&a_free[i], 1);
+      mbar_init(&acc_ready[i], 1); mbar_init(&acc_free[i], 128);
+      mbar_init(&res_ready[i], 1); mbar_init(&res_free[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+
+  if (warp == 8) {
+    // ===== weight producer + MMA issuer: one thread
+    if (lane == 0) {
+      const uint8_t* tiles = reinterpret_cast<const uint8_t*>(p.tc_tiles);
+      // prefetch cursor: runs up to nslot units ahead of the MMAs, across tile boundaries
+      PipeTile pt;
+      int ptile = (int)blockIdx.x - (int)gridDim.x, pu = 0;
+      bool pvalid = false;
+      auto padvance = [&]() {
+        for (ptile += (int)gridDim.x; ptile < total; ptile += (int)gridDim.x)
+          if (pipe_tile(p, ptile, TX, NY, pt)) return true;
+        return false;
+      };
+      pvalid = padvance();
+      const uint8_t* psrc = tiles + (size_t)pt.ny * g.NU * BTILE;
+      auto fetch_into = [&](int slot) {
+        mbar_expect_tx(&full[slot], BTILE);
+        bulk_g2s(sW + (uint32_t)slot * BTILE, psrc, BTILE, &full[slot]);
+        psrc += BTILE;
+        if (++pu == g.NU) { pu = 0; pvalid = padvance(); psrc = tiles + (size_t)pt.ny * g.NU * BTILE; }
+      };
+      for (int k = 0; k < nslot && pvalid; ++k) fetch_into(k);
+
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BNT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t desc_hi32 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);      // SBO, version, SWIZZLE_128B
+      const uint32_t lbo16 = 1u << 16;
+      const uint32_t a_lo0 = ((sA & 0x3FFFFu) >> 4) + (uint32_t)((p.in_shift0 - g.lo) * 8) + lbo16;
+      const uint32_t a_tap_step = (uint32_t)(p.in_shift_step * 8), a_slab_step = g.slab_bytes >> 4;
+      const uint32_t w_lo0 = ((sW & 0x3FFFFu) >> 4) + lbo16;
+      int slot = 0, prev_slot = 0;
+      uint32_t ring_phase = 0, prev_phase = 0;
+      bool first_unit = true;
+      int i = 0, ab = 0;
+      uint32_t a_phase = 0;                          // parity of the current use of A buffer ab
+      PipeTile tl;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        if (!pipe_tile(p, t, TX, NY, tl)) continue;
+        const int b = i & 1;
+        if (i >= 2) ok = mbar_wait(&acc_free[b], (uint32_t)(((i >> 1) - 1) & 1)) && ok;   // tile i-2 has left TMEM
+        ok = mbar_wait(&a_ready[ab], a_phase) && ok;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem + (uint32_t)(b * BNT);
+        uint32_t a_tap = a_lo0 + (uint32_t)ab * (a_bytes >> 4);
+        int sl = 0;
+        for (int u = 0; u < g.NU; ++u) {
+          ok = mbar_wait(&full[slot], ring_phase) && ok;
+          const uint32_t a_lo = a_tap + (uint32_t)sl * a_slab_step;
+          const uint32_t w_lo = w_lo0 + (uint32_t)slot * (BTILE >> 4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            umma_f16(acc, ((uint64_t)desc_hi32 << 32) | (uint64_t)(a_lo + j * 2),
+                     ((uint64_t)desc_hi32 << 32) | (uint64_t)(w_lo + j * 2), idesc, (uint32_t)((u | j) != 0));
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                       ::"r"(smem_u32(&empty[slot])) : "memory");
+          // refill the slot of the PREVIOUS unit (its MMAs finish while this unit's run)
+          if (!first_unit && pvalid) {
+            ok = mbar_wait(&empty[prev_slot], prev_phase) && ok;
+            fetch_into(prev_slot);
+          }
+          first_unit = false;
+          prev_slot = slot; prev_phase = ring_phase;
+          if (++slot == nslot) { slot = 0; ring_phase ^= 1u; }
+          if (++sl == g.slabs) { sl = 0; a_tap += a_tap_step; }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     ::"r"(smem_u32(&acc_ready[b])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     ::"r"(smem_u32(&a_free[ab])) : "memory");
+        ++i;
+        if (++ab == nA) { ab = 0; a_phase ^= 1u; }
+      }
+      if (!ok && err_flag) atomicExch(err_flag, 1);
+    }
+  } else if (warp < 4) {
+    // ===== loaders
+    PipeTile tl;
+    int i = 0, ab = 0;
+    uint32_t a_phase = 0;
+    const bool h16 = p.x16 != nullptr;
+    const int cpr = h16 ? (p.Cin >> 3) : (p.Cin >> 2);            // 16-byte chunks per input row
+    const int rstep = PLD / cpr, fstep = PLD % cpr;
+    const int rr0 = tid / cpr, f0 = tid - rr0 * cpr;
+    const float pre = p.pre_slope;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      if (!pipe_tile(p, t, TX, NY, tl)) continue;
+      const int tbase = tl.q0 + g.lo;
+      uint8_t* abuf = sbase + (uint32_t)ab * a_bytes;
+      if (i >= nA) {                                             // the MMAs of tile i - nA have released the buffer
+        ok = mbar_wait(&a_free[ab], a_phase ^ 1u) && ok;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      if (h16) {
+        const __half* __restrict__ xh = p.x16 + (long long)tl.in0 * p.Cin;
+        const uint32_t abuf_u32 = sA + (uint32_t)ab * a_bytes;
+        int rr = rr0, f = f0;
+        while (rr < g.R) {
+          const int tt = tbase + rr, c = f * 8;
+          const uint32_t off = (uint32_t)(rr * 128 + (c & 63) * 2);
+          const bool in = (unsigned)tt < (unsigned)tl.Tin;
+          cp_async16(abuf_u32 + (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4)),
+                     in ? (const void*)(xh + (long long)tt * p.Cin + c) : (const void*)xh, in ? 16 : 0);
+          f += fstep; rr += rstep;
+          if (f >= cpr) { f -= cpr; ++rr; }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+      } else {
+        const float* __restrict__ xg = p.x + (long long)tl.in0 * p.ldx;
+        int rr = rr0, f = f0;
+        while (rr < g.R) {
+          float4 v[PUNR];
+          const int rs = rr, fs = f;
+#pragma unroll
+          for (int k = 0; k < PUNR; ++k) {
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int tt = tbase + rr;
+            if (rr < g.R && (unsigned)tt < (unsigned)tl.Tin)
+              v[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)tt * p.ldx + f * 4));
+            f += fstep; rr += rstep;
+            if (f >= cpr) { f -= cpr; ++rr; }
+          }
+          int r2 = rs, f2 = fs;
+#pragma unroll
+          for (int k = 0; k < PUNR; ++k) {
+            if (r2 < g.R) {
+              const int c = f2 * 4;
+              const uint32_t off = (uint32_t)(r2 * 128 + (c & 63) * 2);
+              float4 a = v[k];
+              a.x = fmaxf(a.x, a.x * pre); a.y = fmaxf(a.y, a.y * pre);
+              a.z = fmaxf(a.z, a.z * pre); a.w = fmaxf(a.w, a.w * pre);
+              const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+              pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(abuf + (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4))) = pk;
+            }
+            f2 += fstep; r2 += rstep;
+            if (f2 >= cpr) { f2 -= cpr; ++r2; }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+      mbar_arrive(&a_ready[ab]);
+      if (cfg.use_res) {
+        // residual rows of this tile -> staging halves (thread = row); the epilogue of tile i-1 must have left them
+        const int q = tl.q0 + tid;
+        const int lim = tl.nq < tl.Tout ? tl.nq : tl.Tout;
+        const bool rv = q < lim;
+        int nv = lim - tl.q0;
+        nv = nv < 0 ? 0 : (nv > 128 ? 128 : nv);
+        const float* rsrc = p.res + (long long)(tl.out0 + q) * p.ldr + tl.ny * BNT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (i >= 1) ok = mbar_wait(&res_free[h], (uint32_t)((i - 1) & 1)) && ok;
+          if (tid == 0) mbar_expect_tx(&res_ready[h], (uint32_t)nv * 256u);
+          if (rv) bulk_g2s(base + oR + (uint32_t)h * RES_HALF + (uint32_t)tid * 256u, rsrc + h * 64, 256u, &res_ready[h]);
+        }
+      }
+      ++i;
+      if (++ab == nA) { ab = 0; a_phase ^= 1u; }
+    }
+    if (!ok && err_flag) atomicExch(err_flag, 1);
+  } else {
+    // ===== epilogue warps 4-7: TMEM lanes (warp - 4) * 32 ..., accumulator i & 1
+    const int ew = warp - 4, etid = tid - PLD;
+    const int rq = ew * 32;
+    tc_epi::Args ea;
+    ea.y = p.y; ea.res = p.res; ea.acc = p.accumulate ? p.y : nullptr;
+    ea.ldy = p.ldy; ea.ldr = p.ldr;
+    ea.act = p.act; ea.slope = p.act == ACT_RELU ? 0.f : p.act_slope; ea.oscale = p.out_scale;
+    ea.Cout = p.Cout;
+    ea.vec = tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout);
+    ea.y16 = p.y16; ea.ldy16 = p.Cout;
+    float* tile = reinterpret_cast<float*>(sbase + oE) + ew * tc_epi::TILE_FLOATS;
+    const float* rstage = reinterpret_cast<const float*>(sbase + oR);
+    PipeTile tl;
+    int i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      if (!pipe_tile(p, t, TX, NY, tl)) continue;
+      const int b = i & 1;
+      const int n0 = tl.ny * BNT;
+      {
+        const int q = tl.q0 + etid;
+        const int to = q * p.out_mul + p.out_add;
+        s_to[b][etid] = (q < tl.nq && to >= 0 && to < tl.Tout) ? to : -1;
+        float bsum = 0.f;
+        const int n = n0 + etid;
+        if (n < p.Cout) {
+          if (p.bias) bsum += p.bias[n];
+          if (p.bias2) bsum += p.bias2[(long long)tl.seg * p.ldb2 + n];
+        }
+        s_bias[b][etid] = bsum;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+      const bool got = mbar_wait(&acc_ready[b], (uint32_t)((i >> 1) & 1));
+      ok = got && ok;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        bool rgot = true;
+        if (cfg.use_res) { rgot = mbar_wait(&res_ready[h], (uint32_t)(i & 1)); ok = rgot && ok; }
+#pragma unroll 1
+        for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 32) {
+          uint32_t v[32];
+          tc_epi::tmem_load_chunk(tmem + ((uint32_t)rq << 16) + (uint32_t)(b * BNT + c0), true, v);
+          if (c0 + 32 >= BNT) {                             // accumulator b is in registers: hand it back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_free[b]);
+          }
+          if (cfg.use_res) { ea.res_s = rstage + h * (RES_HALF / 4) + rq * 64 + (c0 - h * 64); ea.res_s_ld = 64; }
+          if (got && rgot) tc_epi::store_chunk<32>(v, tile, s_bias[b] + c0, s_to[b] + rq, tl.out0, n0 + c0, ea, lane);
+        }
+        if (cfg.use_res) mbar_arrive(&res_free[h]);
+      }
+      ++i;
+    }
+    if (!ok && err_flag) atomicExch(err_flag, 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * BNT)));
+  }
+}
+
+int halo_pipe_mode() {
+  static int mode = [] { const char* e = getenv("GENIE_HALO_PIPE"); return e ? atoi(e) : 1; }();
+  return mode;
+}
+
+int device_sm_count() {
+  static int cached[16] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+// persistent pipelined form; false = the operands do not fit (caller falls back to the one-tile kernel).
+// GENIE_HALO_PIPE: 0 off, 1 (default) two CTAs per SM (single A buffer, residual from global memory: the SIMT loader /
+// epilogue work needs the warps of two CTAs), 4 one fat CTA per SM (double A buffer, staged residual; +2: no staging)
+bool launch_halo_pipe(const ConvGemm& p, const HaloGeom& g, int* err_flag, cudaStream_t s) {
+  constexpr size_t EPI4 = 4 * tc_epi::TILE_FLOATS * 4;
+  const int mode = halo_pipe_mode();
+  const bool fat = (mode & 4) != 0;
+  const size_t budget = fat ? 220 * 1024 : 109 * 1024;
+  const size_t a_bytes = (size_t)g.slabs * g.slab_bytes;
+  PipeCfg cfg{};
+  cfg.use_res = (fat && p.res && !p.y16 && p.out_mul == 1 && p.out_add == 0 && p.q_extra == 0 && (p.ldr & 3) == 0 &&
+                 (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout) &&
+                 !(mode & 2)) ? 1 : 0;
+  const size_t fixed = EPI4 + 1024 + (cfg.use_res ? 2 * RES_HALF : 0);
+  static const int tries_fat[][2] = {{2, 4}, {2, 3}, {2, 2}, {1, 4}, {1, 3}, {1, 2}};
+  static const int tries_two[][2] = {{1, 4}, {1, 3}, {1, 2}};
+  for (int k = 0; k < (fat ? 6 : 3); ++k) {
+    const int* tr = fat ? tries_fat[k] : tries_two[k];
+    if ((size_t)tr[0] * a_bytes + (size_t)tr[1] * BTILE + fixed <= budget) { cfg.nA = tr[0]; cfg.nslot = tr[1]; break; }
+  }
+  if (cfg.nA == 0) return false;
+  const size_t smem = (size_t)cfg.nA * a_bytes + (size_t)cfg.nslot * BTILE + fixed;
+  const int nq = p.M + p.q_extra;
+  const int NY = p.Cout / BNT;
+  cfg.TX = (nq + 127) / 128;
+  const long long total = (long long)cfg.TX * NY * p.B;
+  if (total <= 0 || total > 0x3fffffff) return false;
+  cfg.total = (int)total;
+  const int grid = (int)std::min<long long>(total, (long long)device_sm_count() * (fat ? 1 : 2));
+  if (fat) {
+    static DynSmemAttr attr;
+    attr.ensure(tc_halo_pipe_kernel<24, 1>, smem);
+    tc_halo_pipe_kernel<24, 1><<<grid, BTHR, smem, s>>>(p, g, cfg, err_flag);
+  } else {
+    static DynSmemAttr attr;
+    attr.ensure(tc_halo_pipe_kernel<8, 2>, smem);
+    tc_halo_pipe_kernel<8, 2><<<grid, BTHR, smem, s>>>(p, g, cfg, err_flag);
+  }
+  GENIE_LAUNCHED("tc_halo_pipe");
+  return true;
+}
+
 bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   HaloGeom g;
   const int s_first = p.in_shift0, s_last = p.in_shift0 + (p.ntaps - 1) * p.in_shift_step;
@@ -529,6 +894,7 @@ bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t 
   g.slab_bytes = (uint32_t)(((size_t)g.R * 128 + 1023) / 1024 * 1024);
   g.NU = p.ntaps * g.slabs;
   g.U = 1; g.NI = g.NU; g.slot_bytes = BTILE; g.flags = flags;
+  if (halo_pipe_mode() && launch_halo_pipe(p, g, err_flag, s)) return true;
   size_t smem = (size_t)g.slabs * g.slab_bytes + (size_t)NSLOT * BTILE;
   if (smem < EPI_BYTES) smem = EPI_BYTES;
   smem += 1024;
