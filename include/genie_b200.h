@@ -211,8 +211,11 @@ int genie_last_timing(genie_model* m, float* ms, int n);
  * in the reference graphs; takes effect at the next prefill / pool_create),
  * use_graph (CUDA-graph replay of the decode step, default 1), use_tc / tc_vits (tensor-core paths),
  * skinny_max_rows, tc_min_rows, decode_split_min (path selection, debugging),
- * time_attention (n > 0: after the next t2s_generate replay the decode attention n x 24 times between events).
- * Environment: GENIE_TC_HALO=-1 disables the halo conv kernel, GENIE_PDL=0 programmatic dependent launch,
+ * time_attention (n > 0: after the next t2s_generate replay the decode attention n x 24 times between events),
+ * prefill_single (experiment, default 0: 1 = prefill linears as ONE fp16 product; measured 94 / 100 on the
+ * acceptance set, so it is off), persistent_step, decode_branches, fuse_pairs, sm_partition (debugging / studies).
+ * Environment: GENIE_TC_HALO=-1 disables the halo conv kernel, GENIE_HALO_PIPE=0 the persistent role-split form of
+ * its Cin = 128 variant (4 = one CTA per SM with staged residual), GENIE_PDL=0 programmatic dependent launch,
  * GENIE_SYNC_DEBUG=1 synchronises after every launch and names the failing kernel. */
 int genie_set_option(genie_model* m, const char* key, int value);
 
