@@ -214,7 +214,10 @@ def test_tc_selftest_shapes():
     for (M, Cin, Cout, nt, dil) in [(300, 64, 64, 1, 1), (1000, 256, 256, 3, 3), (777, 192, 384, 5, 1),
                                     (2000, 32, 32, 11, 5), (2000, 16, 16, 7, 3), (640, 24, 24, 11, 1),
                                     (333, 192, 768, 3, 1), (500, 128, 128, 7, 5), (260, 2048, 512, 1, 1),
-                                    (500, 48, 48, 7, 3), (500, 96, 96, 3, 5), (700, 24, 24, 7, 5), (400, 96, 96, 11, 1)]:
+                                    (500, 48, 48, 7, 3), (500, 96, 96, 3, 5), (700, 24, 24, 7, 5), (400, 96, 96, 11, 1),
+                                    # persistent role-split kernel (Cin = 128): several row tiles per CTA (weight ring
+                                    # and both TMEM accumulators wrap), 2-slot ring (k = 11, d = 5), one-row tail tile
+                                    (80000, 128, 128, 3, 1), (60000, 128, 128, 11, 5), (129, 128, 128, 3, 1)]:
         for mode, exact, tol in ((1, 0, 2e-2), (2, 1, 6e-5), (3, 0, 6e-5)):
             e, r = C.c_float(0), C.c_float(0)
             N.check(L.genie_debug_tc_selftest(M, Cin, Cout, nt, dil, mode, exact, C.byref(e), C.byref(r)))
