@@ -877,8 +877,8 @@ bool launch_halo_pipe(const ConvGemm& p, const HaloGeom& g, int* err_flag, cudaS
     tc_halo_pipe_kernel<24, 1><<<grid, BTHR, smem, s>>>(p, g, cfg, err_flag);
   } else {
     static DynSmemAttr attr;
-    attr.ensure(tc_halo_pipe_kernel<12, 2>, smem);
-    tc_halo_pipe_kernel<12, 2><<<grid, BTHR, smem, s>>>(p, g, cfg, err_flag);
+    attr.ensure(tc_halo_pipe_kernel<8, 2>, smem);
+    tc_halo_pipe_kernel<8, 2><<<grid, BTHR, smem, s>>>(p, g, cfg, err_flag);
   }
   GENIE_LAUNCHED("tc_halo_pipe");
   return true;
