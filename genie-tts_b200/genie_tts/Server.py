@@ -193,6 +193,7 @@ def start_server_per_gpu(host: str = "127.0.0.1", base_port: int = 8000, devices
     per process: send /load_character and /set_reference_audio to every port."""
     import multiprocessing as mp
     from . import _native as N
+    N.require_gpu()
     if devices is None:
         devices = list(range(N.lib().genie_device_count()))
     ctx = mp.get_context("spawn")

@@ -154,6 +154,11 @@ def test_public_api_surface_and_errors(tmp_path):
                  "convert_to_onnx", "clear_reference_audio_cache", "start_server", "wait_for_playback_done",
                  "load_predefined_character", "download_genie_data"]:           # reference __init__.py:16-29
         assert callable(getattr(genie, name))
+    assert callable(genie.start_server_per_gpu)                                  # extension: one server process per GPU
+    from genie_tts import _native as N
+    if N.lib().genie_device_count() == 0:
+        with pytest.raises(Exception):
+            genie.start_server_per_gpu(block=False)                              # fails loudly without a GPU
     with pytest.raises(FileNotFoundError):
         genie.load_character("x", str(tmp_path / "nope"), "ja")
     (tmp_path / "empty").mkdir()
