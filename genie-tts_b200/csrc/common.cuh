@@ -151,6 +151,7 @@ bool tc_pair_conv_supported(int C, int k);
 void launch_tc_pair_conv(const ConvGemm& conv2, const __half* w1, const float* bias1, int kpad1, int d1, int* err_flag,
                          cudaStream_t s);
 bool pretile_w128_supported(int Cin, int Cout, int ntaps);
+long long pretile_w128_halves(int Cin, int Cout, int ntaps);   // size of the pre-tiled copy (last N tile zero padded)
 void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s);
 bool skinny_gemm_supported(const ConvGemm& p);
 void launch_skinny_gemm(const ConvGemm& p, cudaStream_t s);

@@ -324,13 +324,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 __global__ void pretile_w128_kernel(const __half* __restrict__ hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles) {
   const int slabs = Cin / 64;
-  const long long total = (long long)(Cout / BNT) * ntaps * slabs * BNT * 8;     // 16-byte chunks
+  const long long total = (long long)((Cout + BNT - 1) / BNT) * ntaps * slabs * BNT * 8;     // 16-byte chunks
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c8 = (int)(i & 7), n = (int)((i >> 3) % BNT);
   const long long unit = i / (BNT * 8);
   const int sl = (int)(unit % slabs), tap = (int)((unit / slabs) % ntaps), nt = (int)(unit / ((long long)slabs * ntaps));
-  const uint4 v = *reinterpret_cast<const uint4*>(hi + (long long)(nt * BNT + n) * kpad + tap * Cin + sl * 64 + c8 * 8);
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);                                    // rows past Cout: zero (last N tile padded)
+  if (nt * BNT + n < Cout)
+    v = *reinterpret_cast<const uint4*>(hi + (long long)(nt * BNT + n) * kpad + tap * Cin + sl * 64 + c8 * 8);
   const uint32_t off = (uint32_t)(n * 128 + c8 * 16);
   *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tiles) + unit * BTILE + (off ^ (((off >> 7) & 7u) << 4))) = v;
 }
@@ -554,7 +556,9 @@ __device__ __forceinline__ bool pipe_tile(const ConvGemm& p, int t, int TX, int 
   return o.q0 < o.nq;
 }
 
-struct PipeCfg { int TX, total, nslot, nA, use_res; };
+// stages: a tile's K range is staged in `stages` passes of <= 2 slabs (128 input channels) through the same A buffer,
+// all accumulating into one TMEM tile: Cin = 192 / 256 / 384 ... need no more shared memory than Cin = 128
+struct PipeCfg { int TX, total, nslot, nA, use_res, stages, slabs_total, NY; };
 
 // PUNR: 16-byte loads in flight per loader thread (fp32 rows); MINB: CTAs per SM the registers are budgeted for
 template <int PUNR, int MINB>
@@ -567,8 +571,9 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
   __shared__ __align__(16) float s_bias[2][BNT];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NY = p.Cout / BNT;
+  const int NY = cfg.NY;
   const int TX = cfg.TX, total = cfg.total, nslot = cfg.nslot, nA = cfg.nA;
+  const int S = cfg.stages, SLT = cfg.slabs_total;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t a_bytes = (uint32_t)g.slabs * g.slab_bytes;
@@ -606,7 +611,8 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
       const uint8_t* tiles = reinterpret_cast<const uint8_t*>(p.tc_tiles);
       // prefetch cursor: runs up to nslot units ahead of the MMAs, across tile boundaries
       PipeTile pt;
-      int ptile = (int)blockIdx.x - (int)gridDim.x, pu = 0;
+      int ptile = (int)blockIdx.x - (int)gridDim.x;
+      int ps = 0, ptap = 0, psl = 0;                 // prefetch cursor inside the tile: stage, tap, slab of the stage
       bool pvalid = false;
       auto padvance = [&]() {
         for (ptile += (int)gridDim.x; ptile < total; ptile += (int)gridDim.x)
@@ -614,12 +620,19 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
         return false;
       };
       pvalid = padvance();
-      const uint8_t* psrc = tiles + (size_t)pt.ny * g.NU * BTILE;
+      const size_t unit_tile = (size_t)p.ntaps * SLT * BTILE;       // bytes of one N tile's weights
       auto fetch_into = [&](int slot) {
+        const uint8_t* src = tiles + (size_t)pt.ny * unit_tile + ((size_t)ptap * SLT + 2 * ps + psl) * BTILE;
         mbar_expect_tx(&full[slot], BTILE);
-        bulk_g2s(sW + (uint32_t)slot * BTILE, psrc, BTILE, &full[slot]);
-        psrc += BTILE;
-        if (++pu == g.NU) { pu = 0; pvalid = padvance(); psrc = tiles + (size_t)pt.ny * g.NU * BTILE; }
+        bulk_g2s(sW + (uint32_t)slot * BTILE, src, BTILE, &full[slot]);
+        const int nsl = SLT - 2 * ps < 2 ? SLT - 2 * ps : 2;
+        if (++psl == nsl) {
+          psl = 0;
+          if (++ptap == p.ntaps) {
+            ptap = 0;
+            if (++ps == S) { ps = 0; pvalid = padvance(); }
+          }
+        }
       };
       for (int k = 0; k < nslot && pvalid; ++k) fetch_into(k);
 
@@ -639,109 +652,120 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
         if (!pipe_tile(p, t, TX, NY, tl)) continue;
         const int b = i & 1;
         if (i >= 2) ok = mbar_wait(&acc_free[b], (uint32_t)(((i >> 1) - 1) & 1)) && ok;   // tile i-2 has left TMEM
-        ok = mbar_wait(&a_ready[ab], a_phase) && ok;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem + (uint32_t)(b * BNT);
-        uint32_t a_tap = a_lo0 + (uint32_t)ab * (a_bytes >> 4);
-        int sl = 0;
-        for (int u = 0; u < g.NU; ++u) {
-          ok = mbar_wait(&full[slot], ring_phase) && ok;
-          const uint32_t a_lo = a_tap + (uint32_t)sl * a_slab_step;
-          const uint32_t w_lo = w_lo0 + (uint32_t)slot * (BTILE >> 4);
+        for (int st = 0; st < S; ++st) {
+          const int nsl = SLT - 2 * st < 2 ? SLT - 2 * st : 2;
+          ok = mbar_wait(&a_ready[ab], a_phase) && ok;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t a_tap = a_lo0 + (uint32_t)ab * (a_bytes >> 4);
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int sl = 0; sl < nsl; ++sl) {
+              ok = mbar_wait(&full[slot], ring_phase) && ok;
+              const uint32_t a_lo = a_tap + (uint32_t)sl * a_slab_step;
+              const uint32_t w_lo = w_lo0 + (uint32_t)slot * (BTILE >> 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            umma_f16(acc, ((uint64_t)desc_hi32 << 32) | (uint64_t)(a_lo + j * 2),
-                     ((uint64_t)desc_hi32 << 32) | (uint64_t)(w_lo + j * 2), idesc, (uint32_t)((u | j) != 0));
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                       ::"r"(smem_u32(&empty[slot])) : "memory");
-          // refill the slot of the PREVIOUS unit (its MMAs finish while this unit's run)
-          if (!first_unit && pvalid) {
-            ok = mbar_wait(&empty[prev_slot], prev_phase) && ok;
-            fetch_into(prev_slot);
+              for (int j = 0; j < 4; ++j)
+                umma_f16(acc, ((uint64_t)desc_hi32 << 32) | (uint64_t)(a_lo + j * 2),
+                         ((uint64_t)desc_hi32 << 32) | (uint64_t)(w_lo + j * 2), idesc, (uint32_t)((st | tap | sl | j) != 0));
+              asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                           ::"r"(smem_u32(&empty[slot])) : "memory");
+              // refill the slot of the PREVIOUS unit (its MMAs finish while this unit's run)
+              if (!first_unit && pvalid) {
+                ok = mbar_wait(&empty[prev_slot], prev_phase) && ok;
+                fetch_into(prev_slot);
+              }
+              first_unit = false;
+              prev_slot = slot; prev_phase = ring_phase;
+              if (++slot == nslot) { slot = 0; ring_phase ^= 1u; }
+            }
+            a_tap += a_tap_step;
           }
-          first_unit = false;
-          prev_slot = slot; prev_phase = ring_phase;
-          if (++slot == nslot) { slot = 0; ring_phase ^= 1u; }
-          if (++sl == g.slabs) { sl = 0; a_tap += a_tap_step; }
+          if (st == S - 1)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(smem_u32(&acc_ready[b])) : "memory");
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                       ::"r"(smem_u32(&a_free[ab])) : "memory");
+          if (++ab == nA) { ab = 0; a_phase ^= 1u; }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     ::"r"(smem_u32(&acc_ready[b])) : "memory");
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     ::"r"(smem_u32(&a_free[ab])) : "memory");
         ++i;
-        if (++ab == nA) { ab = 0; a_phase ^= 1u; }
       }
       if (!ok && err_flag) atomicExch(err_flag, 1);
     }
   } else if (warp < 4) {
     // ===== loaders
     PipeTile tl;
-    int i = 0, ab = 0;
+    int i = 0, ab = 0, sc = 0;                       // sc: A-buffer uses so far (tile stages)
     uint32_t a_phase = 0;
     const bool h16 = p.x16 != nullptr;
-    const int cpr = h16 ? (p.Cin >> 3) : (p.Cin >> 2);            // 16-byte chunks per input row
-    const int rstep = PLD / cpr, fstep = PLD % cpr;
-    const int rr0 = tid / cpr, f0 = tid - rr0 * cpr;
     const float pre = p.pre_slope;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       if (!pipe_tile(p, t, TX, NY, tl)) continue;
       const int tbase = tl.q0 + g.lo;
-      uint8_t* abuf = sbase + (uint32_t)ab * a_bytes;
-      if (i >= nA) {                                             // the MMAs of tile i - nA have released the buffer
-        ok = mbar_wait(&a_free[ab], a_phase ^ 1u) && ok;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      if (h16) {
-        const __half* __restrict__ xh = p.x16 + (long long)tl.in0 * p.Cin;
-        const uint32_t abuf_u32 = sA + (uint32_t)ab * a_bytes;
-        int rr = rr0, f = f0;
-        while (rr < g.R) {
-          const int tt = tbase + rr, c = f * 8;
-          const uint32_t off = (uint32_t)(rr * 128 + (c & 63) * 2);
-          const bool in = (unsigned)tt < (unsigned)tl.Tin;
-          cp_async16(abuf_u32 + (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4)),
-                     in ? (const void*)(xh + (long long)tt * p.Cin + c) : (const void*)xh, in ? 16 : 0);
-          f += fstep; rr += rstep;
-          if (f >= cpr) { f -= cpr; ++rr; }
+      for (int st = 0; st < S; ++st) {
+        const int c0 = st * 128;
+        const int nch = p.Cin - c0 < 128 ? p.Cin - c0 : 128;          // input channels of this stage
+        const int cpr = h16 ? (nch >> 3) : (nch >> 2);                // 16-byte chunks per row
+        const int rstep = PLD / cpr, fstep = PLD - rstep * cpr;
+        const int rr0 = tid / cpr, f0 = tid - rr0 * cpr;
+        uint8_t* abuf = sbase + (uint32_t)ab * a_bytes;
+        if (sc >= nA) {                                              // the MMAs of use sc - nA have released the buffer
+          ok = mbar_wait(&a_free[ab], a_phase ^ 1u) && ok;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-      } else {
-        const float* __restrict__ xg = p.x + (long long)tl.in0 * p.ldx;
-        int rr = rr0, f = f0;
-        while (rr < g.R) {
-          float4 v[PUNR];
-          const int rs = rr, fs = f;
-#pragma unroll
-          for (int k = 0; k < PUNR; ++k) {
-            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int tt = tbase + rr;
-            if (rr < g.R && (unsigned)tt < (unsigned)tl.Tin)
-              v[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)tt * p.ldx + f * 4));
+        if (h16) {
+          const __half* __restrict__ xh = p.x16 + (long long)tl.in0 * p.Cin + c0;
+          const uint32_t abuf_u32 = sA + (uint32_t)ab * a_bytes;
+          int rr = rr0, f = f0;
+          while (rr < g.R) {
+            const int tt = tbase + rr, c = f * 8;
+            const uint32_t off = (uint32_t)(rr * 128 + (c & 63) * 2);
+            const bool in = (unsigned)tt < (unsigned)tl.Tin;
+            cp_async16(abuf_u32 + (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4)),
+                       in ? (const void*)(xh + (long long)tt * p.Cin + c) : (const void*)xh, in ? 16 : 0);
             f += fstep; rr += rstep;
             if (f >= cpr) { f -= cpr; ++rr; }
           }
-          int r2 = rs, f2 = fs;
+          asm volatile("cp.async.wait_all;" ::: "memory");
+        } else {
+          const float* __restrict__ xg = p.x + (long long)tl.in0 * p.ldx + c0;
+          int rr = rr0, f = f0;
+          while (rr < g.R) {
+            float4 v[PUNR];
+            const int rs = rr, fs = f;
 #pragma unroll
-          for (int k = 0; k < PUNR; ++k) {
-            if (r2 < g.R) {
-              const int c = f2 * 4;
-              const uint32_t off = (uint32_t)(r2 * 128 + (c & 63) * 2);
-              float4 a = v[k];
-              a.x = fmaxf(a.x, a.x * pre); a.y = fmaxf(a.y, a.y * pre);
-              a.z = fmaxf(a.z, a.z * pre); a.w = fmaxf(a.w, a.w * pre);
-              const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
-              uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&h01);
-              pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-              *reinterpret_cast<uint2*>(abuf + (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4))) = pk;
+            for (int k = 0; k < PUNR; ++k) {
+              v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int tt = tbase + rr;
+              if (rr < g.R && (unsigned)tt < (unsigned)tl.Tin)
+                v[k] = __ldg(reinterpret_cast<const float4*>(xg + (long long)tt * p.ldx + f * 4));
+              f += fstep; rr += rstep;
+              if (f >= cpr) { f -= cpr; ++rr; }
             }
-            f2 += fstep; r2 += rstep;
-            if (f2 >= cpr) { f2 -= cpr; ++r2; }
+            int r2 = rs, f2 = fs;
+#pragma unroll
+            for (int k = 0; k < PUNR; ++k) {
+              if (r2 < g.R) {
+                const int c = f2 * 4;
+                const uint32_t off = (uint32_t)(r2 * 128 + (c & 63) * 2);
+                float4 a = v[k];
+                a.x = fmaxf(a.x, a.x * pre); a.y = fmaxf(a.y, a.y * pre);
+                a.z = fmaxf(a.z, a.z * pre); a.w = fmaxf(a.w, a.w * pre);
+                const __half2 h01 = __floats2half2_rn(a.x, a.y), h23 = __floats2half2_rn(a.z, a.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                *reinterpret_cast<uint2*>(abuf + (uint32_t)(c >> 6) * g.slab_bytes + (off ^ (((off >> 7) & 7u) << 4))) = pk;
+              }
+              f2 += fstep; r2 += rstep;
+              if (f2 >= cpr) { f2 -= cpr; ++r2; }
+            }
           }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+        mbar_arrive(&a_ready[ab]);
+        ++sc;
+        if (++ab == nA) { ab = 0; a_phase ^= 1u; }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
-      mbar_arrive(&a_ready[ab]);
       if (cfg.use_res) {
         // residual rows of this tile -> staging halves (thread = row); the epilogue of tile i-1 must have left them
         const int q = tl.q0 + tid;
@@ -758,7 +782,6 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
         }
       }
       ++i;
-      if (++ab == nA) { ab = 0; a_phase ^= 1u; }
     }
     if (!ok && err_flag) atomicExch(err_flag, 1);
   } else {
@@ -824,6 +847,10 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
   }
 }
 
+int g_halo_bulk_max_cin = []() { const char* e = getenv("GENIE_HALO_BULK_MAX_CIN"); return e ? atoi(e) : 128; }();
+// widest layer the persistent K-staged kernel takes (V2: 256, V2ProPlus: 192 / 384 / 768-input conv_pre stays generic)
+int g_halo_pipe_max_cin = []() { const char* e = getenv("GENIE_HALO_PIPE_MAX_CIN"); return e ? atoi(e) : 384; }();
+
 int halo_pipe_mode() {
   static int mode = [] { const char* e = getenv("GENIE_HALO_PIPE"); return e ? atoi(e) : 1; }();
   return mode;
@@ -845,14 +872,19 @@ int device_sm_count() {
 // persistent pipelined form; false = the operands do not fit (caller falls back to the one-tile kernel).
 // GENIE_HALO_PIPE: 0 off, 1 (default) two CTAs per SM (single A buffer, residual from global memory: the SIMT loader /
 // epilogue work needs the warps of two CTAs), 4 one fat CTA per SM (double A buffer, staged residual; +2: no staging)
-bool launch_halo_pipe(const ConvGemm& p, const HaloGeom& g, int* err_flag, cudaStream_t s) {
+bool launch_halo_pipe(const ConvGemm& p, const HaloGeom& g_in, int* err_flag, cudaStream_t s) {
   constexpr size_t EPI4 = 4 * tc_epi::TILE_FLOATS * 4;
   const int mode = halo_pipe_mode();
   const bool fat = (mode & 4) != 0;
   const size_t budget = fat ? 220 * 1024 : 109 * 1024;
-  const size_t a_bytes = (size_t)g.slabs * g.slab_bytes;
+  HaloGeom g = g_in;
   PipeCfg cfg{};
-  cfg.use_res = (fat && p.res && !p.y16 && p.out_mul == 1 && p.out_add == 0 && p.q_extra == 0 && (p.ldr & 3) == 0 &&
+  cfg.slabs_total = g.slabs;
+  cfg.stages = (g.slabs + 1) / 2;
+  cfg.NY = (p.Cout + BNT - 1) / BNT;
+  if (g.slabs > 2) g.slabs = 2;                              // the A buffer holds one stage: <= 2 slabs
+  const size_t a_bytes = (size_t)g.slabs * g.slab_bytes;
+  cfg.use_res = (fat && p.res && p.Cout % BNT == 0 && !p.y16 && p.out_mul == 1 && p.out_add == 0 && p.q_extra == 0 && (p.ldr & 3) == 0 &&
                  (reinterpret_cast<uintptr_t>(p.res) & 15) == 0 && tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, p.Cout) &&
                  !(mode & 2)) ? 1 : 0;
   const size_t fixed = EPI4 + 1024 + (cfg.use_res ? 2 * RES_HALF : 0);
@@ -865,9 +897,8 @@ bool launch_halo_pipe(const ConvGemm& p, const HaloGeom& g, int* err_flag, cudaS
   if (cfg.nA == 0) return false;
   const size_t smem = (size_t)cfg.nA * a_bytes + (size_t)cfg.nslot * BTILE + fixed;
   const int nq = p.M + p.q_extra;
-  const int NY = p.Cout / BNT;
   cfg.TX = (nq + 127) / 128;
-  const long long total = (long long)cfg.TX * NY * p.B;
+  const long long total = (long long)cfg.TX * cfg.NY * p.B;
   if (total <= 0 || total > 0x3fffffff) return false;
   cfg.total = (int)total;
   const int grid = (int)std::min<long long>(total, (long long)device_sm_count() * (fat ? 1 : 2));
@@ -894,7 +925,8 @@ bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t 
   g.slab_bytes = (uint32_t)(((size_t)g.R * 128 + 1023) / 1024 * 1024);
   g.NU = p.ntaps * g.slabs;
   g.U = 1; g.NI = g.NU; g.slot_bytes = BTILE; g.flags = flags;
-  if (halo_pipe_mode() && launch_halo_pipe(p, g, err_flag, s)) return true;
+  if (halo_pipe_mode() && p.Cin <= g_halo_pipe_max_cin && launch_halo_pipe(p, g, err_flag, s)) return true;
+  if (p.Cin > g_halo_bulk_max_cin || p.Cout % BNT != 0) return false;     // the one-tile kernel: Cin = Cout = 128 only
   size_t smem = (size_t)g.slabs * g.slab_bytes + (size_t)NSLOT * BTILE;
   if (smem < EPI_BYTES) smem = EPI_BYTES;
   smem += 1024;
@@ -939,7 +971,6 @@ bool launch_halo(const ConvGemm& p, int flags, int* err_flag, cudaStream_t s) {
   return true;
 }
 
-int g_halo_bulk_max_cin = []() { const char* e = getenv("GENIE_HALO_BULK_MAX_CIN"); return e ? atoi(e) : 128; }();
 
 // GENIE_TC_HALO: -1 disables the path, 1 forces wide layers onto the cp.async kernel; default 0 = on
 int halo_mode() {
@@ -956,13 +987,16 @@ int halo_mode() {
 bool tc_halo_fp16_pair_ok(int C, int ntaps) {
   if (halo_mode() != 0 || ntaps < 2 || C % 8 != 0) return false;
   if (C == 16 || (C > 16 && C <= 64) || (C > 64 && C < 128)) return true;
-  return C % 64 == 0 && C >= 128 && C <= g_halo_bulk_max_cin && C % BNT == 0;   // tc_halo_bulk_kernel
+  if (C % 64 != 0 || C < 128) return false;
+  if (halo_pipe_mode() && C <= g_halo_pipe_max_cin) return true;                // tc_halo_pipe_kernel (any such C)
+  return C <= g_halo_bulk_max_cin && C % BNT == 0;                              // tc_halo_bulk_kernel
 }
 
 // fp16 [Cout][kpad] -> pre-swizzled 128 x 64 tiles [Cout/128][tap][Cin/64] for tc_halo_bulk_kernel
-bool pretile_w128_supported(int Cin, int Cout, int ntaps) { return Cin % 64 == 0 && Cin >= 128 && Cout % BNT == 0 && ntaps >= 2; }
+bool pretile_w128_supported(int Cin, int Cout, int ntaps) { return Cin % 64 == 0 && Cin >= 128 && Cout % 16 == 0 && ntaps >= 2; }
+long long pretile_w128_halves(int Cin, int Cout, int ntaps) { return (long long)((Cout + BNT - 1) / BNT) * BNT * ntaps * Cin; }
 void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s) {
-  const long long total = (long long)(Cout / BNT) * ntaps * (Cin / 64) * BNT * 8;
+  const long long total = (long long)((Cout + BNT - 1) / BNT) * ntaps * (Cin / 64) * BNT * 8;
   pretile_w128_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(hi, Cout, kpad, Cin, ntaps, tiles);
   GENIE_LAUNCHED("pretile_w128");
 }
@@ -983,8 +1017,12 @@ bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   if (p.Cin > 64 && p.Cin < 128 && p.Cout <= 128) return launch_halo<128, 1, 128>(p, mode, err_flag, s); // 96
   // wider layers: the per-tap gather of tc_gemm.cu at two CTAs per SM is faster than one halo CTA per SM
   // (measured: C=256 k=11 586 vs 1269 us, C=128 k=7 1067 vs 1194 us) unless forced for testing
-  if (p.Cin % 64 == 0 && p.Cin >= 128 && p.Cin <= g_halo_bulk_max_cin && p.tc_tiles != nullptr && p.Cout % BNT == 0 && !(mode & 1))
-    return launch_halo_bulk(p, mode, err_flag, s);
+  if (p.Cin % 64 == 0 && p.Cin >= 128 && p.tc_tiles != nullptr && !(mode & 1) &&
+      ((halo_pipe_mode() && p.Cin <= g_halo_pipe_max_cin) || (p.Cin <= g_halo_bulk_max_cin && p.Cout % BNT == 0))) {
+    if (launch_halo_bulk(p, mode, err_flag, s)) return true;
+    GENIE_CHECK(!p.x16 && !p.y16, "fp16 hand-over needs the halo conv kernel");
+    return false;
+  }
   if (p.Cin % 64 != 0 || (p.Cin > 64 && !(mode & 1))) return false;
   if (p.Cout <= 64) return launch_halo<64, 2, 128>(p, mode, err_flag, s);
   return launch_halo<128, 1, 128>(p, mode, err_flag, s);

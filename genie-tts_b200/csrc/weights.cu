@@ -192,8 +192,9 @@ struct Finalizer {
     GENIE_LAUNCHED("pack_tc");
     t.hi = hi; t.lo = lo;
     if (tap_stride == Cin && co_stride == (long long)ntaps * Cin && pretile_w128_supported(Cin, Cout, ntaps)) {
-      __half* tiles = dev_alloc<__half>(m.owner->owned, n);
-      m.weight_bytes += n * 2;
+      const long long nt = pretile_w128_halves(Cin, Cout, ntaps);     // Cout rounded up to whole 128-row tiles
+      __half* tiles = dev_alloc<__half>(m.owner->owned, nt);
+      m.weight_bytes += nt * 2;
       launch_pretile_w128(hi, Cout, t.kpad, Cin, ntaps, tiles, s);
       t.tiles = tiles;
     }
