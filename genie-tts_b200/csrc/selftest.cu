@@ -58,7 +58,7 @@ void tc_selftest(int M, int Cin, int Cout, int ntaps, int dil, int mode, int exa
   p.y = y0;
   launch_conv_gemm(p, s);
   __half* tiles = nullptr;
-  if (pretile_w128_supported(Cin, Cout, ntaps) && kpad == K) {
+  if (pretile_w128_supported(Cin, Cout, ntaps)) {
     GENIE_CUDA(cudaMalloc(&tiles, (size_t)pretile_w128_halves(Cin, Cout, ntaps) * 2));
     launch_pretile_w128(hi, Cout, kpad, Cin, ntaps, tiles, s);
     p.tc_tiles = tiles;

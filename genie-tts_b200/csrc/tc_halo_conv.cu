@@ -323,7 +323,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 __global__ void pretile_w128_kernel(const __half* __restrict__ hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles) {
-  const int slabs = Cin / 64;
+  const int slabs = (Cin + 63) / 64;
   const long long total = (long long)((Cout + BNT - 1) / BNT) * ntaps * slabs * BNT * 8;     // 16-byte chunks
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -331,7 +331,7 @@ __global__ void pretile_w128_kernel(const __half* __restrict__ hi, int Cout, int
   const long long unit = i / (BNT * 8);
   const int sl = (int)(unit % slabs), tap = (int)((unit / slabs) % ntaps), nt = (int)(unit / ((long long)slabs * ntaps));
   uint4 v = make_uint4(0u, 0u, 0u, 0u);                                    // rows past Cout: zero (last N tile padded)
-  if (nt * BNT + n < Cout)
+  if (nt * BNT + n < Cout && sl * 64 + c8 * 8 < Cin)                       // channels past Cin: zero (last slab padded)
     v = *reinterpret_cast<const uint4*>(hi + (long long)(nt * BNT + n) * kpad + tap * Cin + sl * 64 + c8 * 8);
   const uint32_t off = (uint32_t)(n * 128 + c8 * 16);
   *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tiles) + unit * BTILE + (off ^ (((off >> 7) & 7u) << 4))) = v;
@@ -693,6 +693,13 @@ __global__ void __launch_bounds__(BTHR, MINB) tc_halo_pipe_kernel(ConvGemm p, Ha
     }
   } else if (warp < 4) {
     // ===== loaders
+    if (p.Cin & 63) {
+      // channel count padded to whole 64-channel slabs (V2ProPlus: 96): the pad columns are never written by the
+      // staging loops and must read as zero (their weights are zero, but 0 x stale NaN is not)
+      for (uint32_t o = (uint32_t)tid * 16u; o < a_bytes * (uint32_t)nA; o += PLD * 16u)
+        *reinterpret_cast<uint4*>(sbase + o) = make_uint4(0u, 0u, 0u, 0u);
+      asm volatile("bar.sync 2, 128;" ::: "memory");        // the four loader warps only
+    }
     PipeTile tl;
     int i = 0, ab = 0, sc = 0;                       // sc: A-buffer uses so far (tile stages)
     uint32_t a_phase = 0;
@@ -921,7 +928,7 @@ bool launch_halo_bulk(const ConvGemm& p, int flags, int* err_flag, cudaStream_t 
   g.lo = s_first < s_last ? s_first : s_last;
   const int hi = s_first < s_last ? s_last : s_first;
   g.R = 128 + (hi - g.lo);
-  g.slabs = p.Cin / 64; g.cpad = p.Cin;
+  g.slabs = (p.Cin + 63) / 64; g.cpad = g.slabs * 64;
   g.slab_bytes = (uint32_t)(((size_t)g.R * 128 + 1023) / 1024 * 1024);
   g.NU = p.ntaps * g.slabs;
   g.U = 1; g.NI = g.NU; g.slot_bytes = BTILE; g.flags = flags;
@@ -993,10 +1000,12 @@ bool tc_halo_fp16_pair_ok(int C, int ntaps) {
 }
 
 // fp16 [Cout][kpad] -> pre-swizzled 128 x 64 tiles [Cout/128][tap][Cin/64] for tc_halo_bulk_kernel
-bool pretile_w128_supported(int Cin, int Cout, int ntaps) { return Cin % 64 == 0 && Cin >= 128 && Cout % 16 == 0 && ntaps >= 2; }
-long long pretile_w128_halves(int Cin, int Cout, int ntaps) { return (long long)((Cout + BNT - 1) / BNT) * BNT * ntaps * Cin; }
+bool pretile_w128_supported(int Cin, int Cout, int ntaps) { return Cin % 8 == 0 && Cin > 64 && Cout % 16 == 0 && ntaps >= 2; }
+long long pretile_w128_halves(int Cin, int Cout, int ntaps) {
+  return (long long)((Cout + BNT - 1) / BNT) * BNT * ntaps * ((Cin + 63) / 64) * 64;
+}
 void launch_pretile_w128(const __half* hi, int Cout, int kpad, int Cin, int ntaps, __half* tiles, cudaStream_t s) {
-  const long long total = (long long)((Cout + BNT - 1) / BNT) * ntaps * (Cin / 64) * BNT * 8;
+  const long long total = (long long)((Cout + BNT - 1) / BNT) * ntaps * ((Cin + 63) / 64) * BNT * 8;
   pretile_w128_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(hi, Cout, kpad, Cin, ntaps, tiles);
   GENIE_LAUNCHED("pretile_w128");
 }
@@ -1014,6 +1023,11 @@ bool try_launch_tc_halo_conv(const ConvGemm& p, int* err_flag, cudaStream_t s) {
   if (p.Cin == 16 && p.Cout <= 16) return launch_halo<16, 4, 32>(p, mode, err_flag, s);
   if (p.Cin > 16 && p.Cin <= 32 && p.Cout <= 32) return launch_halo<32, 4, 64>(p, mode, err_flag, s);   // 24 (V2ProPlus), 32
   if (p.Cin > 32 && p.Cin < 64 && p.Cout <= 64) return launch_halo<64, 2, 128>(p, mode, err_flag, s);    // 48
+  // 96 (V2ProPlus): as a two-slab layer with zero pad columns on the persistent kernel when its weights are pre-tiled
+  static const bool padded_env = [] { const char* e = getenv("GENIE_HALO_PIPE_PADDED"); return !(e && e[0] == '0'); }();
+  if (padded_env && p.Cin > 64 && p.Cin < 128 && p.tc_tiles != nullptr && halo_pipe_mode() && !(mode & 1) &&
+      launch_halo_bulk(p, mode, err_flag, s))
+    return true;
   if (p.Cin > 64 && p.Cin < 128 && p.Cout <= 128) return launch_halo<128, 1, 128>(p, mode, err_flag, s); // 96
   // wider layers: the per-tap gather of tc_gemm.cu at two CTAs per SM is faster than one halo CTA per SM
   // (measured: C=256 k=11 586 vs 1269 us, C=128 k=7 1067 vs 1194 us) unless forced for testing
