@@ -189,7 +189,7 @@ def _serve_devices(host: str, port: int, devices) -> None:
 def start_server_per_gpu(host: str = "127.0.0.1", base_port: int = 8000, devices=None, block: bool = True):
     """One server PROCESS per GPU on ports base_port, base_port + 1, ... (put any HTTP balancer in front).  One Python
     process tops out near 1500 requests/s on its interpreter lock - 8 GPUs behind one process reach 4.9 k audio-s/s,
-    behind 8 processes 14.7 k (profiles/r02/config5_load_8gpu*.json).  Characters and reference audio are
+    behind 8 processes 15.2 k (profiles/r02/config5_load_8gpu*.json).  Characters and reference audio are
     per process: send /load_character and /set_reference_audio to every port."""
     import multiprocessing as mp
     from . import _native as N
