@@ -16,6 +16,8 @@ namespace tc_epi {
 
 constexpr int TILE_LD = 36;
 constexpr int TILE_FLOATS = 32 * TILE_LD;           // per warp
+constexpr int TILE_LD16 = 20;                       // 16-column chunks: 80-byte rows (also conflict free), 2.5 KB per warp
+constexpr int TILE_FLOATS16 = 32 * TILE_LD16;
 
 struct Args {
   float* y; const float* res; const float* acc;     // acc = y when accumulating, else null
@@ -42,6 +44,7 @@ template <int CW>
 __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile, const float* sbias, const int* rows,
                                             long long out0, int ncol0, const Args& a, int lane) {
   static_assert(CW == 16 || CW == 32, "chunk width");
+  constexpr int LD = CW == 16 ? TILE_LD16 : TILE_LD;
 #pragma unroll
   for (int k = 0; k < CW / 4; ++k) {
     float4 o;
@@ -54,7 +57,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
       o.z = fmaxf(o.z, o.z * a.slope); o.w = fmaxf(o.w, o.w * a.slope);
     }
     o.x *= a.oscale; o.y *= a.oscale; o.z *= a.oscale; o.w *= a.oscale;
-    *reinterpret_cast<float4*>(tile + lane * TILE_LD + 4 * k) = o;
+    *reinterpret_cast<float4*>(tile + lane * LD + 4 * k) = o;
   }
   __syncwarp();
   if (a.y16) {
@@ -66,7 +69,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
       for (int i = 0; i < NP; ++i) {
         const int to = rows[i * RPP + rsub];
         if (to < 0) continue;
-        const float4 t = *reinterpret_cast<const float4*>(tile + (i * RPP + rsub) * TILE_LD + c4 * 4);
+        const float4 t = *reinterpret_cast<const float4*>(tile + (i * RPP + rsub) * LD + c4 * 4);
         const __half2 h01 = __floats2half2_rn(t.x, t.y), h23 = __floats2half2_rn(t.z, t.w);
         uint2 pk;
         pk.x = *reinterpret_cast<const uint32_t*>(&h01);
@@ -112,7 +115,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       if (to[i] >= 0) {
-        float4 t = *reinterpret_cast<const float4*>(tile + (i * RPP + rsub) * TILE_LD + c4 * 4);
+        float4 t = *reinterpret_cast<const float4*>(tile + (i * RPP + rsub) * LD + c4 * 4);
         t.x += add[i].x; t.y += add[i].y; t.z += add[i].z; t.w += add[i].w;
         *reinterpret_cast<float4*>(a.y + (out0 + to[i]) * a.ldy + n) = t;
       }
@@ -124,7 +127,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], float* tile
       for (int r = 0; r < 32; ++r) {
         const int to = rows[r];
         if (to < 0) continue;                       // warp-uniform
-        float x = tile[r * TILE_LD + lane];
+        float x = tile[r * LD + lane];
         if (a.res) x += a.res[(out0 + to) * a.ldr + n];
         if (a.acc) x += a.acc[(out0 + to) * a.ldy + n];
         a.y[(out0 + to) * a.ldy + n] = x;

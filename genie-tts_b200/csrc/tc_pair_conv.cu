@@ -60,7 +60,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 
 template <int C, int MT>
-__global__ void __launch_bounds__(NTHR, C >= 64 ? 1 : 2) tc_pair_conv_kernel(ConvGemm p, const __half* __restrict__ w1,
+__global__ void __launch_bounds__(NTHR, C >= 64 ? 1 : (C == 16 ? 4 : 2)) tc_pair_conv_kernel(ConvGemm p, const __half* __restrict__ w1,
                                                                              const float* __restrict__ bias1, int kpad1,
                                                                              PairGeom g, int* err_flag) {
   constexpr int ROWS = MT * 128;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(NTHR, C >= 64 ? 1 : 2) tc_pair_conv_kernel(Con
   ea.act = ACT_NONE; ea.slope = 0.f; ea.oscale = p.out_scale;
   ea.Cout = C;
   ea.vec = tc_epi::vec_ok(p.y, p.ldy, p.res, p.ldr, C);
-  float* tile = reinterpret_cast<float*>(sbase) + warp * tc_epi::TILE_FLOATS;
+  float* tile = reinterpret_cast<float*>(sbase) + warp * (C >= 32 ? tc_epi::TILE_FLOATS : tc_epi::TILE_FLOATS16);
   if (ok) {
     const int rq = (warp & 3) * 32;
     for (int mt = warp >> 2; mt < MT; mt += 2) {
@@ -263,7 +263,9 @@ void launch_pair(const ConvGemm& p, const __half* w1, const float* bias1, int kp
   g.k = p.ntaps; g.d1 = d1; g.p1 = d1 * (g.k - 1) / 2; g.p2 = (g.k - 1) / 2;
   g.T = ROWS - 2 * g.p2; g.R1 = ROWS + 2 * g.p1;
   auto up = [](size_t v) { return (uint32_t)((v + 1023) / 1024 * 1024); };
-  const size_t epi = (size_t)(NTHR / 32) * tc_epi::TILE_FLOATS * 4;
+  // epilogue-2 transpose tiles alias the x tile; 16-column chunks (C = 16) need 2.5 KB per warp, which is what lets
+  // four CTAs of the C = 16 stage share an SM (its tiles are a chain of latencies: 1.3x from the fourth CTA)
+  const size_t epi = (size_t)(NTHR / 32) * (C >= 32 ? tc_epi::TILE_FLOATS : tc_epi::TILE_FLOATS16) * 4;
   g.x_bytes = up(std::max((size_t)g.R1 * 2 * C, epi));
   g.i_bytes = up((size_t)(ROWS + IPAD) * 2 * C);
   g.w_bytes = up((size_t)g.k * C * 2 * C);
